@@ -1,0 +1,223 @@
+// extern "C" surface of libfdfd_b200.so (see include/fdfd_b200.h).
+#include <cstdarg>
+#include <cstring>
+
+#include "comm.cuh"
+#include "helm2d.cuh"
+#include "krylov.cuh"
+
+namespace fdfd {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %s (%s) at %s:%d in %s", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+    cudaGetLastError();  // clear the sticky flag for non-fatal errors
+    return FDFD_ERR_CUDA;
+}
+
+}  // namespace fdfd
+
+using namespace fdfd;
+
+struct fdfd_helm2d { Helm2D op; };
+struct fdfd_comm { Comm* c; };
+
+extern "C" const char* fdfd_last_error(void) { return g_err; }
+extern "C" int fdfd_version(void) { return 100; }
+extern "C" int fdfd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int fdfd_comm_unique_id(void* id128) { return comm_unique_id(id128); }
+extern "C" int fdfd_comm_create(fdfd_comm_t** out, int nranks, int rank, const void* id128) {
+    FDFD_CHECK_ARG(out, "null out");
+    Comm* c = nullptr;
+    FDFD_TRY(comm_create(&c, nranks, rank, id128));
+    *out = new fdfd_comm{c};
+    return FDFD_OK;
+}
+extern "C" void fdfd_comm_destroy(fdfd_comm_t* c) {
+    if (!c) return;
+    comm_destroy(c->c);
+    delete c;
+}
+
+extern "C" int fdfd_helm2d_create(fdfd_helm2d_t** out, int dtype, int pol, int Nx, int Ny_global,
+                                  int j0, int Ny_local, int bcx, int bcy, const double phase[4],
+                                  double sx, double sy, const void* ca, const void* cb,
+                                  const void* cd, fdfd_comm_t* comm, void* stream) {
+    FDFD_CHECK_ARG(out, "null out");
+    FDFD_CHECK_ARG(dtype == FDFD_C128 || dtype == FDFD_C64, "dtype must be FDFD_C128 or FDFD_C64");
+    FDFD_CHECK_ARG(pol == FDFD_POL_TE || pol == FDFD_POL_TM, "pol must be TE or TM");
+    FDFD_CHECK_ARG(Nx >= 2 && Ny_global >= 2, "matrix-free operator needs Nx, Ny >= 2");
+    FDFD_CHECK_ARG(j0 >= 0 && Ny_local >= 1 && j0 + Ny_local <= Ny_global, "bad slab extent");
+    FDFD_CHECK_ARG((bcx == 0 || bcx == 1) && (bcy == 0 || bcy == 1), "BC must be 0 or 1");
+    FDFD_CHECK_ARG(ca && cb, "null coefficient array");
+    FDFD_CHECK_ARG((int64_t)Nx * Ny_local < ((int64_t)1 << 40), "slab too large");
+    const bool sharded = Ny_local != Ny_global;
+    FDFD_CHECK_ARG(!sharded || (comm && comm->c && comm->c->nranks > 1), "sharded operator needs a communicator");
+    if (fdfd_device_count() <= 0) { set_error("no CUDA device visible: fdfd_b200 has no CPU path"); return FDFD_ERR_CUDA; }
+    fdfd_helm2d* h = new fdfd_helm2d();
+    Helm2D& op = h->op;
+    memset(&op, 0, sizeof(op));
+    op.dtype = dtype; op.pol = pol; op.Nx = Nx; op.Ny_global = Ny_global; op.j0 = j0; op.Ny = Ny_local;
+    op.bcx = bcx; op.bcy = bcy;
+    if (phase) memcpy(op.phase, phase, sizeof(op.phase));
+    else { op.phase[0] = 1; op.phase[1] = 0; op.phase[2] = 1; op.phase[3] = 0; }
+    op.sx = sx; op.sy = sy; op.ca = ca; op.cb = cb; op.cd = cd;
+    op.comm = comm ? comm->c : nullptr;
+    op.variant = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sharded) {
+        const size_t rb = (size_t)Nx * op.elem();
+        cudaError_t e;
+        if ((e = cudaMalloc(&op.halo_south, rb)) != cudaSuccess || (e = cudaMalloc(&op.halo_north, rb)) != cudaSuccess ||
+            (e = cudaMalloc(&op.cb_ghost_buf, rb)) != cudaSuccess) {
+            fdfd_helm2d_destroy(h);
+            return cuda_fail(e, "cudaMalloc(halo)", __FILE__, __LINE__);
+        }
+        cudaMemsetAsync(op.halo_south, 0, rb, st);
+        cudaMemsetAsync(op.halo_north, 0, rb, st);
+        // static coefficient ghost: TE needs cb row j0-1 (from the south rank's last row),
+        // TM needs cb row j0+Ny (from the north rank's first row)
+        const int P = op.comm->nranks, r = op.comm->rank;
+        const bool per = bcy == FDFD_BC_BLOCH;
+        const int south = r > 0 ? r - 1 : (per ? P - 1 : -1);
+        const int north = r < P - 1 ? r + 1 : (per ? 0 : -1);
+        int s;
+        if (pol == FDFD_POL_TE)
+            s = comm_sendrecv(op.comm, (const char*)cb + (size_t)(Ny_local - 1) * rb, north, op.cb_ghost_buf, south, rb, st);
+        else
+            s = comm_sendrecv(op.comm, cb, south, op.cb_ghost_buf, north, rb, st);
+        if (s != FDFD_OK) { fdfd_helm2d_destroy(h); return s; }
+    }
+    *out = h;
+    return FDFD_OK;
+}
+
+extern "C" void fdfd_helm2d_destroy(fdfd_helm2d_t* h) {
+    if (!h) return;
+    cudaFree(h->op.halo_south); cudaFree(h->op.halo_north); cudaFree(h->op.cb_ghost_buf);
+    cudaFree(h->op.h_x); cudaFree(h->op.h_y);
+    delete h;
+}
+
+extern "C" int fdfd_helm2d_apply(fdfd_helm2d_t* h, const void* x, void* y, void* stream) {
+    FDFD_CHECK_ARG(h && x && y, "null pointer");
+    FDFD_CHECK_ARG(x != y, "apply cannot run in place");
+    return helm2d_apply(h->op, APPLY_AX, x, y, nullptr, 0.0, (cudaStream_t)stream);
+}
+
+static int ensure_host_scratch(Helm2D& op) {
+    const size_t bytes = (size_t)op.n_local() * op.elem();
+    if (!op.h_x) FDFD_CUDA(cudaMalloc(&op.h_x, bytes));
+    if (!op.h_y) FDFD_CUDA(cudaMalloc(&op.h_y, bytes));
+    return FDFD_OK;
+}
+
+extern "C" int fdfd_helm2d_apply_host(fdfd_helm2d_t* h, const void* x_host, void* y_host) {
+    FDFD_CHECK_ARG(h && x_host && y_host, "null pointer");
+    Helm2D& op = h->op;
+    FDFD_CHECK_ARG(op.Ny == op.Ny_global, "host-buffer apply is for the unsharded operator");
+    FDFD_TRY(ensure_host_scratch(op));
+    const size_t bytes = (size_t)op.n_local() * op.elem();
+    FDFD_CUDA(cudaMemcpyAsync(op.h_x, x_host, bytes, cudaMemcpyHostToDevice, 0));
+    FDFD_TRY(helm2d_apply(op, APPLY_AX, op.h_x, op.h_y, nullptr, 0.0, 0));
+    FDFD_CUDA(cudaMemcpyAsync(y_host, op.h_y, bytes, cudaMemcpyDeviceToHost, 0));
+    FDFD_CUDA(cudaStreamSynchronize(0));
+    return FDFD_OK;
+}
+
+extern "C" int64_t fdfd_helm2d_bytes_per_apply(const fdfd_helm2d_t* h) {
+    if (!h) return 0;
+    const Helm2D& op = h->op;
+    const int arrays = 4 + (op.cd ? 1 : 0);   // x, y, ca, cb (+ cd)
+    return (int64_t)arrays * op.n_local() * (int64_t)op.elem();
+}
+
+extern "C" int fdfd_helm2d_set_variant(fdfd_helm2d_t* h, int variant) {
+    FDFD_CHECK_ARG(h, "null operator");
+    h->op.variant = variant;
+    return FDFD_OK;
+}
+
+extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->method = FDFD_KRYLOV_BICGSTAB;
+    o->precond = FDFD_PRECOND_JACOBI;
+    o->rtol = 1e-8;
+    o->maxit = 100000;
+    o->restart = 30;
+    o->mg_levels = 0;
+    o->mg_pre = 1; o->mg_post = 1;
+    o->mg_shift_re = 1.0; o->mg_shift_im = 0.5;
+    o->mg_omega = 0.8;
+    o->mg_cycle = 1;
+    o->mg_coarse_its = 8;
+    o->verbose = 0;
+    o->line_x_lo = o->line_x_hi = o->line_y_lo = o->line_y_hi = 0;
+    o->mg_wfrom = 3;
+    o->mg_min_n = 32;
+    o->reorth = 1;
+}
+
+extern "C" int fdfd_krylov_solve(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts, const void* b,
+                                 void* x, double* info_out, void* stream) {
+    FDFD_CHECK_ARG(h && opts && b && x, "null pointer");
+    FDFD_CHECK_ARG(opts->rtol > 0 && opts->maxit >= 0, "bad tolerance / maxit");
+    Helm2D& A = h->op;
+    cudaStream_t st = (cudaStream_t)stream;
+    Precond* M = nullptr;
+    int s = FDFD_OK;
+    if (opts->precond == FDFD_PRECOND_JACOBI) s = make_jacobi_precond(A, &M, st);
+    else if (opts->precond == FDFD_PRECOND_MG) s = make_mg_precond(A, *opts, &M, st);
+    else if (opts->precond != FDFD_PRECOND_NONE) { set_error("unknown preconditioner %d", opts->precond); s = FDFD_ERR_ARG; }
+    if (s != FDFD_OK) return s;
+    SolveInfo info;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    if (opts->method == FDFD_KRYLOV_BICGSTAB) s = bicgstab_solve(A, M, *opts, b, x, info, st);
+    else if (opts->method == FDFD_KRYLOV_FGMRES) s = fgmres_solve(A, M, *opts, b, x, info, st);
+    else { set_error("unknown Krylov method %d", opts->method); s = FDFD_ERR_ARG; }
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    info.seconds = ms * 1e-3;
+    delete M;
+    if (info_out) {
+        info_out[0] = info.iterations; info_out[1] = info.relres; info_out[2] = (double)info.op_applies;
+        info_out[3] = (double)info.precond_applies; info_out[4] = info.seconds; info_out[5] = info.breakdowns;
+        info_out[6] = 0; info_out[7] = 0;
+    }
+    return s;
+}
+
+extern "C" int fdfd_krylov_solve_host(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts,
+                                      const void* b_host, void* x_host, double* info) {
+    FDFD_CHECK_ARG(h && opts && b_host && x_host, "null pointer");
+    Helm2D& op = h->op;
+    FDFD_CHECK_ARG(op.Ny == op.Ny_global, "host-buffer solve is for the unsharded operator");
+    FDFD_TRY(ensure_host_scratch(op));
+    const size_t bytes = (size_t)op.n_local() * op.elem();
+    FDFD_CUDA(cudaMemcpyAsync(op.h_x, b_host, bytes, cudaMemcpyHostToDevice, 0));
+    FDFD_CUDA(cudaMemcpyAsync(op.h_y, x_host, bytes, cudaMemcpyHostToDevice, 0));
+    int s = fdfd_krylov_solve(h, opts, op.h_x, op.h_y, info, nullptr);
+    if (s != FDFD_OK && s != FDFD_ERR_NOCONV) return s;
+    FDFD_CUDA(cudaMemcpyAsync(x_host, op.h_y, bytes, cudaMemcpyDeviceToHost, 0));
+    FDFD_CUDA(cudaStreamSynchronize(0));
+    return s;
+}

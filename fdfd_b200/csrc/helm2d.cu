@@ -1,0 +1,242 @@
+// K2 — matrix-free 5-point complex Helmholtz / curl-curl stencil (see helm2d.cuh).
+//
+// Operator (unit-spacing yeeder2d operators, reference Scattering/yee_derivative.py:44-72,
+// composed as in Scattering_Solver_2D.py:176-188 / Band_Diagram_Solver.py:312,319):
+//   TE-type  y = sx*DHX ca DEX x + sy*DHY cb DEY x + shift*cd x
+//            flux on the face between i and i+1 carries ca_i ; far wall: x_N = 0 ;
+//            near wall: no flux.
+//   TM-type  y = sx*DEX ca DHX x + sy*DEY cb DHY x + shift*cd x
+//            flux on the face between i-1 and i carries ca_i ; near wall: x_-1 = 0 ;
+//            far wall: no flux.
+//   Bloch axis: x_N = ph*x_0, x_-1 = conj(ph)*x_{N-1}, coefficients periodic, and the centre
+//            weight of the wrapped face is |ph|^2 (exactly what -D^H c D gives).
+//
+// Kernel shape: bandwidth bound (80 B/pt in complex128: x, y, ca, cb, cd once each).  One
+// thread owns one grid column of a (blockDim.x wide, rows_per_cta tall) tile and marches in y
+// with a three-row register window, so every x row and every cb row is fetched from L2/HBM
+// once per tile (+1 halo row); the x-neighbours and the second ca value come from L1 (the
+// row was just loaded by the adjacent lanes).  All global accesses are 16-byte, unit-stride
+// across the warp.
+#include "helm2d.cuh"
+#include "comm.cuh"
+
+namespace fdfd {
+
+template <typename C, bool TM, int MODE>
+__global__ void __launch_bounds__(256) helm2d_march_kernel(HelmArgs<C> a) {
+    using R = typename real_of<C>::type;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.Nx) return;
+    const int Nx = a.Nx, Ny = a.Ny;
+    const int jb = blockIdx.y * a.rows_per_cta;
+    const int je = min(jb + a.rows_per_cta, Ny);
+    if (jb >= je) return;
+
+    // x-direction neighbour bookkeeping (column constants)
+    const bool west_edge = (i == 0), east_edge = (i == Nx - 1);
+    const int iw = west_edge ? Nx - 1 : i - 1;
+    const int ie = east_edge ? 0 : i + 1;
+    // multipliers that realise wall / Bloch behaviour on the two x faces
+    R w_on = 1, e_on = 1;      // face present?
+    R w_c2 = 1, e_c2 = 1;      // centre weight on that face
+    bool w_ph = false, e_ph = false;
+    if (west_edge) {
+        if (a.bcx) { w_ph = true; if (!TM) w_c2 = a.phx2; }
+        else if (!TM) w_on = 0;          // TE: no flux through the near wall
+    }
+    if (east_edge) {
+        if (a.bcx) { e_ph = true; if (TM) e_c2 = a.phx2; }
+        else if (TM) e_on = 0;           // TM: no flux through the far wall
+    }
+    const bool west_wall_val = west_edge && !a.bcx;   // x_-1 = 0
+    const bool east_wall_val = east_edge && !a.bcx;   // x_N  = 0
+
+    const C* xcol = a.x + i;
+    const C* cbcol = a.cb + i;
+
+    // ---- prime the register window --------------------------------------------------------
+    C xs, xc, cb_lo;  // cb_lo: TE -> cb[j-1] ; TM -> cb[j]
+    if (jb > 0) {
+        xs = xcol[(int64_t)(jb - 1) * Nx];
+    } else if (a.x_south) {
+        xs = a.x_south[i];
+        if (a.south_wrap) xs = cmulc(a.phy, xs);      // conj(phy) * x_{Ny-1}
+    } else {
+        xs = czero<C>();
+    }
+    xc = xcol[(int64_t)jb * Nx];
+    if (!TM) {
+        if (jb > 0) cb_lo = ld_stream(cbcol + (int64_t)(jb - 1) * Nx);
+        else if (a.cb_ghost) cb_lo = a.cb_ghost[i];
+        else cb_lo = czero<C>();                      // TE: no flux through the near wall
+    } else {
+        cb_lo = ld_stream(cbcol + (int64_t)jb * Nx);
+    }
+
+    for (int j = jb; j < je; ++j) {
+        const int64_t row = (int64_t)j * Nx;
+        // north value and the second cb of this row
+        C xn, cb_hi;
+        R n_on = 1, s_c2 = 1, n_c2 = 1;
+        if (j + 1 < Ny) {
+            xn = xcol[row + Nx];
+            cb_hi = TM ? ld_stream(cbcol + row + Nx) : ld_stream(cbcol + row);
+        } else {
+            if (a.x_north) {
+                xn = a.x_north[i];
+                if (a.north_wrap) { xn = cmul(a.phy, xn); if (TM) n_c2 = a.phy2; }
+            } else {
+                xn = czero<C>();
+            }
+            if (TM) {
+                if (a.cb_ghost) cb_hi = a.cb_ghost[i];
+                else { cb_hi = czero<C>(); n_on = 0; }   // TM: no flux through the far wall
+            } else {
+                cb_hi = ld_stream(cbcol + row);
+            }
+        }
+        if (!TM && j == 0 && a.south_wrap) s_c2 = a.phy2;
+
+        // x neighbours of the centre row (L1 hits) and the two ca values
+        C xw = a.x[row + iw], xe = a.x[row + ie];
+        if (w_ph) xw = cmulc(a.phx, xw);
+        if (e_ph) xe = cmul(a.phx, xe);
+        if (west_wall_val) xw = czero<C>();
+        if (east_wall_val) xe = czero<C>();
+        C ca_w, ca_e;
+        if (TM) { ca_w = a.ca[row + i]; ca_e = a.ca[row + ie]; }
+        else    { ca_w = a.ca[row + iw]; ca_e = a.ca[row + i]; }
+
+        // fluxes
+        C fe = cmul(ca_e, csub(xe, cscale(e_c2, xc)));
+        C fw = cmul(ca_w, csub(cscale(w_c2, xc), xw));
+        C tx = csub(cscale(e_on, fe), cscale(w_on, fw));
+        C c_s = TM ? cb_lo : cb_lo;      // south face coefficient: TE cb[j-1], TM cb[j]
+        C c_n = cb_hi;                   // north face coefficient: TE cb[j],   TM cb[j+1]
+        C fn = cmul(c_n, csub(xn, cscale(n_c2, xc)));
+        C fs = cmul(c_s, csub(cscale(s_c2, xc), xs));
+        C ty = csub(cscale(n_on, fn), fs);
+        C ax = cadd(cscale(a.sx, tx), cscale(a.sy, ty));
+        C dterm = czero<C>();
+        if (a.cd) {
+            dterm = cmul(a.shift, ld_stream(a.cd + row + i));
+            ax = cfma(dterm, xc, ax);
+        }
+
+        C out;
+        if (MODE == APPLY_AX) {
+            out = ax;
+        } else if (MODE == APPLY_RESID) {
+            out = csub(ld_stream(a.b + row + i), ax);
+        } else {
+            // diagonal of A at this point
+            C dg = cadd(cscale(-a.sx, cadd(cscale(e_on * e_c2, ca_e), cscale(w_on * w_c2, ca_w))),
+                        cscale(-a.sy, cadd(cscale(n_on * n_c2, c_n), cscale(s_c2, c_s))));
+            dg = cadd(dg, dterm);
+            if (MODE == APPLY_JACOBI) {
+                C r = csub(ld_stream(a.b + row + i), ax);
+                out = cadd(xc, cscale(a.omega, cdiv(r, dg)));
+            } else if (MODE == APPLY_DINV) {
+                out = cdiv(mk<C>(1, 0), dg);
+            } else {
+                out = cdiv(ax, dg);
+            }
+        }
+        a.y[row + i] = out;
+
+        // rotate the window
+        xs = xc; xc = xn;
+        cb_lo = TM ? cb_hi : cb_hi;
+    }
+}
+
+struct Variant { int bx, ry; };
+static const Variant kVariants[] = {
+    {128, 32}, {128, 16}, {128, 64}, {256, 32}, {256, 16}, {64, 32}, {128, 8}, {256, 64}, {128, 128},
+};
+static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+
+template <typename C>
+int helm2d_launch(const Helm2D& op, int mode, const C* x, C* y, const C* b, const C* ca,
+                  const C* cb, const C* cd, double shift_re, double shift_im, double omega,
+                  cudaStream_t stream) {
+    using R = typename real_of<C>::type;
+    HelmArgs<C> a;
+    a.x = x; a.y = y; a.b = b; a.ca = ca; a.cb = cb; a.cd = cd;
+    a.Nx = op.Nx; a.Ny = op.Ny;
+    a.bcx = (op.bcx == FDFD_BC_BLOCH && op.Nx > 0) ? 1 : 0;
+    a.sx = (R)op.sx; a.sy = (R)op.sy;
+    a.phx = mk<C>((R)op.phase[0], (R)op.phase[1]);
+    a.phy = mk<C>((R)op.phase[2], (R)op.phase[3]);
+    a.phx2 = (R)(op.phase[0] * op.phase[0] + op.phase[1] * op.phase[1]);
+    a.phy2 = (R)(op.phase[2] * op.phase[2] + op.phase[3] * op.phase[3]);
+    a.shift = mk<C>((R)shift_re, (R)shift_im);
+    a.omega = (R)omega;
+    // ghost rows
+    const bool first = op.j0 == 0, last = op.j0 + op.Ny == op.Ny_global;
+    const bool sharded = op.Ny != op.Ny_global;
+    a.x_south = nullptr; a.x_north = nullptr; a.cb_ghost = nullptr;
+    a.south_wrap = a.north_wrap = 0;
+    const bool TM = op.pol == FDFD_POL_TM;
+    if (!sharded) {
+        if (op.bcy == FDFD_BC_BLOCH) {
+            a.x_south = x + (int64_t)(op.Ny - 1) * op.Nx;
+            a.x_north = x;
+            a.south_wrap = a.north_wrap = 1;
+            a.cb_ghost = TM ? cb : cb + (int64_t)(op.Ny - 1) * op.Nx;
+        }
+    } else {
+        const bool bloch_y = op.bcy == FDFD_BC_BLOCH;
+        if (!first || bloch_y) { a.x_south = (const C*)op.halo_south; a.south_wrap = first && bloch_y; }
+        if (!last || bloch_y) { a.x_north = (const C*)op.halo_north; a.north_wrap = last && bloch_y; }
+        const bool need = TM ? (!last || op.bcy == FDFD_BC_BLOCH) : (!first || op.bcy == FDFD_BC_BLOCH);
+        if (need) a.cb_ghost = (const C*)op.cb_ghost_buf;
+    }
+    const Variant v = kVariants[(op.variant >= 0 && op.variant < kNumVariants) ? op.variant : 0];
+    int bx = v.bx;
+    while (bx > 32 && bx / 2 >= op.Nx) bx /= 2;
+    a.rows_per_cta = v.ry;
+    dim3 grid(ceil_div(op.Nx, bx), ceil_div(op.Ny, v.ry));
+    FDFD_CHECK_ARG(grid.y <= 65535, "too many row tiles for one launch");
+#define LAUNCH(TMv, MODEv) helm2d_march_kernel<C, TMv, MODEv><<<grid, bx, 0, stream>>>(a)
+#define LAUNCH_MODE(MODEv) do { if (TM) LAUNCH(true, MODEv); else LAUNCH(false, MODEv); } while (0)
+    switch (mode) {
+        case APPLY_AX: LAUNCH_MODE(APPLY_AX); break;
+        case APPLY_RESID: LAUNCH_MODE(APPLY_RESID); break;
+        case APPLY_JACOBI: LAUNCH_MODE(APPLY_JACOBI); break;
+        case APPLY_DINV_AX: LAUNCH_MODE(APPLY_DINV_AX); break;
+        case APPLY_DINV: LAUNCH_MODE(APPLY_DINV); break;
+        default: set_error("bad apply mode %d", mode); return FDFD_ERR_ARG;
+    }
+#undef LAUNCH
+#undef LAUNCH_MODE
+    FDFD_CUDA(cudaGetLastError());
+    return FDFD_OK;
+}
+
+template int helm2d_launch<double2>(const Helm2D&, int, const double2*, double2*, const double2*,
+                                    const double2*, const double2*, const double2*, double, double,
+                                    double, cudaStream_t);
+template int helm2d_launch<float2>(const Helm2D&, int, const float2*, float2*, const float2*,
+                                   const float2*, const float2*, const float2*, double, double,
+                                   double, cudaStream_t);
+
+int helm2d_halo_exchange(Helm2D& op, const void* x, cudaStream_t stream) {
+    if (op.Ny == op.Ny_global) return FDFD_OK;
+    return comm_halo_rows(op.comm, x, op.halo_south, op.halo_north, op.Nx, op.Ny, op.elem(),
+                          op.bcy == FDFD_BC_BLOCH, stream);
+}
+
+int helm2d_apply(Helm2D& op, int mode, const void* x, void* y, const void* b, double omega,
+                 cudaStream_t stream) {
+    FDFD_TRY(helm2d_halo_exchange(op, x, stream));
+    if (op.dtype == FDFD_C128)
+        return helm2d_launch<double2>(op, mode, (const double2*)x, (double2*)y, (const double2*)b,
+                                      (const double2*)op.ca, (const double2*)op.cb,
+                                      (const double2*)op.cd, 1.0, 0.0, omega, stream);
+    return helm2d_launch<float2>(op, mode, (const float2*)x, (float2*)y, (const float2*)b,
+                                 (const float2*)op.ca, (const float2*)op.cb, (const float2*)op.cd,
+                                 1.0, 0.0, omega, stream);
+}
+
+}  // namespace fdfd

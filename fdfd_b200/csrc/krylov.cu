@@ -1,0 +1,333 @@
+// K3 — right-preconditioned BiCGSTAB and flexible GMRES.  Replaces the SuperLU direct solve of
+// the reference (Scattering_Solver_2D.py:194-203 / :209-217: spla.factorized / spsolve).
+//
+// All vector work runs in the fused BLAS-1 kernels of blas1.cu with coefficients that stay on
+// the device (scalar slots); the host only reads back one squared residual norm per iteration
+// (BiCGSTAB) or one Hessenberg column (FGMRES).  Inner products are summed across y-slab ranks
+// with one NCCL all-reduce per fused group.
+#include "krylov.cuh"
+#include "comm.cuh"
+
+#include <cmath>
+#include <complex>
+#include <vector>
+
+namespace fdfd {
+
+namespace {
+
+struct DeviceBuf {
+    void* p = nullptr;
+    int alloc(size_t bytes) {
+        FDFD_CUDA(cudaMalloc(&p, bytes));
+        return FDFD_OK;
+    }
+    ~DeviceBuf() { if (p) cudaFree(p); }
+};
+
+int read_slots(Scalars& sc, int s0, int count, double2* host, cudaStream_t stream) {
+    FDFD_CUDA(cudaMemcpyAsync(host, sc.slot + s0, sizeof(double2) * count, cudaMemcpyDeviceToHost, stream));
+    FDFD_CUDA(cudaStreamSynchronize(stream));
+    return FDFD_OK;
+}
+
+struct ScalarsGuard {
+    Scalars& s;
+    ~ScalarsGuard() { s.release(); }
+};
+
+struct JacobiPrecond : Precond {
+    Helm2D* A = nullptr;
+    void* dinv = nullptr;
+    ~JacobiPrecond() override { if (dinv) cudaFree(dinv); }
+    int apply(const void* v, void* z, cudaStream_t stream) override {
+        ++applies;
+        if (A->dtype == FDFD_C128)
+            return pointwise_mul<double2>(A->n_local(), (double2*)z, (const double2*)v, (const double2*)dinv, stream);
+        return pointwise_mul<float2>(A->n_local(), (float2*)z, (const float2*)v, (const float2*)dinv, stream);
+    }
+};
+
+// slot map --------------------------------------------------------------------------------------
+enum { S_RHO = 0, S_RHO_OLD, S_ALPHA, S_OMEGA, S_BETA, S_NBO, S_RV, S_TS, S_TT, S_RR, S_BB, S_SS,
+       S_TMP0, S_TMP1, S_TMP2, S_TMP3, S_H0 = 32 /* Hessenberg column / GMRES y (<= 200 entries) */ };
+
+template <typename C>
+int bicgstab_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, SolveInfo& info,
+               cudaStream_t stream) {
+    const int64_t n = A.n_local();
+    const size_t bytes = (size_t)n * sizeof(C);
+    Scalars sc;
+    ScalarsGuard guard{sc};
+    FDFD_TRY(sc.alloc());
+    DeviceBuf br, brh, bp, bv, bt, bph, bsh;
+    FDFD_TRY(br.alloc(bytes)); FDFD_TRY(brh.alloc(bytes)); FDFD_TRY(bp.alloc(bytes));
+    FDFD_TRY(bv.alloc(bytes)); FDFD_TRY(bt.alloc(bytes));
+    C *r = (C*)br.p, *rh = (C*)brh.p, *p = (C*)bp.p, *v = (C*)bv.p, *t = (C*)bt.p;
+    C *ph = p, *sh = r;  // unpreconditioned: p^ = p, s^ = s (= r storage)
+    if (M) {
+        FDFD_TRY(bph.alloc(bytes)); FDFD_TRY(bsh.alloc(bytes));
+        ph = (C*)bph.p; sh = (C*)bsh.p;
+    }
+    Comm* comm = A.comm;
+    double2 h[4];
+    int status = FDFD_OK;
+
+    auto restart = [&]() -> int {
+        // r = b - A x ; r^ = r ; p = v = 0 ; rho_old = alpha = omega = 1
+        FDFD_TRY(helm2d_apply(A, APPLY_RESID, x, r, b, 0.0, stream)); ++info.op_applies;
+        FDFD_CUDA(cudaMemcpyAsync(rh, r, bytes, cudaMemcpyDeviceToDevice, stream));
+        FDFD_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
+        FDFD_CUDA(cudaMemsetAsync(v, 0, bytes, stream));
+        FDFD_TRY(scalar_op(SOP_SET, S_RHO_OLD, 0, 0, 0, 0, 1.0, 0.0, sc, stream));
+        FDFD_TRY(scalar_op(SOP_SET, S_ALPHA, 0, 0, 0, 0, 1.0, 0.0, sc, stream));
+        FDFD_TRY(scalar_op(SOP_SET, S_OMEGA, 0, 0, 0, 0, 1.0, 0.0, sc, stream));
+        const C* xs[2] = {r, b}; const C* ys[2] = {r, b};
+        FDFD_TRY(dots<C>(n, 2, xs, ys, S_TMP0, sc, stream));     // ||r||^2, ||b||^2
+        FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 2, stream));
+        FDFD_TRY(scalar_op(SOP_COPY, S_RHO, S_TMP0, 0, 0, 0, 0, 0, sc, stream));  // (r^, r) = ||r||^2
+        FDFD_TRY(scalar_op(SOP_COPY, S_RR, S_TMP0, 0, 0, 0, 0, 0, sc, stream));
+        FDFD_TRY(scalar_op(SOP_COPY, S_BB, S_TMP1, 0, 0, 0, 0, 0, sc, stream));
+        return FDFD_OK;
+    };
+    FDFD_TRY(restart());
+    FDFD_TRY(read_slots(sc, S_RR, 2, h, stream));
+    const double bnorm2 = h[1].x > 0 ? h[1].x : 1.0;
+    double rr = h[0].x;
+    const double target2 = o.rtol * o.rtol * bnorm2;
+    int it = 0;
+    double best = rr;
+    int since_best = 0;
+    while (rr > target2 && it < o.maxit) {
+        ++it;
+        // beta, p = r + beta (p - omega v)
+        FDFD_TRY(scalar_op(SOP_BICG_BETA, S_BETA, S_RHO, S_RHO_OLD, S_ALPHA, S_OMEGA, 0, 0, sc, stream));
+        FDFD_TRY(lincomb<C>(n, p, nullptr, r, sc.slot + S_BETA, p, sc.slot + S_NBO, v, 0, nullptr, -1, -1, sc, stream));
+        if (M) { FDFD_TRY(M->apply(p, ph, stream)); ++info.precond_applies; }
+        FDFD_TRY(helm2d_apply(A, APPLY_AX, ph, v, nullptr, 0.0, stream)); ++info.op_applies;
+        { const C* xs[1] = {rh}; const C* ys[1] = {v}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_RV, sc, stream)); }
+        FDFD_TRY(allreduce_slots(comm, sc, S_RV, 1, stream));
+        FDFD_TRY(scalar_op(SOP_DIV, S_ALPHA, S_RHO, S_RV, 0, 0, 0, 0, sc, stream));
+        // s = r - alpha v  (in r's storage)
+        FDFD_TRY(lincomb<C>(n, r, nullptr, r, sc.slot + S_ALPHA, v, nullptr, nullptr, 2, nullptr, -1, -1, sc, stream));
+        if (M) { FDFD_TRY(M->apply(r, sh, stream)); ++info.precond_applies; }
+        FDFD_TRY(helm2d_apply(A, APPLY_AX, sh, t, nullptr, 0.0, stream)); ++info.op_applies;
+        { const C* xs[2] = {t, t}; const C* ys[2] = {r, t}; FDFD_TRY(dots<C>(n, 2, xs, ys, S_TS, sc, stream)); }
+        FDFD_TRY(allreduce_slots(comm, sc, S_TS, 2, stream));
+        FDFD_TRY(scalar_op(SOP_DIV, S_OMEGA, S_TS, S_TT, 0, 0, 0, 0, sc, stream));
+        // x += alpha p^ + omega s^
+        FDFD_TRY(lincomb<C>(n, x, nullptr, x, sc.slot + S_ALPHA, ph, sc.slot + S_OMEGA, sh, 0, nullptr, -1, -1, sc, stream));
+        // r = s - omega t ; rho_old <- rho ; rho = (r^, r) ; rr = ||r||^2
+        FDFD_TRY(scalar_op(SOP_COPY, S_RHO_OLD, S_RHO, 0, 0, 0, 0, 0, sc, stream));
+        FDFD_TRY(lincomb<C>(n, r, nullptr, r, sc.slot + S_OMEGA, t, nullptr, nullptr, 2, rh, S_RHO, S_RR, sc, stream));
+        if (comm && comm->nranks > 1) {
+            // S_RHO and S_RR are not adjacent: reduce them through the adjacent temporaries
+            FDFD_TRY(scalar_op(SOP_COPY, S_TMP0, S_RHO, 0, 0, 0, 0, 0, sc, stream));
+            FDFD_TRY(scalar_op(SOP_COPY, S_TMP1, S_RR, 0, 0, 0, 0, 0, sc, stream));
+            FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 2, stream));
+            FDFD_TRY(scalar_op(SOP_COPY, S_RHO, S_TMP0, 0, 0, 0, 0, 0, sc, stream));
+            FDFD_TRY(scalar_op(SOP_COPY, S_RR, S_TMP1, 0, 0, 0, 0, 0, sc, stream));
+        }
+        FDFD_TRY(read_slots(sc, S_RR, 1, h, stream));
+        rr = h[0].x;
+        if (!std::isfinite(rr)) {
+            ++info.breakdowns;
+            if (info.breakdowns > 5) { status = FDFD_ERR_BREAKDOWN; set_error("BiCGSTAB breakdown (non-finite residual) at iteration %d", it); break; }
+            FDFD_TRY(restart());
+            FDFD_TRY(read_slots(sc, S_RR, 1, h, stream));
+            rr = h[0].x;
+            if (!std::isfinite(rr)) { status = FDFD_ERR_BREAKDOWN; set_error("BiCGSTAB: iterate became non-finite"); break; }
+            continue;
+        }
+        if (o.verbose && (it % o.verbose == 0))
+            fprintf(stderr, "[fdfd] bicgstab it %d relres %.3e\n", it, std::sqrt(rr / bnorm2));
+        if (rr < best) { best = rr; since_best = 0; }
+        else if (++since_best >= 200) {       // stagnation: rebuild the recurrences from the true residual
+            ++info.breakdowns; since_best = 0;
+            FDFD_TRY(restart());
+            FDFD_TRY(read_slots(sc, S_RR, 1, h, stream));
+            rr = h[0].x; best = rr;
+        }
+        if (rr <= target2) {
+            // confirm with the true residual before stopping (recurrence drift)
+            FDFD_TRY(helm2d_apply(A, APPLY_RESID, x, t, b, 0.0, stream)); ++info.op_applies;
+            const C* xs[1] = {t}; const C* ys[1] = {t};
+            FDFD_TRY(dots<C>(n, 1, xs, ys, S_TMP0, sc, stream));
+            FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 1, stream));
+            FDFD_TRY(read_slots(sc, S_TMP0, 1, h, stream));
+            if (h[0].x > target2 && it < o.maxit) {
+                FDFD_TRY(restart());
+                FDFD_TRY(read_slots(sc, S_RR, 1, h, stream));
+                rr = h[0].x; best = rr;
+            } else {
+                rr = h[0].x;
+            }
+        }
+    }
+    // true residual
+    FDFD_TRY(helm2d_apply(A, APPLY_RESID, x, t, b, 0.0, stream)); ++info.op_applies;
+    { const C* xs[1] = {t}; const C* ys[1] = {t}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_TMP0, sc, stream)); }
+    FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 1, stream));
+    FDFD_TRY(read_slots(sc, S_TMP0, 1, h, stream));
+    info.iterations = it;
+    info.relres = std::sqrt(h[0].x / bnorm2);
+    if (status == FDFD_OK && !(info.relres <= o.rtol * 1.0000001)) {
+        set_error("BiCGSTAB did not converge: relres %.3e after %d iterations", info.relres, it);
+        status = FDFD_ERR_NOCONV;
+    }
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename C>
+int fgmres_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, SolveInfo& info,
+             cudaStream_t stream) {
+    using cd = std::complex<double>;
+    const int64_t n = A.n_local();
+    const size_t bytes = (size_t)n * sizeof(C);
+    int m = o.restart > 0 ? o.restart : 30;
+    if (m > 160) m = 160;
+    Scalars sc;
+    ScalarsGuard guard{sc};
+    FDFD_TRY(sc.alloc());
+    DeviceBuf bV, bZ, bw;
+    FDFD_TRY(bV.alloc(bytes * (m + 1)));
+    if (M) FDFD_TRY(bZ.alloc(bytes * m));
+    FDFD_TRY(bw.alloc(bytes));
+    C* V = (C*)bV.p;
+    C* Z = M ? (C*)bZ.p : V;
+    C* w = (C*)bw.p;
+    Comm* comm = A.comm;
+    std::vector<double2> hbuf(m + 8);
+    std::vector<cd> H((size_t)(m + 1) * m), g(m + 1), cs(m), sn(m), y(m);
+    int status = FDFD_OK;
+    int it = 0;
+    double bnorm2 = 0, relres = 1.0;
+    {
+        const C* xs[1] = {b}; const C* ys[1] = {b};
+        FDFD_TRY(dots<C>(n, 1, xs, ys, S_BB, sc, stream));
+        FDFD_TRY(allreduce_slots(comm, sc, S_BB, 1, stream));
+        FDFD_TRY(read_slots(sc, S_BB, 1, hbuf.data(), stream));
+        bnorm2 = hbuf[0].x > 0 ? hbuf[0].x : 1.0;
+    }
+    const double bnorm = std::sqrt(bnorm2);
+    bool done = false;
+    while (!done) {
+        // r = b - A x -> V0 (normalised)
+        FDFD_TRY(helm2d_apply(A, APPLY_RESID, x, w, b, 0.0, stream)); ++info.op_applies;
+        { const C* xs[1] = {w}; const C* ys[1] = {w}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_RR, sc, stream)); }
+        FDFD_TRY(allreduce_slots(comm, sc, S_RR, 1, stream));
+        FDFD_TRY(read_slots(sc, S_RR, 1, hbuf.data(), stream));
+        const double beta = std::sqrt(hbuf[0].x);
+        relres = beta / bnorm;
+        if (!std::isfinite(beta)) { status = FDFD_ERR_BREAKDOWN; set_error("FGMRES: non-finite residual"); break; }
+        if (relres <= o.rtol || it >= o.maxit) break;
+        FDFD_TRY(scale_inv_sqrt<C>(n, V, w, S_RR, sc, stream));
+        std::fill(H.begin(), H.end(), cd(0));
+        std::fill(g.begin(), g.end(), cd(0));
+        g[0] = beta;
+        int k = 0;
+        for (int j = 0; j < m; ++j) {
+            C* vj = V + (int64_t)j * n;
+            C* zj = Z + (int64_t)j * n;
+            if (M) { FDFD_TRY(M->apply(vj, zj, stream)); ++info.precond_applies; }
+            FDFD_TRY(helm2d_apply(A, APPLY_AX, zj, w, nullptr, 0.0, stream)); ++info.op_applies;
+            // classical Gram-Schmidt with one re-orthogonalisation pass, fused multi-vector kernels
+            const int passes = o.reorth ? 2 : 1;
+            for (int pass = 0; pass < passes; ++pass) {
+                FDFD_TRY(multi_dot<C>(n, j + 1, V, n, w, S_H0, sc, stream));
+                FDFD_TRY(allreduce_slots(comm, sc, S_H0, j + 1, stream));
+                const bool last = pass == passes - 1;
+                FDFD_TRY(multi_axpy<C>(n, j + 1, V, n, w, S_H0, -1.0, last ? S_TMP0 : -1, sc, stream));
+                if (last) FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 1, stream));
+                FDFD_CUDA(cudaMemcpyAsync(hbuf.data(), sc.slot + S_H0, sizeof(double2) * (j + 1), cudaMemcpyDeviceToHost, stream));
+                if (last) FDFD_CUDA(cudaMemcpyAsync(hbuf.data() + j + 1, sc.slot + S_TMP0, sizeof(double2), cudaMemcpyDeviceToHost, stream));
+                FDFD_CUDA(cudaStreamSynchronize(stream));
+                for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] += cd(hbuf[i].x, hbuf[i].y);
+            }
+            const double hn = std::sqrt(hbuf[j + 1].x);
+            H[(size_t)(j + 1) * m + j] = hn;
+            if (j + 1 < m + 1 && hn > 0)
+                FDFD_TRY(scale_inv_sqrt<C>(n, V + (int64_t)(j + 1) * n, w, S_TMP0, sc, stream));
+            // Givens rotations on the new column
+            for (int i = 0; i < j; ++i) {
+                const cd a = H[(size_t)i * m + j], bb = H[(size_t)(i + 1) * m + j];
+                H[(size_t)i * m + j] = std::conj(cs[i]) * a + std::conj(sn[i]) * bb;
+                H[(size_t)(i + 1) * m + j] = -sn[i] * a + cs[i] * bb;
+            }
+            {
+                const cd a = H[(size_t)j * m + j], bb = H[(size_t)(j + 1) * m + j];
+                const double d = std::sqrt(std::norm(a) + std::norm(bb));
+                if (d == 0) { cs[j] = 1; sn[j] = 0; }
+                else { cs[j] = a / d; sn[j] = bb / d; }
+                H[(size_t)j * m + j] = std::conj(cs[j]) * a + std::conj(sn[j]) * bb;
+                H[(size_t)(j + 1) * m + j] = 0;
+                const cd gj = g[j];
+                g[j] = std::conj(cs[j]) * gj;
+                g[j + 1] = -sn[j] * gj;
+            }
+            ++it; k = j + 1;
+            relres = std::abs(g[j + 1]) / bnorm;
+            if (o.verbose && (it % o.verbose == 0))
+                fprintf(stderr, "[fdfd] fgmres it %d relres %.3e\n", it, relres);
+            if (!std::isfinite(relres)) { status = FDFD_ERR_BREAKDOWN; set_error("FGMRES: non-finite Hessenberg entry"); done = true; break; }
+            if (relres <= o.rtol || it >= o.maxit || hn == 0) break;
+        }
+        if (status != FDFD_OK) break;
+        // y = H^-1 g (upper triangular), x += Z y
+        for (int i = k - 1; i >= 0; --i) {
+            cd s = g[i];
+            for (int q = i + 1; q < k; ++q) s -= H[(size_t)i * m + q] * y[q];
+            y[i] = s / H[(size_t)i * m + i];
+        }
+        for (int i = 0; i < k; ++i) hbuf[i] = make_double2(y[i].real(), y[i].imag());
+        FDFD_CUDA(cudaMemcpyAsync(sc.slot + S_H0, hbuf.data(), sizeof(double2) * k, cudaMemcpyHostToDevice, stream));
+        FDFD_TRY(multi_axpy<C>(n, k, Z, n, x, S_H0, 1.0, -1, sc, stream));
+        FDFD_CUDA(cudaStreamSynchronize(stream));
+    }
+    // true residual
+    FDFD_TRY(helm2d_apply(A, APPLY_RESID, x, w, b, 0.0, stream)); ++info.op_applies;
+    { const C* xs[1] = {w}; const C* ys[1] = {w}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_RR, sc, stream)); }
+    FDFD_TRY(allreduce_slots(comm, sc, S_RR, 1, stream));
+    FDFD_TRY(read_slots(sc, S_RR, 1, hbuf.data(), stream));
+    info.iterations = it;
+    info.relres = std::sqrt(hbuf[0].x) / bnorm;
+    if (status == FDFD_OK && !(info.relres <= o.rtol * 1.0000001)) {
+        set_error("FGMRES did not converge: relres %.3e after %d iterations", info.relres, it);
+        status = FDFD_ERR_NOCONV;
+    }
+    return status;
+}
+
+}  // namespace
+
+int make_jacobi_precond(Helm2D& A, Precond** out, cudaStream_t stream) {
+    JacobiPrecond* P = new JacobiPrecond();
+    P->A = &A;
+    cudaError_t e = cudaMalloc(&P->dinv, (size_t)A.n_local() * A.elem());
+    if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaMalloc(dinv)", __FILE__, __LINE__); }
+    // halo not needed: the diagonal only depends on coefficients
+    int st;
+    if (A.dtype == FDFD_C128)
+        st = helm2d_launch<double2>(A, APPLY_DINV, (const double2*)P->dinv, (double2*)P->dinv, nullptr,
+                                    (const double2*)A.ca, (const double2*)A.cb, (const double2*)A.cd, 1.0, 0.0, 0.0, stream);
+    else
+        st = helm2d_launch<float2>(A, APPLY_DINV, (const float2*)P->dinv, (float2*)P->dinv, nullptr,
+                                   (const float2*)A.ca, (const float2*)A.cb, (const float2*)A.cd, 1.0, 0.0, 0.0, stream);
+    if (st != FDFD_OK) { delete P; return st; }
+    *out = P;
+    return FDFD_OK;
+}
+
+int bicgstab_solve(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
+                   SolveInfo& info, cudaStream_t stream) {
+    if (A.dtype == FDFD_C128) return bicgstab_t<double2>(A, M, o, (const double2*)b, (double2*)x, info, stream);
+    return bicgstab_t<float2>(A, M, o, (const float2*)b, (float2*)x, info, stream);
+}
+int fgmres_solve(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
+                 SolveInfo& info, cudaStream_t stream) {
+    if (A.dtype == FDFD_C128) return fgmres_t<double2>(A, M, o, (const double2*)b, (double2*)x, info, stream);
+    return fgmres_t<float2>(A, M, o, (const float2*)b, (float2*)x, info, stream);
+}
+
+}  // namespace fdfd

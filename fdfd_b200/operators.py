@@ -1,0 +1,190 @@
+"""Host handle of the matrix-free Helmholtz / curl-curl operator K2 and of the Krylov stack.
+
+Mirrors what the reference materialises as scipy sparse matrices:
+  ``A_TE = DHX mu_yy^-1 DEX + DHY mu_xx^-1 DEY + eps_zz``  (Scattering_Solver_2D.py:176-181)
+  ``A_TM = DEX eps_yy^-1 DHX + DEY eps_xx^-1 DHY + mu_zz`` (Scattering_Solver_2D.py:183-188)
+  ``A_tm = -DHX mu_yy^-1 DEX - DHY mu_xx^-1 DEY``          (Band_Diagram_Solver.py:312)
+  ``A_te = -DEX eps_yy^-1 DHX - DEY eps_xx^-1 DHY``        (Band_Diagram_Solver.py:319)
+but never forms them: ``apply`` runs the sm_100a stencil kernel through the C-ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_POL = {"TE": _lib.POL_TE, "TM": _lib.POL_TM}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class HelmholtzOperator2D:
+    """y = sx * D1 diag(ca) D2 x + sy * D3 diag(cb) D4 x + cd .* x   on an Nx x Ny Yee grid.
+
+    pol='TE': D = (DHX, DEX, DHY, DEY); pol='TM': D = (DEX, DHX, DEY, DHY)  (unit spacing).
+    ca, cb, cd: (Ny, Nx) complex arrays (numpy or torch); cd may be None.
+    bc: (xbc, ybc) with 0 Dirichlet / 1 Bloch; phase = exp(-1j*k*N*d) per axis.
+    Sharding: ``rows=(j0, j1)`` selects this rank's y-slab, ``comm`` a :class:`SlabComm`.
+    """
+
+    def __init__(self, pol, Nx, Ny, ca, cb, cd, sx, sy, bc=(0, 0), phase=(1.0 + 0j, 1.0 + 0j),
+                 dtype="complex128", device=None, rows=None, comm=None):
+        torch = _torch()
+        _lib.require_cuda()
+        self._L = _lib.lib()
+        self.pol = pol.upper()
+        if self.pol not in _POL:
+            raise ValueError("pol must be 'TE' or 'TM'")
+        self.Nx, self.Ny = int(Nx), int(Ny)
+        self.device = torch.device(device or "cuda")
+        self.tdtype = {"complex128": torch.complex128, "complex64": torch.complex64}[str(dtype).replace("torch.", "")]
+        self.code = _lib.C128 if self.tdtype == torch.complex128 else _lib.C64
+        self.j0, self.j1 = (0, self.Ny) if rows is None else (int(rows[0]), int(rows[1]))
+        self.ny_local = self.j1 - self.j0
+        self.comm = comm
+        shape = (self.ny_local, self.Nx)
+        self.ca = self._dev(ca, shape)
+        self.cb = self._dev(cb, shape)
+        self.cd = None if cd is None else self._dev(cd, shape)
+        self.sx, self.sy = float(sx), float(sy)
+        self.bc = (int(bc[0]), int(bc[1]))
+        ph = (C.c_double * 4)(complex(phase[0]).real, complex(phase[0]).imag,
+                              complex(phase[1]).real, complex(phase[1]).imag)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.fdfd_helm2d_create(
+                C.byref(self._h), self.code, _POL[self.pol], self.Nx, self.Ny, self.j0, self.ny_local,
+                self.bc[0], self.bc[1], ph, self.sx, self.sy, self.ca.data_ptr(), self.cb.data_ptr(),
+                None if self.cd is None else self.cd.data_ptr(),
+                None if comm is None else comm.handle, self._stream()))
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _dev(self, a, shape):
+        torch = _torch()
+        if not isinstance(a, torch.Tensor):
+            a = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.complex128).reshape(shape)))
+        a = a.to(device=self.device, dtype=self.tdtype).reshape(shape).contiguous()
+        return a
+
+    def _stream(self):
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    @property
+    def n(self):
+        return self.Nx * self.ny_local
+
+    @property
+    def bytes_per_apply(self):
+        return int(self._L.fdfd_helm2d_bytes_per_apply(self._h))
+
+    def set_variant(self, v):
+        _lib.check(self._L.fdfd_helm2d_set_variant(self._h, int(v)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.fdfd_helm2d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- operator application -------------------------------------------------------------------
+    def apply(self, x, out=None):
+        """y = A x for a device tensor x (any shape with n elements)."""
+        torch = _torch()
+        if not isinstance(x, torch.Tensor):
+            raise TypeError("apply() takes a CUDA torch tensor; use apply_host() for numpy arrays")
+        if x.numel() != self.n or x.dtype != self.tdtype or not x.is_cuda:
+            raise ValueError("x must be a CUDA tensor with Nx*Ny_local elements of the operator dtype")
+        x = x.contiguous()
+        if out is None:
+            out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.fdfd_helm2d_apply(self._h, x.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def apply_host(self, x):
+        """y = A x with numpy in / numpy out (H2D + kernel + D2H inside the C-ABI call)."""
+        ndt = np.complex128 if self.code == _lib.C128 else np.complex64
+        x = np.ascontiguousarray(x, dtype=ndt)
+        if x.size != self.n:
+            raise ValueError("x has the wrong number of elements")
+        y = np.empty_like(x)
+        _lib.check(self._L.fdfd_helm2d_apply_host(self._h, x.ctypes.data, y.ctypes.data))
+        return y
+
+    __matmul__ = lambda self, x: self.apply(x) if not isinstance(x, np.ndarray) else self.apply_host(x)
+
+    # -- linear solve -------------------------------------------------------------------------------
+    def solve(self, b, x0=None, *, method="bicgstab", precond="jacobi", rtol=1e-8, maxit=100000,
+              raise_on_noconv=True, **opts):
+        """Solve A x = b on the device.  Returns (x, info dict)."""
+        torch = _torch()
+        o = _lib.default_opts(method={"bicgstab": _lib.KRYLOV_BICGSTAB, "fgmres": _lib.KRYLOV_FGMRES}[method],
+                              precond={"none": _lib.PRECOND_NONE, None: _lib.PRECOND_NONE,
+                                       "jacobi": _lib.PRECOND_JACOBI, "mg": _lib.PRECOND_MG}[precond],
+                              rtol=float(rtol), maxit=int(maxit), **opts)
+        info = (C.c_double * 8)()
+        host = isinstance(b, np.ndarray)
+        ndt = np.complex128 if self.code == _lib.C128 else np.complex64
+        if host:
+            bh = np.ascontiguousarray(b, dtype=ndt).ravel()
+            xh = np.zeros_like(bh) if x0 is None else np.ascontiguousarray(x0, dtype=ndt).ravel().copy()
+            st = self._L.fdfd_krylov_solve_host(self._h, C.byref(o), bh.ctypes.data, xh.ctypes.data, info)
+            x = xh
+        else:
+            bd = b.to(device=self.device, dtype=self.tdtype).contiguous().reshape(-1)
+            x = torch.zeros_like(bd) if x0 is None else x0.to(device=self.device, dtype=self.tdtype).reshape(-1).clone()
+            with torch.cuda.device(self.device):
+                st = self._L.fdfd_krylov_solve(self._h, C.byref(o), bd.data_ptr(), x.data_ptr(), info, self._stream())
+        d = dict(iterations=int(info[0]), relres=float(info[1]), applies=int(info[2]),
+                 precond_applies=int(info[3]), seconds=float(info[4]), breakdowns=int(info[5]),
+                 method=method, precond=precond, converged=(st == _lib.FDFD_OK))
+        if st == _lib.FDFD_ERR_NOCONV and not raise_on_noconv:
+            return x, d
+        _lib.check(st, d)
+        return x, d
+
+
+class SlabComm:
+    """NCCL communicator for y-slab sharding; the 128-byte unique id travels through
+    ``torch.distributed`` (any backend) from rank 0."""
+
+    def __init__(self, rank=None, world_size=None):
+        import torch
+        import torch.distributed as dist
+
+        L = _lib.lib()
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world_size = dist.get_world_size() if world_size is None else world_size
+        buf = C.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(L.fdfd_comm_unique_id(buf))
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        ident = bytes(t.cpu().numpy().tobytes())
+        self.handle = C.c_void_p()
+        _lib.check(L.fdfd_comm_create(C.byref(self.handle), self.world_size, self.rank, ident))
+        self._L = L
+
+    def close(self):
+        if self.handle and self.handle.value:
+            self._L.fdfd_comm_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+def slab_rows(Ny, world_size, rank):
+    """Contiguous y-slab [j0, j1) of rank `rank`; remainders go to the low ranks."""
+    base, rem = divmod(int(Ny), int(world_size))
+    j0 = rank * base + min(rank, rem)
+    return j0, j0 + base + (1 if rank < rem else 0)

@@ -1,0 +1,157 @@
+/*
+ * fdfd_b200 — C-ABI of the B200-native FDFD solve engine (libfdfd_b200.so).
+ *
+ * The reference (SolverNotConverging/FDFD) is pure Python: its "interface" for this path is a
+ * set of in-process Python calls, cited per entry point below (file:line relative to the
+ * reference root).  A reference maintainer binds this header with ctypes — see
+ * INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative fdfd_status otherwise; the message of
+ *     the last failure on the calling thread is available from fdfd_last_error().
+ *   - *_host entry points take HOST pointers and do their own H2D/D2H copies;
+ *     all other data pointers are caller-owned DEVICE pointers (cudaMalloc / torch tensors).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - flat index n = i + Nx*j (x fastest), exactly as the reference
+ *     (Scattering_Solver_2D.py:41,61,107; Band_Diagram_Solver.py:286-291).
+ *   - complex128 = interleaved (re, im) doubles, complex64 = interleaved floats.
+ *   - no CPU fallback anywhere: without a CUDA device every compute call fails with
+ *     FDFD_ERR_CUDA.
+ */
+#ifndef FDFD_B200_H
+#define FDFD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    FDFD_OK = 0,
+    FDFD_ERR_ARG = -1,       /* bad argument (ValueError on the Python side)            */
+    FDFD_ERR_CUDA = -2,      /* CUDA runtime failure / no device                        */
+    FDFD_ERR_BREAKDOWN = -3, /* Krylov breakdown (rho or omega ~ 0, NaN)                 */
+    FDFD_ERR_NOCONV = -4,    /* maxit reached (solution still returned, relres reported) */
+    FDFD_ERR_NCCL = -5,
+    FDFD_ERR_STATE = -6
+} fdfd_status;
+
+enum { FDFD_C128 = 0, FDFD_C64 = 1 };
+enum { FDFD_POL_TE = 0, FDFD_POL_TM = 1 };       /* operator type, see fdfd_helm2d_create   */
+enum { FDFD_BC_DIRICHLET = 0, FDFD_BC_BLOCH = 1 };/* yeeder2d BC codes (yee_derivative.py:16-19) */
+enum { FDFD_KRYLOV_BICGSTAB = 0, FDFD_KRYLOV_FGMRES = 1 };
+enum { FDFD_PRECOND_NONE = 0, FDFD_PRECOND_JACOBI = 1, FDFD_PRECOND_MG = 2 };
+
+const char* fdfd_last_error(void);
+int fdfd_version(void);
+/* number of visible CUDA devices (0 when none) — the Python layer refuses to run on 0. */
+int fdfd_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  Yee derivative-operator assembly  — replaces yeeder2d(NS, RES, BC, kinc)
+ *     (Scattering/yee_derivative.py:6-74 == Band_Diagram_Solver/yee_derivative.py:6-74).
+ *
+ * Per axis the operator has at most three distinct values; they are evaluated on the host
+ * with the reference's numpy expressions (bit parity of values) and passed in:
+ *   diag  = -1/d            (or -1j*k when N==1,  yee_derivative.py:47-48)
+ *   fwd   = +1/d
+ *   wrap  = exp(-1j*k*N*d)/d   (Bloch axis only, yee_derivative.py:54-57 / :66-68)
+ * An axis is complex128 iff N==1 or bc==BLOCH, else float64 — the same per-axis rule scipy's
+ * type promotion produces.  Index arrays are int32 (scipy picks int32 while nnz < 2^31).
+ * DHX/DHY (CSC) share the index arrays of DEX/DEY (CSR); data = -conj (yee_derivative.py:71-72).
+ * ------------------------------------------------------------------------------------------ */
+int fdfd_yee2d_csr_nnz(int Nx, int Ny, int bcx, int bcy,
+                       int64_t* nnz_dex, int64_t* nnz_dey,
+                       int* dex_is_complex, int* dey_is_complex);
+
+/* axis: 0 -> DEX, 1 -> DEY.  vals = {diag_re, diag_im, fwd_re, fwd_im, wrap_re, wrap_im}.
+ * e_data / h_data: float64[nnz] or complex128[nnz] per the rule above; h_data may be NULL. */
+int fdfd_yee2d_csr_fill(int Nx, int Ny, int axis, int bc, const double vals[6],
+                        int32_t* indptr, int32_t* indices, void* e_data, void* h_data,
+                        void* stream);
+/* same, HOST output buffers (device scratch + D2H inside). */
+int fdfd_yee2d_csr_fill_host(int Nx, int Ny, int axis, int bc, const double vals[6],
+                             int32_t* indptr, int32_t* indices, void* e_data, void* h_data);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  matrix-free complex Helmholtz / curl-curl operator on an Nx x Ny (slab of a) Yee grid
+ *     — replaces the explicit sparse products of
+ *       _build_A_TE / _build_A_TM   (Scattering_Solver_2D.py:176-188) and
+ *       A_tm / A_te of the band solver (Band_Diagram_Solver.py:312,319).
+ *
+ *   pol = FDFD_POL_TE :  y = sx*DHX diag(ca) DEX x + sy*DHY diag(cb) DEY x + cd.*x
+ *   pol = FDFD_POL_TM :  y = sx*DEX diag(ca) DHX x + sy*DEY diag(cb) DHY x + cd.*x
+ * with DEX.. the *unit-spacing* yeeder2d operators for (bcx, bcy, phase), i.e. sx = +-1/dx^2.
+ * ca, cb, cd are device arrays of Nx*Ny_local complex numbers in `dtype` (cd may be NULL = 0).
+ * phase = {phx_re, phx_im, phy_re, phy_im} = exp(-1j*k*N*d) per axis (ignored for Dirichlet).
+ *
+ * y-slab sharding: rank r of nranks owns rows [j0, j0+Ny_local) of the global
+ * Ny_global rows.  comm = opaque communicator from fdfd_comm_create (NULL for nranks==1).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct fdfd_helm2d fdfd_helm2d_t;
+typedef struct fdfd_comm fdfd_comm_t;
+
+int fdfd_helm2d_create(fdfd_helm2d_t** out, int dtype, int pol, int Nx, int Ny_global,
+                       int j0, int Ny_local, int bcx, int bcy, const double phase[4],
+                       double sx, double sy,
+                       const void* ca, const void* cb, const void* cd,
+                       fdfd_comm_t* comm, void* stream);
+void fdfd_helm2d_destroy(fdfd_helm2d_t*);
+/* y = A x  (device pointers, Nx*Ny_local complex each; halo exchange inside when sharded) */
+int fdfd_helm2d_apply(fdfd_helm2d_t*, const void* x, void* y, void* stream);
+/* HOST-buffer apply of the full (unsharded) operator: uploads x, applies, downloads y. */
+int fdfd_helm2d_apply_host(fdfd_helm2d_t*, const void* x_host, void* y_host);
+/* algorithmic bytes one apply moves (80 B/pt c128, 40 B/pt c64) */
+int64_t fdfd_helm2d_bytes_per_apply(const fdfd_helm2d_t*);
+/* selects the kernel variant (0 = default) — benchmarking aid */
+int fdfd_helm2d_set_variant(fdfd_helm2d_t*, int variant);
+
+/* ------------------------------------------------------------------------------------------
+ * K3-K5  Krylov solve  A x = b  — replaces spla.factorized / spsolve
+ *        (Scattering_Solver_2D.py:194-203, :209-217).
+ * b, x: device, Nx*Ny_local complex of the operator's dtype; x holds the initial guess.
+ * info (host, optional, 8 doubles): {iterations, relres (true), applies, precond_applies,
+ *        seconds (device time), breakdowns, 0, 0}.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int method;       /* FDFD_KRYLOV_*                                   */
+    int precond;      /* FDFD_PRECOND_*                                  */
+    double rtol;      /* stop when ||b - A x|| <= rtol * ||b||           */
+    int maxit;
+    int restart;      /* FGMRES restart length                           */
+    int mg_levels;    /* 0 = automatic                                   */
+    int mg_pre, mg_post;   /* smoothing sweeps                           */
+    double mg_shift_re, mg_shift_im;  /* complex shift (beta1, beta2) of the preconditioner */
+    double mg_omega;  /* Jacobi damping                                  */
+    int mg_cycle;     /* 1 = V, 2 = W                                    */
+    int mg_coarse_its;/* smoother sweeps / Krylov its on the coarsest level */
+    int verbose;      /* print the residual every `verbose` iterations (0 = silent) */
+    /* tangential line relaxation inside absorbing layers (UPML): number of columns at the low/high
+     * x end and rows at the low/high y end of the GLOBAL grid that get line (tridiagonal) solves
+     * instead of point Jacobi; 0 = none.  The Python solver passes its add_UPML widths. */
+    int line_x_lo, line_x_hi, line_y_lo, line_y_hi;
+    int mg_wfrom;     /* first level (0 = finest) that is cycled as a W instead of a V; <0 = never */
+    int mg_min_n;     /* stop coarsening when min(Nx, Ny) of the next level would drop below this */
+    int reorth;       /* FGMRES: 1 = second Gram-Schmidt pass                                   */
+} fdfd_krylov_opts;
+
+void fdfd_krylov_default_opts(fdfd_krylov_opts*);
+int fdfd_krylov_solve(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts,
+                      const void* b, void* x, double* info, void* stream);
+/* HOST-buffer solve (full operator): uploads b and x0, solves, downloads x. */
+int fdfd_krylov_solve_host(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts,
+                           const void* b_host, void* x_host, double* info);
+
+/* ------------------------------------------------------------------------------------------
+ * multi-GPU plumbing: one process per GPU; the 128-byte NCCL unique id is produced by rank 0
+ * (fdfd_comm_unique_id) and distributed by the host framework (torch.distributed).
+ * ------------------------------------------------------------------------------------------ */
+int fdfd_comm_unique_id(void* id128);
+int fdfd_comm_create(fdfd_comm_t** out, int nranks, int rank, const void* id128);
+void fdfd_comm_destroy(fdfd_comm_t*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDFD_B200_H */

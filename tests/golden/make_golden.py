@@ -1,0 +1,98 @@
+"""Regenerates the golden fixtures in this directory from the UNMODIFIED reference
+(/root/reference, imported read-only through oracle/ref_loader.py with matplotlib/tkinter
+stubs).  Run in the build container only:  python tests/golden/make_golden.py
+
+Fixtures (all produced by the reference's own code paths, scipy 1.18.1 / numpy 2.3.5):
+  yee2d_kat.npz        yeeder2d outputs (indptr/indices/data of DEX, DEY, DHX, DHY) for the
+                       edge-case grid of SURVEY.md §4.2 / §8c
+  scatter_small.npz    FDFD2DScatteringSolver at 120x120 (eps_r=4 cylinder, UPML 20, mask 30):
+                       A@x for a seeded x (TE and TM), right-hand sides and solved Ez / Hz
+  scatter_cfg1.npz     BASELINE config 1 (example_scattering_by_cylinder.py, 300x300, TM) and the
+                       same geometry solved TE: probe values, norms and a 10x-decimated field
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+YEE_CASES = [
+    # (Nx, Ny, dx, dy, bcx, bcy, kx, ky)
+    (4, 3, 0.5, 0.25, 0, 0, None, None),
+    (4, 3, 0.5, 0.25, 1, 1, 0.3, 0.7),
+    (7, 5, 0.13, 0.29, 1, 0, 1.1, -0.4),
+    (7, 5, 0.13, 0.29, 0, 1, 1.1, -0.4),
+    (1, 5, 0.2, 0.3, 0, 0, 0.9, 0.2),
+    (5, 1, 0.2, 0.3, 1, 1, 0.9, 0.2),
+    (1, 1, 0.2, 0.3, 0, 1, 0.5, 0.6),
+    (2, 2, 1.0, 1.0, 1, 1, 0.0, 0.0),
+    (16, 33, 0.05, 0.07, 1, 1, 2.5, 3.5),
+]
+
+
+def yee_fixture():
+    yeeder2d = ref_loader.ref_yeeder2d("Scattering")
+    out = {"cases": np.array([[np.nan if v is None else v for v in c] for c in YEE_CASES], dtype=float)}
+    for n, (Nx, Ny, dx, dy, bx, by, kx, ky) in enumerate(YEE_CASES):
+        kinc = None if kx is None else [kx, ky]
+        ops = yeeder2d([Nx, Ny], [dx, dy], [bx, by], kinc)
+        for name, m in zip(("DEX", "DEY", "DHX", "DHY"), ops):
+            out[f"c{n}_{name}_indptr"] = m.indptr
+            out[f"c{n}_{name}_indices"] = m.indices
+            out[f"c{n}_{name}_data"] = m.data
+            out[f"c{n}_{name}_format"] = np.array(m.format)
+    np.savez_compressed(os.path.join(HERE, "yee2d_kat.npz"), **out)
+
+
+def _ref_sim(N, eps, pw, mask, f0=10e9):
+    mod = ref_loader.load("Scattering_Solver_2D")
+    lam = 299792458 / f0
+    L = N / 50 * lam
+    sim = mod.FDFD2DScatteringSolver(frequency=f0, x_range=L, y_range=L, Nx=N, Ny=N)
+    sim.add_object(er_tensor=eps, mr_tensor=1.0, region_mask=(sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
+    sim.add_UPML(pml_width=pw, sigma_max=10)
+    sim.add_mask(value=mask)
+    sim.add_source(src_type="plane_wave", angle_deg=45.0, polarization="TE")
+    return sim
+
+
+def scatter_small():
+    N = 120
+    sim = _ref_sim(N, 4.0, 20, 30)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(N * N) + 1j * rng.standard_normal(N * N)
+    out = dict(N=N, eps=4.0, pml=20, mask=30, x=x)
+    for pol in ("TE", "TM"):
+        F = getattr(sim, "solve_total_field_" + pol)()
+        A = getattr(sim, "_A_" + pol)
+        out[f"y_{pol}"] = A @ x
+        out[f"b_{pol}"] = np.asarray((sim.Q @ A - A @ sim.Q) @ sim.source).ravel()
+        out[f"F_{pol}"] = F
+    np.savez_compressed(os.path.join(HERE, "scatter_small.npz"), **out)
+
+
+def scatter_cfg1():
+    N = 300
+    sim = _ref_sim(N, -1e6, 40, 80)
+    out = dict(N=N)
+    for pol in ("TM", "TE"):
+        F = getattr(sim, "solve_total_field_" + pol)()
+        out[f"probe_{pol}"] = F[150, 75]
+        out[f"max_{pol}"] = np.abs(F).max()
+        out[f"norm_{pol}"] = np.linalg.norm(F)
+        out[f"dec_{pol}"] = F[::10, ::10].copy()
+    np.savez_compressed(os.path.join(HERE, "scatter_cfg1.npz"), **out)
+
+
+if __name__ == "__main__":
+    yee_fixture()
+    scatter_small()
+    scatter_cfg1()
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -1,0 +1,72 @@
+"""Pins the oracle (oracle/*.py) against the UNMODIFIED reference imported from /root/reference.
+Runs in the build container only (skipped where the reference tree is absent)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from conftest import same_sparse
+from oracle import ref_loader, scattering_oracle as so, yee_oracle
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present")
+
+
+@pytest.mark.parametrize("folder", ["Scattering", "Band_Diagram_Solver"])
+def test_yeeder2d_bitwise(folder):
+    ref = ref_loader.ref_yeeder2d(folder)
+    rng = np.random.default_rng(1)
+    n = 0
+    for Nx, Ny in itertools.product([1, 2, 3, 4, 7, 16, 33], repeat=2):
+        for bc in itertools.product([0, 1], repeat=2):
+            for kinc in (None, [0.3, 0.7], rng.standard_normal(2)):
+                res = [0.5, 0.25] if kinc is None else list(rng.uniform(0.01, 1, 2))
+                R = ref([Nx, Ny], res, list(bc), kinc)
+                O = yee_oracle.yeeder2d([Nx, Ny], res, list(bc), kinc)
+                for r, o in zip(R, O):
+                    assert same_sparse(r, o), (Nx, Ny, bc, kinc)
+                    n += 1
+    assert n == 7 * 7 * 4 * 3 * 4
+
+
+@pytest.mark.parametrize("N,eps,pw,mask", [(96, 4.0, 16, 24), (128, -1e6, 20, 40)])
+def test_scattering_pieces(N, eps, pw, mask):
+    mod = ref_loader.load("Scattering_Solver_2D")
+    f0 = 10e9
+    lam = 299792458 / f0
+    sim = mod.FDFD2DScatteringSolver(frequency=f0, x_range=N / 50 * lam, y_range=N / 50 * lam, Nx=N, Ny=N)
+    sim.add_object(er_tensor=eps, mr_tensor=1.0, region_mask=(sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
+    sim.add_UPML(pml_width=pw, sigma_max=10)
+    sim.add_mask(value=mask)
+    sim.add_source(src_type="plane_wave", angle_deg=45.0, polarization="TE")
+    p = so.cylinder_problem(N, eps_r=eps, pml_width=pw, mask=mask)
+    for k in p.mats:
+        assert np.array_equal(p.mats[k], getattr(sim, k))
+    assert np.array_equal(p.source, sim.source)
+    assert np.array_equal(p.q, sim.Q.diagonal())
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(p.N) + 1j * rng.standard_normal(p.N)
+    for pol in ("TE", "TM"):
+        F = getattr(sim, "solve_total_field_" + pol)()
+        Aref = getattr(sim, "_A_" + pol)
+        A = so.build_A(p, pol)
+        assert A.format == Aref.format and (A != Aref).nnz == 0
+        bref = np.asarray((sim.Q @ Aref - Aref @ sim.Q) @ sim.source).ravel()
+        assert np.array_equal(so.rhs(A, p), bref)
+        b2 = so.rhs_matrix_free(p, pol)
+        # cancellation: both terms of Q(As) - A(Qs) are O(|A s|) (1e6 inside the eps=-1e6 cylinder)
+        assert np.linalg.norm(b2 - bref) <= 1e-14 * np.linalg.norm(Aref @ sim.source)
+        y = so.apply_stencil(pol, *so.stencil_coefficients(p, pol), x).ravel()
+        yr = Aref @ x
+        assert np.linalg.norm(y - yr) <= 1e-14 * np.linalg.norm(yr)
+        Fo = so.solve_total_field(p, pol, A)
+        assert np.linalg.norm(Fo - F) <= 1e-12 * np.linalg.norm(F)
+
+
+def test_point_source_matches():
+    mod = ref_loader.load("Scattering_Solver_2D")
+    sim = mod.FDFD2DScatteringSolver(10e9, 0.06, 0.05, 40, 30)
+    p = so.make_problem(10e9, 0.06, 0.05, 40, 30)
+    for pol in ("TE", "TM"):
+        sim.add_source("point", polarization=pol, location=(0.001, -0.002), amplitude=2.0)
+        so.add_source(p, "point", polarization=pol, location=(0.001, -0.002), amplitude=2.0)
+        assert np.array_equal(sim.source, p.source)
