@@ -206,6 +206,23 @@ extern "C" int fdfd_krylov_solve(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts,
     return s;
 }
 
+extern "C" int fdfd_precond_apply(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts, const void* v,
+                                  void* z, void* stream) {
+    FDFD_CHECK_ARG(h && opts && v && z, "null pointer");
+    Helm2D& A = h->op;
+    cudaStream_t st = (cudaStream_t)stream;
+    Precond* M = nullptr;
+    int s = FDFD_OK;
+    if (opts->precond == FDFD_PRECOND_JACOBI) s = make_jacobi_precond(A, &M, st);
+    else if (opts->precond == FDFD_PRECOND_MG) s = make_mg_precond(A, *opts, &M, st);
+    else { set_error("fdfd_precond_apply: no preconditioner selected"); s = FDFD_ERR_ARG; }
+    if (s != FDFD_OK) return s;
+    s = M->apply(v, z, st);
+    cudaStreamSynchronize(st);
+    delete M;
+    return s;
+}
+
 extern "C" int fdfd_krylov_solve_host(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts,
                                       const void* b_host, void* x_host, double* info) {
     FDFD_CHECK_ARG(h && opts && b_host && x_host, "null pointer");

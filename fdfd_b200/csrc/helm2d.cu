@@ -53,6 +53,14 @@ __global__ void __launch_bounds__(256) helm2d_march_kernel(HelmArgs<C> a) {
 
     const C* xcol = a.x + i;
     const C* cbcol = a.cb + i;
+    // APPLY_SMOOTH: is this column relaxed by y-lines?
+    bool in_strip = false;
+    int line_idx = 0, line_nl = 0;
+    if (MODE == APPLY_SMOOTH) {
+        line_nl = a.strip_lo + a.strip_hi;
+        if (i < a.strip_lo) { in_strip = true; line_idx = i; }
+        else if (i >= Nx - a.strip_hi) { in_strip = true; line_idx = a.strip_lo + (i - (Nx - a.strip_hi)); }
+    }
 
     // ---- prime the register window --------------------------------------------------------
     C xs, xc, cb_lo;  // cb_lo: TE -> cb[j-1] ; TM -> cb[j]
@@ -136,6 +144,14 @@ __global__ void __launch_bounds__(256) helm2d_march_kernel(HelmArgs<C> a) {
             if (MODE == APPLY_JACOBI) {
                 C r = csub(ld_stream(a.b + row + i), ax);
                 out = cadd(xc, cscale(a.omega, cdiv(r, dg)));
+            } else if (MODE == APPLY_SMOOTH) {
+                C r = csub(ld_stream(a.b + row + i), ax);
+                if (in_strip) {
+                    out = xc;
+                    a.line_rhs[(int64_t)(a.row0 + j) * line_nl + line_idx] = r;
+                } else {
+                    out = cadd(xc, cscale(a.omega, cdiv(r, dg)));
+                }
             } else if (MODE == APPLY_DINV) {
                 out = cdiv(mk<C>(1, 0), dg);
             } else {
@@ -152,19 +168,18 @@ __global__ void __launch_bounds__(256) helm2d_march_kernel(HelmArgs<C> a) {
 
 struct Variant { int bx, ry; };
 static const Variant kVariants[] = {
-    {128, 32}, {128, 16}, {128, 64}, {256, 32}, {256, 16}, {64, 32}, {128, 8}, {256, 64}, {128, 128},
+    {128, 8}, {128, 16}, {128, 32}, {256, 8}, {256, 16}, {64, 8}, {128, 4}, {64, 16}, {256, 4},
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
 template <typename C>
-int helm2d_launch(const Helm2D& op, int mode, const C* x, C* y, const C* b, const C* ca,
-                  const C* cb, const C* cd, double shift_re, double shift_im, double omega,
-                  cudaStream_t stream) {
+HelmArgs<C> helm2d_args(const Helm2D& op, const C* x, C* y, const C* b, const C* ca, const C* cb,
+                        const C* cd, double shift_re, double shift_im, double omega) {
     using R = typename real_of<C>::type;
     HelmArgs<C> a;
     a.x = x; a.y = y; a.b = b; a.ca = ca; a.cb = cb; a.cd = cd;
     a.Nx = op.Nx; a.Ny = op.Ny;
-    a.bcx = (op.bcx == FDFD_BC_BLOCH && op.Nx > 0) ? 1 : 0;
+    a.bcx = (op.bcx == FDFD_BC_BLOCH) ? 1 : 0;
     a.sx = (R)op.sx; a.sy = (R)op.sy;
     a.phx = mk<C>((R)op.phase[0], (R)op.phase[1]);
     a.phy = mk<C>((R)op.phase[2], (R)op.phase[3]);
@@ -172,6 +187,7 @@ int helm2d_launch(const Helm2D& op, int mode, const C* x, C* y, const C* b, cons
     a.phy2 = (R)(op.phase[2] * op.phase[2] + op.phase[3] * op.phase[3]);
     a.shift = mk<C>((R)shift_re, (R)shift_im);
     a.omega = (R)omega;
+    a.strip_lo = a.strip_hi = 0; a.line_rhs = nullptr; a.row0 = 0;
     // ghost rows
     const bool first = op.j0 == 0, last = op.j0 + op.Ny == op.Ny_global;
     const bool sharded = op.Ny != op.Ny_global;
@@ -189,9 +205,15 @@ int helm2d_launch(const Helm2D& op, int mode, const C* x, C* y, const C* b, cons
         const bool bloch_y = op.bcy == FDFD_BC_BLOCH;
         if (!first || bloch_y) { a.x_south = (const C*)op.halo_south; a.south_wrap = first && bloch_y; }
         if (!last || bloch_y) { a.x_north = (const C*)op.halo_north; a.north_wrap = last && bloch_y; }
-        const bool need = TM ? (!last || op.bcy == FDFD_BC_BLOCH) : (!first || op.bcy == FDFD_BC_BLOCH);
+        const bool need = TM ? (!last || bloch_y) : (!first || bloch_y);
         if (need) a.cb_ghost = (const C*)op.cb_ghost_buf;
     }
+    return a;
+}
+
+template <typename C>
+int helm2d_launch_args(const Helm2D& op, int mode, HelmArgs<C>& a, cudaStream_t stream) {
+    const bool TM = op.pol == FDFD_POL_TM;
     const Variant v = kVariants[(op.variant >= 0 && op.variant < kNumVariants) ? op.variant : 0];
     int bx = v.bx;
     while (bx > 32 && bx / 2 >= op.Nx) bx /= 2;
@@ -206,6 +228,7 @@ int helm2d_launch(const Helm2D& op, int mode, const C* x, C* y, const C* b, cons
         case APPLY_JACOBI: LAUNCH_MODE(APPLY_JACOBI); break;
         case APPLY_DINV_AX: LAUNCH_MODE(APPLY_DINV_AX); break;
         case APPLY_DINV: LAUNCH_MODE(APPLY_DINV); break;
+        case APPLY_SMOOTH: LAUNCH_MODE(APPLY_SMOOTH); break;
         default: set_error("bad apply mode %d", mode); return FDFD_ERR_ARG;
     }
 #undef LAUNCH
@@ -214,12 +237,26 @@ int helm2d_launch(const Helm2D& op, int mode, const C* x, C* y, const C* b, cons
     return FDFD_OK;
 }
 
+template <typename C>
+int helm2d_launch(const Helm2D& op, int mode, const C* x, C* y, const C* b, const C* ca,
+                  const C* cb, const C* cd, double shift_re, double shift_im, double omega,
+                  cudaStream_t stream) {
+    HelmArgs<C> a = helm2d_args<C>(op, x, y, b, ca, cb, cd, shift_re, shift_im, omega);
+    return helm2d_launch_args<C>(op, mode, a, stream);
+}
+
 template int helm2d_launch<double2>(const Helm2D&, int, const double2*, double2*, const double2*,
                                     const double2*, const double2*, const double2*, double, double,
                                     double, cudaStream_t);
 template int helm2d_launch<float2>(const Helm2D&, int, const float2*, float2*, const float2*,
                                    const float2*, const float2*, const float2*, double, double,
                                    double, cudaStream_t);
+template HelmArgs<double2> helm2d_args<double2>(const Helm2D&, const double2*, double2*, const double2*,
+        const double2*, const double2*, const double2*, double, double, double);
+template HelmArgs<float2> helm2d_args<float2>(const Helm2D&, const float2*, float2*, const float2*,
+        const float2*, const float2*, const float2*, double, double, double);
+template int helm2d_launch_args<double2>(const Helm2D&, int, HelmArgs<double2>&, cudaStream_t);
+template int helm2d_launch_args<float2>(const Helm2D&, int, HelmArgs<float2>&, cudaStream_t);
 
 int helm2d_halo_exchange(Helm2D& op, const void* x, cudaStream_t stream) {
     if (op.Ny == op.Ny_global) return FDFD_OK;

@@ -13,6 +13,8 @@ enum ApplyMode {
     APPLY_JACOBI = 2,    // y = x + omega * (b - A x) / diag(A)      (damped-Jacobi sweep)
     APPLY_DINV_AX = 3,   // y = (A x) / diag(A)
     APPLY_DINV = 4,      // y = 1 / diag(A)              (x ignored)
+    APPLY_SMOOTH = 5,    // damped Jacobi outside the x-strips; inside them y = x and the residual
+                         // b - A x is written to the line-solver workspace (see mg.cu)
 };
 
 template <typename C>
@@ -36,6 +38,10 @@ struct HelmArgs {
     R phx2, phy2;        // |ph|^2 (1 for real Bloch vectors)
     C shift;             // cd is multiplied by (shift) — (1,0) for A, (b1, b2) for the shifted preconditioner
     R omega;             // Jacobi damping
+    // APPLY_SMOOTH: columns [0, strip_lo) and [Nx - strip_hi, Nx) belong to y-line relaxation
+    int strip_lo, strip_hi;
+    C* line_rhs;         // workspace [row][line], line = strip column index, row stride = strip_lo + strip_hi
+    int row0;            // global row of local row 0 (sharded lines)
 };
 
 struct Helm2D {
@@ -55,11 +61,19 @@ struct Helm2D {
     size_t elem() const { return dtype == FDFD_C128 ? 16 : 8; }
 };
 
+// Fill the kernel argument block for operator `op` (ghost rows resolved from op's halo buffers).
+template <typename C>
+HelmArgs<C> helm2d_args(const Helm2D& op, const C* x, C* y, const C* b, const C* ca, const C* cb,
+                        const C* cd, double shift_re, double shift_im, double omega);
+template <typename C>
+int helm2d_launch_args(const Helm2D& op, int mode, HelmArgs<C>& a, cudaStream_t stream);
+
 // Launch one stencil pass.  x_south/x_north/cb_ghost resolved by the caller (halo exchange).
 template <typename C>
 int helm2d_launch(const Helm2D& op, int mode, const C* x, C* y, const C* b,
                   const C* ca, const C* cb, const C* cd, double shift_re, double shift_im,
                   double omega, cudaStream_t stream);
+int helm2d_halo_exchange(Helm2D& op, const void* x, cudaStream_t stream);
 
 // y = A x including halo exchange when sharded (dispatches on dtype).
 int helm2d_apply(Helm2D& op, int mode, const void* x, void* y, const void* b, double omega,

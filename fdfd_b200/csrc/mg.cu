@@ -1,0 +1,595 @@
+// K5 — complex shifted-Laplacian multigrid preconditioner for the scattering operator.
+//
+// M = A with its diagonal term multiplied by (beta1 + j beta2)  (shift folded into the K2
+// kernel argument `shift`), approximated by one multigrid cycle:
+//   * cell-centred 2x coarsening, re-discretised coarse operators of the same TE/TM stencil
+//     type: face coefficients are the arithmetic mean of the two fine faces on the coarse
+//     face, the diagonal term the mean of the four fine cells, sx, sy divided by 4;
+//   * the Dirichlet wall (TE: far end, TM: near end) keeps its physical position: the coarse
+//     wall-face coefficient is scaled by delta_l / delta_{l+1}, delta = distance of the wall
+//     cell centre to the wall in units of the level spacing (1 on the finest level,
+//     delta_{l+1} = (delta_l + 1/2) / 2);
+//   * restriction = mean of the four fine residuals, prolongation = cell-centred bilinear
+//     (clamped at the flux-free side, interpolating to 0 at the wall);
+//   * smoother = damped point Jacobi, except inside the absorbing layers where the UPML makes
+//     the operator strongly anisotropic with complex coefficients of opposite phase (point
+//     relaxation diverges there): columns of the x-layers are relaxed by y-line (tridiagonal)
+//     solves, then rows of the y-layers by x-line solves (alternating-direction line Jacobi);
+//   * the tridiagonal systems are static, so they are factorised once per hierarchy with a
+//     partitioned (Wang / SPIKE) scheme: P chunks per line, local LU + spikes, and a dense
+//     inverse of the 2P x 2P interface system.  A solve is three fully parallel kernels
+//     (chunk-local forward/backward substitution, interface mat-vec, spike correction).
+// The algorithm is restated in numpy in oracle/mg_oracle.py, which the GPU tests compare with.
+#include "krylov.cuh"
+#include "comm.cuh"
+
+#include <vector>
+
+namespace fdfd {
+
+namespace {
+
+constexpr int kMaxChunks = 32;
+
+// ---------------------------------------------------------------------------------------------
+// matrix entries of the operator at one grid point (Dirichlet / flux-free walls only)
+template <typename C>
+struct PointCoefs { C kw, ke, ks, kn, dg; };
+
+template <typename C, bool TM>
+__device__ __forceinline__ PointCoefs<C> point_coefs(const C* ca, const C* cb, const C* cd, int Nx, int Ny,
+        typename real_of<C>::type sx, typename real_of<C>::type sy, C shift, int i, int j) {
+    PointCoefs<C> p;
+    const int64_t n = (int64_t)j * Nx + i;
+    C fw, fe, fs, fn;          // face coefficients incl. wall faces
+    bool has_w, has_e, has_s, has_n;   // neighbour unknown exists
+    if (TM) {
+        fw = ca[n]; has_w = i > 0;
+        has_e = i < Nx - 1; fe = has_e ? ca[n + 1] : czero<C>();
+        fs = cb[n]; has_s = j > 0;
+        has_n = j < Ny - 1; fn = has_n ? cb[n + Nx] : czero<C>();
+    } else {
+        has_w = i > 0; fw = has_w ? ca[n - 1] : czero<C>();
+        fe = ca[n]; has_e = i < Nx - 1;
+        has_s = j > 0; fs = has_s ? cb[n - Nx] : czero<C>();
+        fn = cb[n]; has_n = j < Ny - 1;
+    }
+    p.kw = has_w ? cscale(sx, fw) : czero<C>();
+    p.ke = has_e ? cscale(sx, fe) : czero<C>();
+    p.ks = has_s ? cscale(sy, fs) : czero<C>();
+    p.kn = has_n ? cscale(sy, fn) : czero<C>();
+    p.dg = cadd(cscale(-sx, cadd(fw, fe)), cscale(-sy, cadd(fs, fn)));
+    if (cd) p.dg = cfma(shift, cd[n], p.dg);
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// line sets
+template <typename C>
+struct LineSet {
+    int dir = 0;          // 0: lines along y inside x-strips ; 1: lines along x inside y-strips
+    int lo = 0, hi = 0;   // strip widths (number of lines at the low / high end)
+    int nl = 0;           // lo + hi
+    int len = 0;          // unknowns per line
+    int m = 0, P = 0;     // chunk length, chunks per line
+    C *fl = nullptr, *fc = nullptr, *fip = nullptr, *sv = nullptr, *sw = nullptr;  // [len][nl]
+    C *rinv = nullptr;    // [nl][2P*2P] column-major
+    C *g = nullptr;       // [len][nl] right-hand side / solution workspace
+    C *ifg = nullptr, *ifu = nullptr;  // [nl][2P]
+    void release() {
+        cudaFree(fl); cudaFree(fc); cudaFree(fip); cudaFree(sv); cudaFree(sw); cudaFree(rinv);
+        cudaFree(g); cudaFree(ifg); cudaFree(ifu);
+        fl = fc = fip = sv = sw = rinv = g = ifg = ifu = nullptr;
+    }
+};
+
+template <typename C>
+struct LineView {
+    int dir, lo, hi, nl, len, m, P, Nx, Ny;
+    C *fl, *fc, *fip, *sv, *sw, *rinv, *g, *ifg, *ifu;
+};
+
+template <typename C>
+LineView<C> view(const LineSet<C>& s, int Nx, int Ny) {
+    LineView<C> v;
+    v.dir = s.dir; v.lo = s.lo; v.hi = s.hi; v.nl = s.nl; v.len = s.len; v.m = s.m; v.P = s.P;
+    v.Nx = Nx; v.Ny = Ny;
+    v.fl = s.fl; v.fc = s.fc; v.fip = s.fip; v.sv = s.sv; v.sw = s.sw; v.rinv = s.rinv;
+    v.g = s.g; v.ifg = s.ifg; v.ifu = s.ifu;
+    return v;
+}
+
+// grid coordinate of (line l, position t)
+template <typename C>
+__device__ __forceinline__ void line_point(const LineView<C>& v, int l, int t, int& i, int& j) {
+    if (v.dir == 0) { i = l < v.lo ? l : v.Nx - v.hi + (l - v.lo); j = t; }
+    else { j = l < v.lo ? l : v.Ny - v.hi + (l - v.lo); i = t; }
+}
+
+// tridiagonal entries of every line: fl <- sub, fip <- diag, fc <- super
+template <typename C, bool TM>
+__global__ void line_extract_kernel(LineView<C> v, const C* ca, const C* cb, const C* cd,
+        typename real_of<C>::type sx, typename real_of<C>::type sy, C shift) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)v.nl * v.len) return;
+    const int l = (int)(idx % v.nl), t = (int)(idx / v.nl);
+    int i, j;
+    line_point(v, l, t, i, j);
+    PointCoefs<C> p = point_coefs<C, TM>(ca, cb, cd, v.Nx, v.Ny, sx, sy, shift, i, j);
+    v.fl[idx] = v.dir == 0 ? p.ks : p.kw;
+    v.fc[idx] = v.dir == 0 ? p.kn : p.ke;
+    v.fip[idx] = p.dg;
+}
+
+// chunk-local LU (Thomas) + spikes; one thread per (line, chunk)
+template <typename C>
+__global__ void line_factor_kernel(LineView<C> v) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= v.nl * v.P) return;
+    const int l = idx % v.nl, k = idx / v.nl;
+    const int t0 = k * v.m, t1 = min(v.len, t0 + v.m);
+    if (t0 >= t1) return;
+    const int64_t nl = v.nl;
+    const C one = mk<C>(1, 0);
+    const C a_first = v.fl[t0 * nl + l];
+    const C c_last = v.fc[(t1 - 1) * nl + l];
+    C piv = v.fip[t0 * nl + l];
+    C ip = cdiv(one, piv);
+    v.fip[t0 * nl + l] = ip;
+    v.fl[t0 * nl + l] = czero<C>();
+    // forward elimination; V's forward sweep rides along (rhs = a_first * e_first)
+    C yv = a_first;
+    v.sv[t0 * nl + l] = yv;
+    for (int t = t0 + 1; t < t1; ++t) {
+        const C lm = cmul(v.fl[t * nl + l], ip);           // sub / previous pivot
+        piv = csub(v.fip[t * nl + l], cmul(lm, v.fc[(t - 1) * nl + l]));
+        ip = cdiv(one, piv);
+        v.fl[t * nl + l] = lm;
+        v.fip[t * nl + l] = ip;
+        yv = cneg(cmul(lm, yv));
+        v.sv[t * nl + l] = yv;
+    }
+    // backward substitution for both spikes (W: rhs = c_last * e_last, forward sweep is trivial)
+    C ev = cmul(v.sv[(t1 - 1) * nl + l], ip);
+    C ew = cmul(c_last, ip);
+    v.sv[(t1 - 1) * nl + l] = ev;
+    v.sw[(t1 - 1) * nl + l] = ew;
+    for (int t = t1 - 2; t >= t0; --t) {
+        const C c = v.fc[t * nl + l], q = v.fip[t * nl + l];
+        ev = cmul(csub(v.sv[t * nl + l], cmul(c, ev)), q);
+        ew = cmul(cneg(cmul(c, ew)), q);
+        v.sv[t * nl + l] = ev;
+        v.sw[t * nl + l] = ew;
+    }
+}
+
+// interface system R (2P x 2P, unknowns f_0, z_0, f_1, z_1, ...) and its inverse by Gauss-Jordan
+// in shared memory; one CTA per line.  R = I + spike tips, diagonally dominant -> no pivoting.
+template <typename C>
+__global__ void line_reduced_inverse_kernel(LineView<C> v) {
+    extern __shared__ unsigned char smem_raw[];
+    C* R = reinterpret_cast<C*>(smem_raw);
+    const int l = blockIdx.x;
+    const int n = 2 * v.P;
+    const int64_t nl = v.nl;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) R[e] = (e / n == e % n) ? mk<C>(1, 0) : czero<C>();
+    __syncthreads();
+    for (int k = threadIdx.x; k < v.P; k += blockDim.x) {
+        const int t0 = k * v.m, t1 = min(v.len, t0 + v.m);
+        if (t0 >= t1) continue;
+        if (k > 0) {       // coupling to z_{k-1}
+            R[(2 * k) * n + 2 * (k - 1) + 1] = v.sv[t0 * nl + l];
+            R[(2 * k + 1) * n + 2 * (k - 1) + 1] = v.sv[(t1 - 1) * nl + l];
+        }
+        if (k < v.P - 1 && (k + 1) * v.m < v.len) {   // coupling to f_{k+1}
+            R[(2 * k) * n + 2 * (k + 1)] = v.sw[t0 * nl + l];
+            R[(2 * k + 1) * n + 2 * (k + 1)] = v.sw[(t1 - 1) * nl + l];
+        }
+    }
+    __syncthreads();
+    __shared__ double2 piv_sh;
+    for (int p = 0; p < n; ++p) {
+        if (threadIdx.x == 0) {
+            const C d = R[p * n + p];
+            const C ip = cdiv(mk<C>(1, 0), d);
+            piv_sh = make_double2((double)ip.x, (double)ip.y);
+            R[p * n + p] = mk<C>(1, 0);
+        }
+        __syncthreads();
+        const C ip = mk<C>((typename real_of<C>::type)piv_sh.x, (typename real_of<C>::type)piv_sh.y);
+        for (int c = threadIdx.x; c < n; c += blockDim.x) R[p * n + c] = cmul(R[p * n + c], ip);
+        __syncthreads();
+        // eliminate column p from every other row: each thread owns rows r (loop) and all columns
+        for (int r = threadIdx.x; r < n; r += blockDim.x) {
+            if (r == p) continue;
+            const C f = R[r * n + p];
+            R[r * n + p] = czero<C>();
+            for (int c = 0; c < n; ++c) R[r * n + c] = csub(R[r * n + c], cmul(f, R[p * n + c]));
+        }
+        __syncthreads();
+    }
+    C* out = v.rinv + (int64_t)l * n * n;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int row = e % n, col = e / n;
+        out[col * n + row] = R[row * n + col];     // column-major
+    }
+}
+
+// phase A: chunk-local solve, in place in g; interface values to ifg
+template <typename C>
+__global__ void __launch_bounds__(128) line_local_solve_kernel(LineView<C> v) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= v.nl * v.P) return;
+    const int l = idx % v.nl, k = idx / v.nl;
+    const int t0 = k * v.m, t1 = min(v.len, t0 + v.m);
+    if (t0 >= t1) return;
+    const int64_t nl = v.nl;
+    C y = v.g[t0 * nl + l];
+#pragma unroll 4
+    for (int t = t0 + 1; t < t1; ++t) {
+        y = csub(v.g[t * nl + l], cmul(v.fl[t * nl + l], y));
+        v.g[t * nl + l] = y;
+    }
+    C e = cmul(y, v.fip[(t1 - 1) * nl + l]);
+    v.g[(t1 - 1) * nl + l] = e;
+    const C e_last = e;
+#pragma unroll 4
+    for (int t = t1 - 2; t >= t0; --t) {
+        e = cmul(csub(v.g[t * nl + l], cmul(v.fc[t * nl + l], e)), v.fip[t * nl + l]);
+        v.g[t * nl + l] = e;
+    }
+    if (v.P > 1) {
+        v.ifg[(int64_t)l * 2 * v.P + 2 * k] = e;
+        v.ifg[(int64_t)l * 2 * v.P + 2 * k + 1] = e_last;
+    }
+}
+
+// phase B: u = R^-1 g_interface ; one warp per line
+template <typename C>
+__global__ void line_reduced_kernel(LineView<C> v) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= v.nl) return;
+    const int n = 2 * v.P;
+    const C* Ri = v.rinv + (int64_t)warp * n * n;
+    const C* gi = v.ifg + (int64_t)warp * n;
+    for (int row = lane; row < n; row += 32) {
+        C acc = czero<C>();
+        for (int q = 0; q < n; ++q) acc = cfma(Ri[q * n + row], gi[q], acc);
+        v.ifu[(int64_t)warp * n + row] = acc;
+    }
+}
+
+// phase C: spike correction; dir 0 also applies the update x += omega * e
+template <typename C>
+__global__ void line_correct_kernel(LineView<C> v, C* x, typename real_of<C>::type omega) {
+    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)v.nl * v.len) return;
+    const int l = (int)(idx % v.nl), t = (int)(idx / v.nl);
+    C e = v.g[idx];
+    if (v.P > 1) {
+        const int k = t / v.m;
+        const C* u = v.ifu + (int64_t)l * 2 * v.P;
+        if (k > 0) e = csub(e, cmul(v.sv[idx], u[2 * (k - 1) + 1]));
+        if (k < v.P - 1 && (k + 1) * v.m < v.len) e = csub(e, cmul(v.sw[idx], u[2 * (k + 1)]));
+    }
+    if (v.dir == 0) {
+        int i, j;
+        line_point(v, l, t, i, j);
+        const int64_t n = (int64_t)j * v.Nx + i;
+        x[n] = cadd(x[n], cscale(omega, e));
+    } else {
+        v.g[idx] = e;
+    }
+}
+
+// x-lines: residual of the strip rows, written transposed ([t = i][line = row]) via a smem tile
+template <typename C, bool TM>
+__global__ void __launch_bounds__(256) strip_rows_resid_kernel(LineView<C> v, const C* x, const C* b,
+        const C* ca, const C* cb, const C* cd, typename real_of<C>::type sx,
+        typename real_of<C>::type sy, C shift) {
+    __shared__ C tile[32][33];
+    const int i0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int l = l0 + r, i = i0 + tx;
+        C val = czero<C>();
+        if (l < v.nl && i < v.Nx) {
+            const int j = l < v.lo ? l : v.Ny - v.hi + (l - v.lo);
+            PointCoefs<C> p = point_coefs<C, TM>(ca, cb, cd, v.Nx, v.Ny, sx, sy, shift, i, j);
+            const int64_t n = (int64_t)j * v.Nx + i;
+            C ax = cmul(p.dg, x[n]);
+            if (i > 0) ax = cfma(p.kw, x[n - 1], ax);
+            if (i < v.Nx - 1) ax = cfma(p.ke, x[n + 1], ax);
+            if (j > 0) ax = cfma(p.ks, x[n - v.Nx], ax);
+            if (j < v.Ny - 1) ax = cfma(p.kn, x[n + v.Nx], ax);
+            val = csub(b[n], ax);
+        }
+        tile[r][tx] = val;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, l = l0 + tx;
+        if (l < v.nl && i < v.Nx) v.g[(int64_t)i * v.nl + l] = tile[tx][r];
+    }
+}
+
+// x-lines: x[row(l)][i] += omega * e[i][l]   (transposed through a smem tile)
+template <typename C>
+__global__ void __launch_bounds__(256) strip_rows_scatter_kernel(LineView<C> v, C* x,
+        typename real_of<C>::type omega) {
+    __shared__ C tile[32][33];
+    const int i0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, l = l0 + tx;
+        tile[r][tx] = (l < v.nl && i < v.Nx) ? v.g[(int64_t)i * v.nl + l] : czero<C>();
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int l = l0 + r, i = i0 + tx;
+        if (l < v.nl && i < v.Nx) {
+            const int j = l < v.lo ? l : v.Ny - v.hi + (l - v.lo);
+            const int64_t n = (int64_t)j * v.Nx + i;
+            x[n] = cadd(x[n], cscale(omega, tile[tx][r]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// grid transfer and coarse coefficients
+template <typename C, bool TM>
+__global__ void coarsen_coefs_kernel(int Nxc, int Nyc, const C* ca, const C* cb, const C* cd,
+        C* cac, C* cbc, C* cdc, typename real_of<C>::type wall_mult) {
+    using R = typename real_of<C>::type;
+    const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= Nxc || J >= Nyc) return;
+    const int Nx = 2 * Nxc;
+    const int ix = TM ? 0 : 1;
+    const int64_t f00 = (int64_t)(2 * J) * Nx + 2 * I;
+    C a = cscale((R)0.5, cadd(ca[f00 + ix], ca[f00 + Nx + ix]));
+    C b = cscale((R)0.5, cadd(cb[f00 + (int64_t)ix * Nx], cb[f00 + (int64_t)ix * Nx + 1]));
+    if (TM) { if (I == 0) a = cscale(wall_mult, a); if (J == 0) b = cscale(wall_mult, b); }
+    else { if (I == Nxc - 1) a = cscale(wall_mult, a); if (J == Nyc - 1) b = cscale(wall_mult, b); }
+    const int64_t c = (int64_t)J * Nxc + I;
+    cac[c] = a; cbc[c] = b;
+    if (cd) cdc[c] = cscale((R)0.25, cadd(cadd(cd[f00], cd[f00 + 1]), cadd(cd[f00 + Nx], cd[f00 + Nx + 1])));
+}
+
+template <typename C>
+__global__ void restrict_kernel(int Nxc, int Nyc, const C* rf, C* rc) {
+    using R = typename real_of<C>::type;
+    const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y * blockDim.y + threadIdx.y;
+    if (I >= Nxc || J >= Nyc) return;
+    const int Nx = 2 * Nxc;
+    const int64_t f = (int64_t)(2 * J) * Nx + 2 * I;
+    rc[(int64_t)J * Nxc + I] = cscale((R)0.25, cadd(cadd(rf[f], rf[f + 1]), cadd(rf[f + Nx], rf[f + Nx + 1])));
+}
+
+// x_f += P e_c ; bilinear, clamped on the flux-free side, linear to zero at the wall
+template <typename C, bool TM>
+__global__ void prolong_add_kernel(int Nxc, int Nyc, const C* ec, C* xf, typename real_of<C>::type wq) {
+    using R = typename real_of<C>::type;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int Nx = 2 * Nxc, Ny = 2 * Nyc;
+    if (i >= Nx || j >= Ny) return;
+    // 1-D weights: value = w0 * e[I0] + w1 * e[I1]
+    auto axis = [&](int f, int Nc, int& I0, int& I1, R& w0, R& w1) {
+        const int I = f >> 1;
+        I0 = I; w0 = (R)0.75; w1 = (R)0.25;
+        I1 = (f & 1) ? I + 1 : I - 1;
+        if (I1 < 0) { if (TM) { w0 = wq; w1 = 0; } I1 = 0; if (!TM) { I1 = I; } }
+        else if (I1 >= Nc) { if (!TM) { w0 = wq; w1 = 0; } I1 = Nc - 1; if (TM) { I1 = I; } }
+    };
+    int I0, I1, J0, J1; R wx0, wx1, wy0, wy1;
+    axis(i, Nxc, I0, I1, wx0, wx1);
+    axis(j, Nyc, J0, J1, wy0, wy1);
+    C v = cscale(wy0, cadd(cscale(wx0, ec[(int64_t)J0 * Nxc + I0]), cscale(wx1, ec[(int64_t)J0 * Nxc + I1])));
+    v = cadd(v, cscale(wy1, cadd(cscale(wx0, ec[(int64_t)J1 * Nxc + I0]), cscale(wx1, ec[(int64_t)J1 * Nxc + I1]))));
+    const int64_t n = (int64_t)j * Nx + i;
+    xf[n] = cadd(xf[n], v);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename C>
+struct Level {
+    Helm2D op;
+    C *ca = nullptr, *cb = nullptr, *cd = nullptr;   // owned when own_coefs
+    bool own_coefs = false;
+    C *x = nullptr, *b = nullptr, *r = nullptr, *t = nullptr;
+    bool own_xb = true;
+    double delta = 1.0;
+    LineSet<C> ylines, xlines;
+};
+
+template <typename C>
+struct MGPrecond : Precond {
+    std::vector<Level<C>> L;
+    fdfd_krylov_opts o;
+    double shift_re = 1.0, shift_im = 0.5;
+    cudaStream_t setup_stream = 0;
+
+    ~MGPrecond() override {
+        for (size_t l = 0; l < L.size(); ++l) {
+            Level<C>& v = L[l];
+            if (v.own_coefs) { cudaFree(v.ca); cudaFree(v.cb); cudaFree(v.cd); }
+            if (l > 0) { cudaFree(v.x); cudaFree(v.b); }
+            cudaFree(v.r); cudaFree(v.t);
+            v.ylines.release(); v.xlines.release();
+        }
+    }
+
+    bool TM() const { return L[0].op.pol == FDFD_POL_TM; }
+    C shift() const { return mk<C>((typename real_of<C>::type)shift_re, (typename real_of<C>::type)shift_im); }
+
+    int setup_lines(Level<C>& lv, LineSet<C>& s, int dir, int lo, int hi, cudaStream_t st) {
+        using R = typename real_of<C>::type;
+        const int Nx = lv.op.Nx, Ny = lv.op.Ny;
+        const int across = dir == 0 ? Nx : Ny;
+        if (lo + hi > across) { lo = across; hi = 0; }
+        s.dir = dir; s.lo = lo; s.hi = hi; s.nl = lo + hi;
+        s.len = dir == 0 ? Ny : Nx;
+        if (s.nl == 0) return FDFD_OK;
+        int P = s.len >= 512 ? kMaxChunks : (s.len >= 128 ? 8 : 1);
+        s.m = (s.len + P - 1) / P;
+        s.P = (s.len + s.m - 1) / s.m;
+        const size_t e = (size_t)s.len * s.nl * sizeof(C);
+        FDFD_CUDA(cudaMalloc(&s.fl, e)); FDFD_CUDA(cudaMalloc(&s.fc, e)); FDFD_CUDA(cudaMalloc(&s.fip, e));
+        FDFD_CUDA(cudaMalloc(&s.sv, e)); FDFD_CUDA(cudaMalloc(&s.sw, e)); FDFD_CUDA(cudaMalloc(&s.g, e));
+        FDFD_CUDA(cudaMemsetAsync(s.sv, 0, e, st)); FDFD_CUDA(cudaMemsetAsync(s.sw, 0, e, st));
+        const size_t ni = (size_t)s.nl * 2 * s.P;
+        FDFD_CUDA(cudaMalloc(&s.ifg, ni * sizeof(C))); FDFD_CUDA(cudaMalloc(&s.ifu, ni * sizeof(C)));
+        FDFD_CUDA(cudaMalloc(&s.rinv, ni * 2 * s.P * sizeof(C)));
+        LineView<C> v = view(s, Nx, Ny);
+        const int64_t tot = (int64_t)s.nl * s.len;
+        const int blocks = (int)((tot + 255) / 256);
+        if (TM()) line_extract_kernel<C, true><<<blocks, 256, 0, st>>>(v, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift());
+        else line_extract_kernel<C, false><<<blocks, 256, 0, st>>>(v, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift());
+        line_factor_kernel<C><<<(s.nl * s.P + 127) / 128, 128, 0, st>>>(v);
+        if (s.P > 1) {
+            const size_t smem = (size_t)4 * s.P * s.P * sizeof(C);
+            FDFD_CUDA(cudaFuncSetAttribute(line_reduced_inverse_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            line_reduced_inverse_kernel<C><<<s.nl, 128, smem, st>>>(v);
+        }
+        FDFD_CUDA(cudaGetLastError());
+        return FDFD_OK;
+    }
+
+    int line_solve(Level<C>& lv, LineSet<C>& s, C* x, double omega, cudaStream_t st) {
+        using R = typename real_of<C>::type;
+        LineView<C> v = view(s, lv.op.Nx, lv.op.Ny);
+        line_local_solve_kernel<C><<<(s.nl * s.P + 127) / 128, 128, 0, st>>>(v);
+        if (s.P > 1) line_reduced_kernel<C><<<(s.nl * 32 + 127) / 128, 128, 0, st>>>(v);
+        const int64_t tot = (int64_t)s.nl * s.len;
+        if (s.P > 1 || s.dir == 0)
+            line_correct_kernel<C><<<(int)((tot + 255) / 256), 256, 0, st>>>(v, x, (R)omega);
+        if (s.dir == 1) {
+            dim3 grid((lv.op.Nx + 31) / 32, (s.nl + 31) / 32);
+            strip_rows_scatter_kernel<C><<<grid, 256, 0, st>>>(v, x, (R)omega);
+        }
+        FDFD_CUDA(cudaGetLastError());
+        return FDFD_OK;
+    }
+
+    // one smoothing sweep on level l (x <- smoothed x); uses lv.t as ping-pong buffer
+    int smooth(int l, cudaStream_t st) {
+        using R = typename real_of<C>::type;
+        Level<C>& lv = L[l];
+        HelmArgs<C> a = helm2d_args<C>(lv.op, lv.x, lv.t, lv.b, lv.ca, lv.cb, lv.cd, shift_re, shift_im, o.mg_omega);
+        a.strip_lo = lv.ylines.lo; a.strip_hi = lv.ylines.hi; a.line_rhs = lv.ylines.g; a.row0 = 0;
+        FDFD_TRY(helm2d_launch_args<C>(lv.op, APPLY_SMOOTH, a, st));
+        if (lv.ylines.nl) FDFD_TRY(line_solve(lv, lv.ylines, lv.t, o.mg_omega, st));
+        std::swap(lv.x, lv.t);
+        if (lv.xlines.nl) {
+            LineView<C> v = view(lv.xlines, lv.op.Nx, lv.op.Ny);
+            dim3 grid((lv.op.Nx + 31) / 32, (lv.xlines.nl + 31) / 32);
+            if (TM()) strip_rows_resid_kernel<C, true><<<grid, 256, 0, st>>>(v, lv.x, lv.b, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift());
+            else strip_rows_resid_kernel<C, false><<<grid, 256, 0, st>>>(v, lv.x, lv.b, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift());
+            FDFD_TRY(line_solve(lv, lv.xlines, lv.x, o.mg_omega, st));
+        }
+        return FDFD_OK;
+    }
+
+    int cycle(int l, cudaStream_t st) {
+        using R = typename real_of<C>::type;
+        Level<C>& lv = L[l];
+        const int last = (int)L.size() - 1;
+        if (l == last) {
+            for (int s = 0; s < o.mg_coarse_its; ++s) FDFD_TRY(smooth(l, st));
+            return FDFD_OK;
+        }
+        for (int s = 0; s < o.mg_pre; ++s) FDFD_TRY(smooth(l, st));
+        FDFD_TRY(helm2d_launch<C>(lv.op, APPLY_RESID, lv.x, lv.r, lv.b, lv.ca, lv.cb, lv.cd, shift_re, shift_im, 0.0, st));
+        Level<C>& lc = L[l + 1];
+        dim3 bt(32, 8);
+        dim3 gc((lc.op.Nx + 31) / 32, (lc.op.Ny + 7) / 8);
+        restrict_kernel<C><<<gc, bt, 0, st>>>(lc.op.Nx, lc.op.Ny, lv.r, lc.b);
+        FDFD_CUDA(cudaMemsetAsync(lc.x, 0, (size_t)lc.op.n_local() * sizeof(C), st));
+        const int gamma = (o.mg_cycle == 2 || (o.mg_wfrom >= 0 && l + 1 >= o.mg_wfrom)) && (l + 1 < last) ? 2 : 1;
+        for (int g = 0; g < gamma; ++g) FDFD_TRY(cycle(l + 1, st));
+        const double dc = (lv.delta + 0.5) / 2.0;
+        const R wq = (R)(lv.delta / (2.0 * dc));
+        dim3 gf((lv.op.Nx + 31) / 32, (lv.op.Ny + 7) / 8);
+        if (TM()) prolong_add_kernel<C, true><<<gf, bt, 0, st>>>(lc.op.Nx, lc.op.Ny, lc.x, lv.x, wq);
+        else prolong_add_kernel<C, false><<<gf, bt, 0, st>>>(lc.op.Nx, lc.op.Ny, lc.x, lv.x, wq);
+        FDFD_CUDA(cudaGetLastError());
+        for (int s = 0; s < o.mg_post; ++s) FDFD_TRY(smooth(l, st));
+        return FDFD_OK;
+    }
+
+    int apply(const void* v, void* z, cudaStream_t st) override {
+        ++applies;
+        Level<C>& l0 = L[0];
+        const size_t bytes = (size_t)l0.op.n_local() * sizeof(C);
+        // level-0 rhs and solution live in solver-owned buffers; smoothing ping-pongs x <-> t, so
+        // work in the level's own x and copy out at the end
+        l0.b = (C*)v;
+        FDFD_CUDA(cudaMemsetAsync(l0.x, 0, bytes, st));
+        FDFD_TRY(cycle(0, st));
+        FDFD_CUDA(cudaMemcpyAsync(z, l0.x, bytes, cudaMemcpyDeviceToDevice, st));
+        return FDFD_OK;
+    }
+
+    int build(Helm2D& A, const fdfd_krylov_opts& opts, cudaStream_t st) {
+        using R = typename real_of<C>::type;
+        o = opts;
+        shift_re = opts.mg_shift_re; shift_im = opts.mg_shift_im;
+        FDFD_CHECK_ARG(A.Ny == A.Ny_global, "multigrid preconditioner: sharded operators not supported yet");
+        FDFD_CHECK_ARG(A.bcx == FDFD_BC_DIRICHLET && A.bcy == FDFD_BC_DIRICHLET, "multigrid preconditioner needs Dirichlet walls");
+        FDFD_CHECK_ARG(A.cd != nullptr, "multigrid preconditioner needs the diagonal term");
+        const int min_n = opts.mg_min_n > 2 ? opts.mg_min_n : 2;
+        int lx_lo = opts.line_x_lo, lx_hi = opts.line_x_hi, ly_lo = opts.line_y_lo, ly_hi = opts.line_y_hi;
+        Level<C> f;
+        f.op = A; f.op.halo_south = f.op.halo_north = f.op.cb_ghost_buf = nullptr; f.op.h_x = f.op.h_y = nullptr;
+        f.ca = (C*)A.ca; f.cb = (C*)A.cb; f.cd = (C*)A.cd; f.own_coefs = false; f.delta = 1.0;
+        L.push_back(f);
+        while (true) {
+            Level<C>& cur = L.back();
+            const int Nx = cur.op.Nx, Ny = cur.op.Ny;
+            const size_t bytes = (size_t)Nx * Ny * sizeof(C);
+            FDFD_CUDA(cudaMalloc(&cur.x, bytes)); FDFD_CUDA(cudaMalloc(&cur.r, bytes)); FDFD_CUDA(cudaMalloc(&cur.t, bytes));
+            if (L.size() > 1) FDFD_CUDA(cudaMalloc(&cur.b, bytes));
+            FDFD_TRY(setup_lines(cur, cur.ylines, 0, lx_lo, lx_hi, st));
+            FDFD_TRY(setup_lines(cur, cur.xlines, 1, ly_lo, ly_hi, st));
+            const bool max_levels = opts.mg_levels > 0 && (int)L.size() >= opts.mg_levels;
+            if (max_levels || (Nx & 1) || (Ny & 1) || Nx / 2 < min_n || Ny / 2 < min_n) break;
+            Level<C> c;
+            c.op = cur.op;
+            c.op.Nx = Nx / 2; c.op.Ny = Ny / 2; c.op.Ny_global = Ny / 2; c.op.j0 = 0;
+            c.op.sx = cur.op.sx / 4; c.op.sy = cur.op.sy / 4;
+            c.delta = (cur.delta + 0.5) / 2.0;
+            const size_t cb = (size_t)c.op.Nx * c.op.Ny * sizeof(C);
+            FDFD_CUDA(cudaMalloc(&c.ca, cb)); FDFD_CUDA(cudaMalloc(&c.cb, cb)); FDFD_CUDA(cudaMalloc(&c.cd, cb));
+            c.own_coefs = true;
+            const R mult = (R)(cur.delta / c.delta);
+            dim3 bt(32, 8), g((c.op.Nx + 31) / 32, (c.op.Ny + 7) / 8);
+            if (TM()) coarsen_coefs_kernel<C, true><<<g, bt, 0, st>>>(c.op.Nx, c.op.Ny, cur.ca, cur.cb, cur.cd, c.ca, c.cb, c.cd, mult);
+            else coarsen_coefs_kernel<C, false><<<g, bt, 0, st>>>(c.op.Nx, c.op.Ny, cur.ca, cur.cb, cur.cd, c.ca, c.cb, c.cd, mult);
+            FDFD_CUDA(cudaGetLastError());
+            c.op.ca = c.ca; c.op.cb = c.cb; c.op.cd = c.cd;
+            lx_lo = (lx_lo + 1) / 2; lx_hi = (lx_hi + 1) / 2; ly_lo = (ly_lo + 1) / 2; ly_hi = (ly_hi + 1) / 2;
+            L.push_back(c);
+        }
+        FDFD_CUDA(cudaStreamSynchronize(st));
+        return FDFD_OK;
+    }
+};
+
+}  // namespace
+
+int make_mg_precond(Helm2D& A, const fdfd_krylov_opts& opts, Precond** out, cudaStream_t stream) {
+    int s;
+    if (A.dtype == FDFD_C128) {
+        auto* M = new MGPrecond<double2>();
+        s = M->build(A, opts, stream);
+        if (s != FDFD_OK) { delete M; return s; }
+        *out = M;
+    } else {
+        auto* M = new MGPrecond<float2>();
+        s = M->build(A, opts, stream);
+        if (s != FDFD_OK) { delete M; return s; }
+        *out = M;
+    }
+    return FDFD_OK;
+}
+
+}  // namespace fdfd

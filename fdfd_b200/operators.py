@@ -154,6 +154,17 @@ class HelmholtzOperator2D:
         return x, d
 
 
+    def precond_apply(self, v, precond="mg", **opts):
+        """z = M^-1 v (one preconditioner application) — validation hook for the tests."""
+        torch = _torch()
+        o = _lib.default_opts(precond={"jacobi": _lib.PRECOND_JACOBI, "mg": _lib.PRECOND_MG}[precond], **opts)
+        v = v.to(device=self.device, dtype=self.tdtype).contiguous().reshape(-1)
+        z = torch.empty_like(v)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.fdfd_precond_apply(self._h, C.byref(o), v.data_ptr(), z.data_ptr(), self._stream()))
+        return z
+
+
 class SlabComm:
     """NCCL communicator for y-slab sharding; the 128-byte unique id travels through
     ``torch.distributed`` (any backend) from rank 0."""

@@ -143,6 +143,11 @@ int fdfd_krylov_solve(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts,
 int fdfd_krylov_solve_host(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts,
                            const void* b_host, void* x_host, double* info);
 
+/* z = M^-1 v: one application of the preconditioner `opts->precond` selects (device pointers).
+ * Exposed so the preconditioner can be validated on its own (tests/test_mg_gpu.py). */
+int fdfd_precond_apply(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts, const void* v, void* z,
+                       void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * multi-GPU plumbing: one process per GPU; the 128-byte NCCL unique id is produced by rank 0
  * (fdfd_comm_unique_id) and distributed by the host framework (torch.distributed).
