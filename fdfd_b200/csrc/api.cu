@@ -75,6 +75,7 @@ extern "C" int fdfd_helm2d_create(fdfd_helm2d_t** out, int dtype, int pol, int N
     if (phase) memcpy(op.phase, phase, sizeof(op.phase));
     else { op.phase[0] = 1; op.phase[1] = 0; op.phase[2] = 1; op.phase[3] = 0; }
     op.sx = sx; op.sy = sy; op.ca = ca; op.cb = cb; op.cd = cd;
+    op.shift_re = 1.0; op.shift_im = 0.0;
     op.comm = comm ? comm->c : nullptr;
     op.variant = 0;
     cudaStream_t st = (cudaStream_t)stream;
@@ -164,7 +165,9 @@ extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
     o->mg_shift_re = 1.0; o->mg_shift_im = 0.5;
     o->mg_omega = 0.8;
     o->mg_cycle = 1;
-    o->mg_coarse_its = 8;
+    o->mg_coarse_its = 0;          /* 0 = automatic from k*h of the coarsest level */
+    o->mg_coarse_mode = 1;
+    o->mg_kh_max = 1.3;
     o->verbose = 0;
     o->line_x_lo = o->line_x_hi = o->line_y_lo = o->line_y_hi = 0;
     o->mg_wfrom = 3;

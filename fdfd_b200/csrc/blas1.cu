@@ -322,12 +322,20 @@ int allreduce_slots(Comm* comm, Scalars& sc, int s0, int count, cudaStream_t str
     return comm_allreduce_sum(comm, (double*)(sc.slot + s0), 2 * count, stream);
 }
 
+// a / b with 0 for an exactly-zero (or non-finite) denominator: a Krylov recurrence that has
+// converged to machine zero then turns into a no-op instead of producing NaN
+__device__ __forceinline__ double2 safe_div(double2 a, double2 b) {
+    const double d = b.x * b.x + b.y * b.y;
+    if (!(d > 0.0) || !isfinite(d)) return make_double2(0.0, 0.0);
+    return make_double2((a.x * b.x + a.y * b.y) / d, (a.y * b.x - a.x * b.y) / d);
+}
+
 __global__ void scalar_op_kernel(int op, int a, int b, int c, int d, int e, double p, double q, double2* s) {
     switch (op) {
         case SOP_SET: s[a] = make_double2(p, q); break;
-        case SOP_DIV: s[a] = cdiv(s[b], s[c]); break;
+        case SOP_DIV: s[a] = safe_div(s[b], s[c]); break;
         case SOP_BICG_BETA: {
-            const double2 beta = cmul(cdiv(s[b], s[c]), cdiv(s[d], s[e]));
+            const double2 beta = cmul(safe_div(s[b], s[c]), safe_div(s[d], s[e]));
             s[a] = beta;
             s[a + 1] = cneg(cmul(beta, s[e]));
             break;

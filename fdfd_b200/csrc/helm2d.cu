@@ -270,10 +270,10 @@ int helm2d_apply(Helm2D& op, int mode, const void* x, void* y, const void* b, do
     if (op.dtype == FDFD_C128)
         return helm2d_launch<double2>(op, mode, (const double2*)x, (double2*)y, (const double2*)b,
                                       (const double2*)op.ca, (const double2*)op.cb,
-                                      (const double2*)op.cd, 1.0, 0.0, omega, stream);
+                                      (const double2*)op.cd, op.shift_re, op.shift_im, omega, stream);
     return helm2d_launch<float2>(op, mode, (const float2*)x, (float2*)y, (const float2*)b,
                                  (const float2*)op.ca, (const float2*)op.cb, (const float2*)op.cd,
-                                 1.0, 0.0, omega, stream);
+                                 op.shift_re, op.shift_im, omega, stream);
 }
 
 }  // namespace fdfd

@@ -50,6 +50,7 @@ struct Helm2D {
     int bcx, bcy;
     double phase[4];
     double sx, sy;
+    double shift_re, shift_im;   // multiplier of the diagonal term cd (1,0 for A itself)
     const void *ca, *cb, *cd;
     Comm* comm;
     int variant;

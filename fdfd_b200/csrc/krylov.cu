@@ -48,27 +48,42 @@ struct JacobiPrecond : Precond {
     }
 };
 
+}  // namespace
+
+int BicgWorkspace::ensure(size_t bytes, bool precond) {
+    if (!sc.slot) FDFD_TRY(sc.alloc());
+    const int need = precond ? 7 : 5;
+    if (bytes > cap) {
+        for (int i = 0; i < 7; ++i) { cudaFree(v[i]); v[i] = nullptr; }
+        cap = bytes; count = 0;
+    }
+    for (int i = count; i < need; ++i) FDFD_CUDA(cudaMalloc(&v[i], cap));
+    if (need > count) count = need;
+    return FDFD_OK;
+}
+BicgWorkspace::~BicgWorkspace() {
+    for (int i = 0; i < 7; ++i) cudaFree(v[i]);
+    sc.release();
+}
+
+namespace {
+
 // slot map --------------------------------------------------------------------------------------
 enum { S_RHO = 0, S_RHO_OLD, S_ALPHA, S_OMEGA, S_BETA, S_NBO, S_RV, S_TS, S_TT, S_RR, S_BB, S_SS,
        S_TMP0, S_TMP1, S_TMP2, S_TMP3, S_H0 = 32 /* Hessenberg column / GMRES y (<= 200 entries) */ };
 
 template <typename C>
 int bicgstab_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, SolveInfo& info,
-               cudaStream_t stream) {
+               cudaStream_t stream, BicgWorkspace* ext_ws = nullptr, bool fixed_its = false) {
     const int64_t n = A.n_local();
     const size_t bytes = (size_t)n * sizeof(C);
-    Scalars sc;
-    ScalarsGuard guard{sc};
-    FDFD_TRY(sc.alloc());
-    DeviceBuf br, brh, bp, bv, bt, bph, bsh;
-    FDFD_TRY(br.alloc(bytes)); FDFD_TRY(brh.alloc(bytes)); FDFD_TRY(bp.alloc(bytes));
-    FDFD_TRY(bv.alloc(bytes)); FDFD_TRY(bt.alloc(bytes));
-    C *r = (C*)br.p, *rh = (C*)brh.p, *p = (C*)bp.p, *v = (C*)bv.p, *t = (C*)bt.p;
+    BicgWorkspace own;
+    BicgWorkspace& ws = ext_ws ? *ext_ws : own;
+    FDFD_TRY(ws.ensure(bytes, M != nullptr));
+    Scalars& sc = ws.sc;
+    C *r = (C*)ws.v[0], *rh = (C*)ws.v[1], *p = (C*)ws.v[2], *v = (C*)ws.v[3], *t = (C*)ws.v[4];
     C *ph = p, *sh = r;  // unpreconditioned: p^ = p, s^ = s (= r storage)
-    if (M) {
-        FDFD_TRY(bph.alloc(bytes)); FDFD_TRY(bsh.alloc(bytes));
-        ph = (C*)bph.p; sh = (C*)bsh.p;
-    }
+    if (M) { ph = (C*)ws.v[5]; sh = (C*)ws.v[6]; }
     Comm* comm = A.comm;
     double2 h[4];
     int status = FDFD_OK;
@@ -91,6 +106,34 @@ int bicgstab_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* 
         return FDFD_OK;
     };
     FDFD_TRY(restart());
+    if (fixed_its) {
+        // sync-free variant for inner solves: exactly o.maxit iterations, no host reads
+        for (int it = 0; it < o.maxit; ++it) {
+            FDFD_TRY(scalar_op(SOP_BICG_BETA, S_BETA, S_RHO, S_RHO_OLD, S_ALPHA, S_OMEGA, 0, 0, sc, stream));
+            FDFD_TRY(lincomb<C>(n, p, nullptr, r, sc.slot + S_BETA, p, sc.slot + S_NBO, v, 0, nullptr, -1, -1, sc, stream));
+            if (M) { FDFD_TRY(M->apply(p, ph, stream)); ++info.precond_applies; }
+            FDFD_TRY(helm2d_apply(A, APPLY_AX, ph, v, nullptr, 0.0, stream)); ++info.op_applies;
+            { const C* xs[1] = {rh}; const C* ys[1] = {v}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_RV, sc, stream)); }
+            FDFD_TRY(allreduce_slots(comm, sc, S_RV, 1, stream));
+            FDFD_TRY(scalar_op(SOP_DIV, S_ALPHA, S_RHO, S_RV, 0, 0, 0, 0, sc, stream));
+            FDFD_TRY(lincomb<C>(n, r, nullptr, r, sc.slot + S_ALPHA, v, nullptr, nullptr, 2, nullptr, -1, -1, sc, stream));
+            if (M) { FDFD_TRY(M->apply(r, sh, stream)); ++info.precond_applies; }
+            FDFD_TRY(helm2d_apply(A, APPLY_AX, sh, t, nullptr, 0.0, stream)); ++info.op_applies;
+            { const C* xs[2] = {t, t}; const C* ys[2] = {r, t}; FDFD_TRY(dots<C>(n, 2, xs, ys, S_TS, sc, stream)); }
+            FDFD_TRY(allreduce_slots(comm, sc, S_TS, 2, stream));
+            FDFD_TRY(scalar_op(SOP_DIV, S_OMEGA, S_TS, S_TT, 0, 0, 0, 0, sc, stream));
+            FDFD_TRY(lincomb<C>(n, x, nullptr, x, sc.slot + S_ALPHA, ph, sc.slot + S_OMEGA, sh, 0, nullptr, -1, -1, sc, stream));
+            FDFD_TRY(scalar_op(SOP_COPY, S_RHO_OLD, S_RHO, 0, 0, 0, 0, 0, sc, stream));
+            FDFD_TRY(lincomb<C>(n, r, nullptr, r, sc.slot + S_OMEGA, t, nullptr, nullptr, 2, rh, S_RHO, S_RR, sc, stream));
+            if (comm && comm->nranks > 1) {
+                FDFD_TRY(scalar_op(SOP_COPY, S_TMP0, S_RHO, 0, 0, 0, 0, 0, sc, stream));
+                FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 1, stream));
+                FDFD_TRY(scalar_op(SOP_COPY, S_RHO, S_TMP0, 0, 0, 0, 0, 0, sc, stream));
+            }
+        }
+        info.iterations = o.maxit;
+        return FDFD_OK;
+    }
     FDFD_TRY(read_slots(sc, S_RR, 2, h, stream));
     const double bnorm2 = h[1].x > 0 ? h[1].x : 1.0;
     double rr = h[0].x;
@@ -320,9 +363,9 @@ int make_jacobi_precond(Helm2D& A, Precond** out, cudaStream_t stream) {
 }
 
 int bicgstab_solve(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
-                   SolveInfo& info, cudaStream_t stream) {
-    if (A.dtype == FDFD_C128) return bicgstab_t<double2>(A, M, o, (const double2*)b, (double2*)x, info, stream);
-    return bicgstab_t<float2>(A, M, o, (const float2*)b, (float2*)x, info, stream);
+                   SolveInfo& info, cudaStream_t stream, BicgWorkspace* ws, bool fixed_its) {
+    if (A.dtype == FDFD_C128) return bicgstab_t<double2>(A, M, o, (const double2*)b, (double2*)x, info, stream, ws, fixed_its);
+    return bicgstab_t<float2>(A, M, o, (const float2*)b, (float2*)x, info, stream, ws, fixed_its);
 }
 int fgmres_solve(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
                  SolveInfo& info, cudaStream_t stream) {

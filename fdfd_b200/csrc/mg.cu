@@ -23,6 +23,8 @@
 #include "krylov.cuh"
 #include "comm.cuh"
 
+#include <algorithm>
+#include <cmath>
 #include <vector>
 
 namespace fdfd {
@@ -406,7 +408,26 @@ struct MGPrecond : Precond {
     std::vector<Level<C>> L;
     fdfd_krylov_opts o;
     double shift_re = 1.0, shift_im = 0.5;
-    cudaStream_t setup_stream = 0;
+    int coarse_its = 8;
+    BicgWorkspace coarse_ws;
+
+    // preconditioner of the coarsest-level Krylov solve: one smoothing sweep from a zero guess
+    struct SmoothPrecond : Precond {
+        MGPrecond* mg = nullptr;
+        int level = 0;
+        int apply(const void* v, void* z, cudaStream_t st) override {
+            Level<C>& lv = mg->L[level];
+            C* saved = lv.b;
+            lv.b = (C*)v;
+            const size_t bytes = (size_t)lv.op.n_local() * sizeof(C);
+            FDFD_CUDA(cudaMemsetAsync(lv.x, 0, bytes, st));
+            int s = mg->smooth(level, st);
+            lv.b = saved;
+            FDFD_TRY(s);
+            FDFD_CUDA(cudaMemcpyAsync(z, lv.x, bytes, cudaMemcpyDeviceToDevice, st));
+            return FDFD_OK;
+        }
+    } coarse_pre;
 
     ~MGPrecond() override {
         for (size_t l = 0; l < L.size(); ++l) {
@@ -494,7 +515,20 @@ struct MGPrecond : Precond {
         Level<C>& lv = L[l];
         const int last = (int)L.size() - 1;
         if (l == last) {
-            for (int s = 0; s < o.mg_coarse_its; ++s) FDFD_TRY(smooth(l, st));
+            if (o.mg_coarse_mode == 1) {
+                // coarse_its sync-free BiCGSTAB iterations on the shifted coarse operator; the
+                // solution lives in lv.r (the smoother ping-pongs lv.x / lv.t underneath)
+                const size_t bytes = (size_t)lv.op.n_local() * sizeof(C);
+                FDFD_CUDA(cudaMemcpyAsync(lv.r, lv.x, bytes, cudaMemcpyDeviceToDevice, st));
+                fdfd_krylov_opts io = o;
+                io.maxit = coarse_its;
+                SolveInfo ii;
+                coarse_pre.mg = this; coarse_pre.level = l;
+                FDFD_TRY(bicgstab_solve(lv.op, &coarse_pre, io, lv.b, lv.r, ii, st, &coarse_ws, true));
+                std::swap(lv.x, lv.r);
+            } else {
+                for (int s = 0; s < coarse_its; ++s) FDFD_TRY(smooth(l, st));
+            }
             return FDFD_OK;
         }
         for (int s = 0; s < o.mg_pre; ++s) FDFD_TRY(smooth(l, st));
@@ -541,6 +575,8 @@ struct MGPrecond : Precond {
         Level<C> f;
         f.op = A; f.op.halo_south = f.op.halo_north = f.op.cb_ghost_buf = nullptr; f.op.h_x = f.op.h_y = nullptr;
         f.ca = (C*)A.ca; f.cb = (C*)A.cb; f.cd = (C*)A.cd; f.own_coefs = false; f.delta = 1.0;
+        f.op.shift_re = shift_re; f.op.shift_im = shift_im;
+        const double kh_max = opts.mg_kh_max > 0 ? opts.mg_kh_max : 1e30;
         L.push_back(f);
         while (true) {
             Level<C>& cur = L.back();
@@ -551,7 +587,9 @@ struct MGPrecond : Precond {
             FDFD_TRY(setup_lines(cur, cur.ylines, 0, lx_lo, lx_hi, st));
             FDFD_TRY(setup_lines(cur, cur.xlines, 1, ly_lo, ly_hi, st));
             const bool max_levels = opts.mg_levels > 0 && (int)L.size() >= opts.mg_levels;
-            if (max_levels || (Nx & 1) || (Ny & 1) || Nx / 2 < min_n || Ny / 2 < min_n) break;
+            const double s_next = std::min(cur.op.sx, cur.op.sy) / 4.0;
+            const double kh_next = s_next > 0 ? 1.0 / std::sqrt(std::fabs(s_next)) : 1e30;
+            if (max_levels || (Nx & 1) || (Ny & 1) || Nx / 2 < min_n || Ny / 2 < min_n || kh_next > kh_max) break;
             Level<C> c;
             c.op = cur.op;
             c.op.Nx = Nx / 2; c.op.Ny = Ny / 2; c.op.Ny_global = Ny / 2; c.op.j0 = 0;
@@ -568,6 +606,19 @@ struct MGPrecond : Precond {
             c.op.ca = c.ca; c.op.cb = c.cb; c.op.cd = c.cd;
             lx_lo = (lx_lo + 1) / 2; lx_hi = (lx_hi + 1) / 2; ly_lo = (ly_lo + 1) / 2; ly_hi = (ly_hi + 1) / 2;
             L.push_back(c);
+        }
+        {
+            const Level<C>& c = L.back();
+            const double kh = 1.0 / std::sqrt(std::fabs(std::min(c.op.sx, c.op.sy)));
+            if (opts.mg_coarse_its > 0) coarse_its = opts.mg_coarse_its;
+            else {
+                coarse_its = (int)std::ceil(10.0 / kh);
+                if (coarse_its < 8) coarse_its = 8;
+                if (coarse_its > 80) coarse_its = 80;
+            }
+            if (o.verbose)
+                fprintf(stderr, "[fdfd] multigrid: %d levels, coarsest %d x %d (k*h = %.3f), coarse mode %d its %d\n",
+                        (int)L.size(), c.op.Nx, c.op.Ny, kh, o.mg_coarse_mode, coarse_its);
         }
         FDFD_CUDA(cudaStreamSynchronize(st));
         return FDFD_OK;

@@ -134,6 +134,9 @@ typedef struct {
     int mg_wfrom;     /* first level (0 = finest) that is cycled as a W instead of a V; <0 = never */
     int mg_min_n;     /* stop coarsening when min(Nx, Ny) of the next level would drop below this */
     int reorth;       /* FGMRES: 1 = second Gram-Schmidt pass                                   */
+    int mg_coarse_mode; /* coarsest level: 0 = mg_coarse_its smoothing sweeps, 1 = mg_coarse_its
+                         * iterations of BiCGSTAB preconditioned by one smoothing sweep              */
+    double mg_kh_max; /* stop coarsening once k*h = 1/sqrt(min(sx,sy)) of the next level exceeds this */
 } fdfd_krylov_opts;
 
 void fdfd_krylov_default_opts(fdfd_krylov_opts*);

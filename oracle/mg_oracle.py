@@ -70,9 +70,11 @@ def prolong(e, pol, delta_fine):
 
 class MGOracle:
     def __init__(self, pol, ca, cb, cd, sx, sy, shift=(1.0, 0.5), omega=0.8, pre=1, post=1,
-                 lines=(0, 0, 0, 0), levels=0, min_n=32, coarse_its=8, cycle=1, wfrom=3):
+                 lines=(0, 0, 0, 0), levels=0, min_n=32, coarse_its=0, cycle=1, wfrom=3, coarse_mode=1,
+                 kh_max=1.3):
         self.pol, self.omega, self.pre, self.post = pol, omega, pre, post
         self.coarse_its, self.cycle_kind, self.wfrom = coarse_its, cycle, wfrom
+        self.coarse_mode = coarse_mode
         self.levels = []
         sh = shift[0] + 1j * shift[1]
         cdm = sh * np.asarray(cd, dtype=complex)
@@ -98,13 +100,51 @@ class MGOracle:
             L["B2"] = blk((dcol == 0) | ((abs(dcol) == 1) & iny[C.row] & iny[C.col])) if iny.any() else None
             L["m2"] = iny.astype(float)
             self.levels.append(L)
-            stop = (levels and len(self.levels) >= levels) or Nx % 2 or Ny % 2 or Nx // 2 < min_n or Ny // 2 < min_n
+            kh_next = 1.0 / np.sqrt(min(sx, sy) / 4.0)
+            stop = ((levels and len(self.levels) >= levels) or Nx % 2 or Ny % 2 or Nx // 2 < min_n
+                    or Ny // 2 < min_n or kh_next > kh_max)
+            L["kh"] = 1.0 / np.sqrt(min(sx, sy))
             if stop:
                 break
             ca, cb, cdm = coarsen(pol, ca, cb, cdm, delta)
             delta = (delta + 0.5) / 2.0
             sx, sy = sx / 4, sy / 4
             lx_lo, lx_hi, ly_lo, ly_hi = [(w + 1) // 2 for w in (lx_lo, lx_hi, ly_lo, ly_hi)]
+
+    def _coarse_its(self):
+        if self.coarse_its > 0:
+            return self.coarse_its
+        return int(min(80, max(8, np.ceil(10.0 / self.levels[-1]["kh"]))))
+
+    def _coarse_bicgstab(self, l, x, b, its):
+        """`its` iterations of right-preconditioned BiCGSTAB (preconditioner = one smoothing sweep
+        from zero), same recurrences as csrc/krylov.cu."""
+        A = self.levels[l]["A"]
+
+        def sdiv(a, c):
+            return a / c if (abs(c) > 0 and np.isfinite(abs(c))) else 0.0
+        M = lambda v: self.smooth(l, np.zeros_like(v), v)  # noqa: E731
+        r = b - A @ x
+        rh = r.copy()
+        rho = np.vdot(r, r)
+        rho_old = alpha = om = 1.0
+        v = np.zeros_like(b)
+        p = np.zeros_like(b)
+        for _ in range(its):
+            beta = sdiv(rho, rho_old) * sdiv(alpha, om)
+            p = r + beta * p - (beta * om) * v
+            ph = M(p)
+            v = A @ ph
+            alpha = sdiv(rho, np.vdot(rh, v))
+            s = r - alpha * v
+            sh = M(s)
+            t = A @ sh
+            om = sdiv(np.vdot(t, s), np.vdot(t, t))
+            x = x + alpha * ph + om * sh
+            rho_old = rho
+            r = s - om * t
+            rho = np.vdot(rh, r)
+        return x
 
     def smooth(self, l, x, b):
         L = self.levels[l]
@@ -117,7 +157,9 @@ class MGOracle:
         L = self.levels[l]
         last = len(self.levels) - 1
         if l == last:
-            for _ in range(self.coarse_its):
+            if self.coarse_mode == 1:
+                return self._coarse_bicgstab(l, x, b, self._coarse_its())
+            for _ in range(self._coarse_its()):
                 x = self.smooth(l, x, b)
             return x
         for _ in range(self.pre):
