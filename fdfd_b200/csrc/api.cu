@@ -129,7 +129,6 @@ static int ensure_host_scratch(Helm2D& op) {
 extern "C" int fdfd_helm2d_apply_host(fdfd_helm2d_t* h, const void* x_host, void* y_host) {
     FDFD_CHECK_ARG(h && x_host && y_host, "null pointer");
     Helm2D& op = h->op;
-    FDFD_CHECK_ARG(op.Ny == op.Ny_global, "host-buffer apply is for the unsharded operator");
     FDFD_TRY(ensure_host_scratch(op));
     const size_t bytes = (size_t)op.n_local() * op.elem();
     FDFD_CUDA(cudaMemcpyAsync(op.h_x, x_host, bytes, cudaMemcpyHostToDevice, 0));

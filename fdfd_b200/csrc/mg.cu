@@ -211,34 +211,61 @@ __global__ void line_reduced_inverse_kernel(LineView<C> v) {
         __syncthreads();
     }
     C* out = v.rinv + (int64_t)l * n * n;
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-        const int row = e % n, col = e / n;
-        out[col * n + row] = R[row * n + col];     // column-major
-    }
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) out[e] = R[e];   // row-major
 }
 
-// phase A: chunk-local solve, in place in g; interface values to ifg
+// phase A: chunk-local solve, in place in g; interface values to ifg.  The recurrences are
+// latency bound (one dependent complex FMA per step), so the operands of kLB steps are fetched
+// into registers ahead of the dependent chain.
+constexpr int kLB = 16;
 template <typename C>
-__global__ void __launch_bounds__(128) line_local_solve_kernel(LineView<C> v) {
+__global__ void __launch_bounds__(64) line_local_solve_kernel(LineView<C> v) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= v.nl * v.P) return;
     const int l = idx % v.nl, k = idx / v.nl;
     const int t0 = k * v.m, t1 = min(v.len, t0 + v.m);
     if (t0 >= t1) return;
     const int64_t nl = v.nl;
-    C y = v.g[t0 * nl + l];
-#pragma unroll 4
-    for (int t = t0 + 1; t < t1; ++t) {
-        y = csub(v.g[t * nl + l], cmul(v.fl[t * nl + l], y));
-        v.g[t * nl + l] = y;
+    C* g = v.g + l;
+    const C* fl = v.fl + l;
+    const C* fc = v.fc + l;
+    const C* fip = v.fip + l;
+    C y = g[t0 * nl];
+    for (int tb = t0 + 1; tb < t1; tb += kLB) {
+        C gb[kLB], lb[kLB];
+#pragma unroll
+        for (int q = 0; q < kLB; ++q) {
+            const int t = min(tb + q, t1 - 1);
+            gb[q] = g[t * nl];
+            lb[q] = fl[t * nl];
+        }
+#pragma unroll
+        for (int q = 0; q < kLB; ++q) {
+            if (tb + q < t1) {
+                y = csub(gb[q], cmul(lb[q], y));
+                g[(tb + q) * nl] = y;
+            }
+        }
     }
-    C e = cmul(y, v.fip[(t1 - 1) * nl + l]);
-    v.g[(t1 - 1) * nl + l] = e;
+    C e = cmul(y, fip[(t1 - 1) * nl]);
+    g[(t1 - 1) * nl] = e;
     const C e_last = e;
-#pragma unroll 4
-    for (int t = t1 - 2; t >= t0; --t) {
-        e = cmul(csub(v.g[t * nl + l], cmul(v.fc[t * nl + l], e)), v.fip[t * nl + l]);
-        v.g[t * nl + l] = e;
+    for (int tb = t1 - 2; tb >= t0; tb -= kLB) {
+        C gb[kLB], cb[kLB], pb[kLB];
+#pragma unroll
+        for (int q = 0; q < kLB; ++q) {
+            const int t = max(tb - q, t0);
+            gb[q] = g[t * nl];
+            cb[q] = fc[t * nl];
+            pb[q] = fip[t * nl];
+        }
+#pragma unroll
+        for (int q = 0; q < kLB; ++q) {
+            if (tb - q >= t0) {
+                e = cmul(csub(gb[q], cmul(cb[q], e)), pb[q]);
+                g[(tb - q) * nl] = e;
+            }
+        }
     }
     if (v.P > 1) {
         v.ifg[(int64_t)l * 2 * v.P + 2 * k] = e;
@@ -246,19 +273,28 @@ __global__ void __launch_bounds__(128) line_local_solve_kernel(LineView<C> v) {
     }
 }
 
-// phase B: u = R^-1 g_interface ; one warp per line
+// phase B: u = R^-1 g_interface ; one warp per (line, row), lanes across the row, shuffle reduce
 template <typename C>
-__global__ void line_reduced_kernel(LineView<C> v) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= v.nl) return;
+__global__ void __launch_bounds__(256) line_reduced_kernel(LineView<C> v) {
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     const int n = 2 * v.P;
-    const C* Ri = v.rinv + (int64_t)warp * n * n;
-    const C* gi = v.ifg + (int64_t)warp * n;
-    for (int row = lane; row < n; row += 32) {
-        C acc = czero<C>();
-        for (int q = 0; q < n; ++q) acc = cfma(Ri[q * n + row], gi[q], acc);
-        v.ifu[(int64_t)warp * n + row] = acc;
+    if (warp >= (int64_t)v.nl * n) return;
+    const int l = (int)(warp / n), row = (int)(warp % n);
+    const C* Ri = v.rinv + ((int64_t)l * n + row) * n;
+    const C* gi = v.ifg + (int64_t)l * n;
+    double ax = 0.0, ay = 0.0;
+    for (int q = lane; q < n; q += 32) {
+        const C r = Ri[q], g = gi[q];
+        ax += (double)r.x * g.x - (double)r.y * g.y;
+        ay += (double)r.x * g.y + (double)r.y * g.x;
     }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ax += __shfl_down_sync(0xffffffffu, ax, off);
+        ay += __shfl_down_sync(0xffffffffu, ay, off);
+    }
+    if (lane == 0) v.ifu[(int64_t)l * n + row] = mk<C>((typename real_of<C>::type)ax, (typename real_of<C>::type)ay);
 }
 
 // phase C: spike correction; dir 0 also applies the update x += omega * e
@@ -478,8 +514,8 @@ struct MGPrecond : Precond {
     int line_solve(Level<C>& lv, LineSet<C>& s, C* x, double omega, cudaStream_t st) {
         using R = typename real_of<C>::type;
         LineView<C> v = view(s, lv.op.Nx, lv.op.Ny);
-        line_local_solve_kernel<C><<<(s.nl * s.P + 127) / 128, 128, 0, st>>>(v);
-        if (s.P > 1) line_reduced_kernel<C><<<(s.nl * 32 + 127) / 128, 128, 0, st>>>(v);
+        line_local_solve_kernel<C><<<(s.nl * s.P + 63) / 64, 64, 0, st>>>(v);
+        if (s.P > 1) line_reduced_kernel<C><<<(int)(((int64_t)s.nl * 2 * s.P * 32 + 255) / 256), 256, 0, st>>>(v);
         const int64_t tot = (int64_t)s.nl * s.len;
         if (s.P > 1 || s.dir == 0)
             line_correct_kernel<C><<<(int)((tot + 255) / 256), 256, 0, st>>>(v, x, (R)omega);

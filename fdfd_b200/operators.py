@@ -111,14 +111,18 @@ class HelmholtzOperator2D:
             _lib.check(self._L.fdfd_helm2d_apply(self._h, x.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
-    def apply_host(self, x):
-        """y = A x with numpy in / numpy out (H2D + kernel + D2H inside the C-ABI call)."""
+    def apply_host(self, x, out=None):
+        """y = A x with numpy in / numpy out (H2D + kernel + D2H inside the C-ABI call).
+        `out` may be a preallocated (e.g. pinned) array of the same dtype and size."""
         ndt = np.complex128 if self.code == _lib.C128 else np.complex64
         x = np.ascontiguousarray(x, dtype=ndt)
         if x.size != self.n:
             raise ValueError("x has the wrong number of elements")
-        y = np.empty_like(x)
-        _lib.check(self._L.fdfd_helm2d_apply_host(self._h, x.ctypes.data, y.ctypes.data))
+        y = np.empty_like(x) if out is None else out
+        if y.dtype != ndt or y.size != self.n or not y.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous array of the operator dtype and size")
+        with _torch().cuda.device(self.device):
+            _lib.check(self._L.fdfd_helm2d_apply_host(self._h, x.ctypes.data, y.ctypes.data))
         return y
 
     __matmul__ = lambda self, x: self.apply(x) if not isinstance(x, np.ndarray) else self.apply_host(x)

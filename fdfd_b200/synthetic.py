@@ -1,0 +1,50 @@
+"""Synthetic scattering inputs built directly on the device (bench / multi-GPU slabs).
+
+Same problem family as the reference example scaled per SURVEY.md §8d
+(Scattering/example_scattering_by_cylinder.py:8-32: f0 = 10 GHz, 50 cells per wavelength,
+eps_r cylinder of radius lambda/2 at the centre, UPML 40 cells with sigma_max = 10, n = 3;
+UPML scaling as Scattering_Solver_2D.py:124-153), but evaluated with torch on the GPU for the
+rows of one y-slab only, so that a 4096 x 32768 global grid never exists on the host.
+These arrays feed K2 directly; they are inputs, not part of any parity claim (parity tests
+use the numpy host path of `FDFD2DScatteringSolver`).
+"""
+from __future__ import annotations
+
+import math
+
+C0 = 299_792_458.0
+EPS0 = 8.854187817e-12
+
+
+def slab_coefficients(Nx, Ny, j0, j1, pol="TE", eps_r=-1e6, f0=10e9, pml=40, sigma_max=10.0, order=3,
+                      device="cuda", dtype=None):
+    """(ca, cb, cd, sx, sy) for rows [j0, j1) of the Nx x Ny problem; ca = 1/m_a, cb = 1/m_b."""
+    import torch
+
+    dtype = dtype or torch.complex128
+    lam = C0 / f0
+    dx = dy = lam / 50.0
+    omega = 2 * math.pi * f0
+    k0 = omega / C0
+    x = (torch.arange(Nx, device=device, dtype=torch.float64) + 0.5) * dx - Nx * dx / 2
+    y = (torch.arange(j0, j1, device=device, dtype=torch.float64) + 0.5) * dy - Ny * dy / 2
+
+    def sigma(idx, n):
+        d = torch.minimum(idx, (n - 1) - idx).to(torch.float64)
+        s = sigma_max * torch.clamp((pml - d) / pml, min=0.0) ** order
+        return s
+
+    sig_x = sigma(torch.arange(Nx, device=device), Nx)
+    sig_y = sigma(torch.arange(j0, j1, device=device), Ny)
+    Sx = torch.complex(torch.ones_like(sig_x), sig_x / (EPS0 * omega))[None, :]
+    Sy = torch.complex(torch.ones_like(sig_y), sig_y / (EPS0 * omega))[:, None]
+    inside = (x[None, :] ** 2 + y[:, None] ** 2) <= (0.5 * lam) ** 2
+    one = torch.ones((j1 - j0, Nx), device=device, dtype=torch.complex128)
+    er = torch.where(inside, torch.full_like(one, complex(eps_r)), one)
+    mr = one
+    if pol.upper() == "TE":
+        ma, mb, dg = mr * (Sx / Sy), mr * (Sy / Sx), er * (Sx * Sy)      # MRyy, MRxx, ERzz
+    else:
+        ma, mb, dg = er * (Sx / Sy), er * (Sy / Sx), mr * (Sx * Sy)      # ERyy, ERxx, MRzz
+    s = 1.0 / (k0 * dx) ** 2
+    return (1.0 / ma).to(dtype).contiguous(), (1.0 / mb).to(dtype).contiguous(), dg.to(dtype).contiguous(), s, s
