@@ -192,12 +192,23 @@ template <typename C>
 int dots(int64_t n, int ndots, const C* const* xs, const C* const* ys, int s0, Scalars& sc,
          cudaStream_t stream) {
     FDFD_CHECK_ARG(ndots >= 1 && ndots <= 4, "dots: 1..4 inner products per launch");
-    DotPtrs<C, 4> p;
-    for (int k = 0; k < 4; ++k) { p.x[k] = k < ndots ? xs[k] : nullptr; p.y[k] = k < ndots ? ys[k] : nullptr; }
     const int grid = stream_grid(n);
-    // slots are double2 = consecutive (re, im) doubles, so write the totals in place
-    dots_kernel<C, 4><<<grid, kThreads, 0, stream>>>(n, p, ndots, (double*)(sc.slot + s0),
-                                                      sc.partials, sc.counter);
+    // slots are double2 = consecutive (re, im) doubles, so write the totals in place; the kernel
+    // is instantiated per count so that exactly `ndots` slots are written
+#define LAUNCH_DOTS(K)                                                                            \
+    do {                                                                                          \
+        DotPtrs<C, K> p;                                                                          \
+        for (int k = 0; k < K; ++k) { p.x[k] = xs[k]; p.y[k] = ys[k]; }                           \
+        dots_kernel<C, K><<<grid, kThreads, 0, stream>>>(n, p, ndots, (double*)(sc.slot + s0),   \
+                                                          sc.partials, sc.counter);               \
+    } while (0)
+    switch (ndots) {
+        case 1: LAUNCH_DOTS(1); break;
+        case 2: LAUNCH_DOTS(2); break;
+        case 3: LAUNCH_DOTS(3); break;
+        default: LAUNCH_DOTS(4); break;
+    }
+#undef LAUNCH_DOTS
     FDFD_CUDA(cudaGetLastError());
     return FDFD_OK;
 }

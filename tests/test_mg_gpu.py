@@ -28,8 +28,11 @@ def _problem(N, pol, eps=4.0, pw=12):
     dict(N=544, levels=1, lines=(5, 3, 4, 6), coarse_its=1),         # 32 chunks, ragged last chunk
     dict(N=256, levels=0, lines=(12, 12, 12, 12), min_n=16, coarse_its=6, wfrom=2),
     dict(N=64, levels=1, lines=(12, 12, 12, 12), coarse_its=5, coarse_mode=1),     # coarse BiCGSTAB alone
-    dict(N=256, levels=0, lines=(12, 12, 12, 12), coarse_its=0, coarse_mode=1, kh_max=1.3),  # production shape
-    dict(N=200, levels=0, lines=(12, 12, 12, 12), coarse_its=0, coarse_mode=1, kh_max=1.3),  # 200-100-50-25 (odd stop)
+    dict(N=64, levels=2, lines=(12, 12, 12, 12), coarse_its=4, coarse_mode=1),     # two-grid + coarse BiCGSTAB
+    dict(N=64, levels=2, lines=(0, 0, 0, 0), coarse_its=4, coarse_mode=1),         # same, no line relaxation
+    dict(N=256, levels=0, lines=(12, 12, 12, 12), coarse_its=6, coarse_mode=1, kh_max=1.3),  # production shape
+    dict(N=200, levels=0, lines=(12, 12, 12, 12), coarse_its=6, coarse_mode=1, kh_max=1.3),  # 200-100-50-25 (odd stop)
+    dict(N=256, levels=0, lines=(12, 12, 12, 12), coarse_its=0, coarse_mode=1, kh_max=1.3),  # automatic coarse its
 ])
 def test_precond_apply_matches_oracle(pol, cfg):
     import torch
