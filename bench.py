@@ -156,7 +156,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     comm = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
         comm = fdfd_b200.SlabComm()
     steps, warmup = max(args.steps, 1), max(args.warmup, 3)
 
@@ -188,17 +189,17 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    # keep the GPU busy a little longer if the timed region was too short for nvidia-smi to see it
-    if sampler is not None:
-        t_end = time.perf_counter() + max(0.0, 0.25 - ms * 1e-3)
-        while time.perf_counter() < t_end:
-            A.apply(x, out=y)
-        torch.cuda.synchronize(dev)
-    clocks = sampler.stop() if sampler is not None else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # keep the GPUs under the same load a little longer when the timed region was too short for
+    # nvidia-smi to sample it (every rank runs the same number of extra steps: apply() is collective)
+    extra = int(max(0.0, 0.3 - ms * 1e-3) / max(ms * 1e-3 / steps, 1e-6))
+    for _ in range(extra):
+        A.apply(x, out=y)
+    barrier()
+    clocks = sampler.stop() if sampler is not None else None
     value = world * bytes_rank * steps / (ms * 1e-3) / 1e9
 
     # kernel-only duration for the roofline (single-rank: identical to the step; sharded: the

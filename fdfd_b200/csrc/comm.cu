@@ -115,15 +115,14 @@ int comm_halo_rows(Comm* c, const void* x, void* halo_south, void* halo_north, i
     const char* first_row = (const char*)x;
     const char* last_row = (const char*)x + (size_t)(Ny - 1) * bytes;
     ncclComm_t comm = (ncclComm_t)c->nccl;
+    // Order matters when both neighbours are the same peer (2 ranks, periodic): NCCL pairs the
+    // sends and receives between two ranks in issue order, so "my last row -> north's south ghost"
+    // is issued (and received) first on every rank, "my first row -> south's north ghost" second.
     FDFD_NCCL(g_api.GroupStart());
-    if (south >= 0) {
-        FDFD_NCCL(g_api.Send(first_row, bytes, ncclChar, south, comm, stream));
-        FDFD_NCCL(g_api.Recv(halo_south, bytes, ncclChar, south, comm, stream));
-    }
-    if (north >= 0) {
-        FDFD_NCCL(g_api.Send(last_row, bytes, ncclChar, north, comm, stream));
-        FDFD_NCCL(g_api.Recv(halo_north, bytes, ncclChar, north, comm, stream));
-    }
+    if (north >= 0) FDFD_NCCL(g_api.Send(last_row, bytes, ncclChar, north, comm, stream));
+    if (south >= 0) FDFD_NCCL(g_api.Recv(halo_south, bytes, ncclChar, south, comm, stream));
+    if (south >= 0) FDFD_NCCL(g_api.Send(first_row, bytes, ncclChar, south, comm, stream));
+    if (north >= 0) FDFD_NCCL(g_api.Recv(halo_north, bytes, ncclChar, north, comm, stream));
     FDFD_NCCL(g_api.GroupEnd());
     return FDFD_OK;
 }

@@ -17,7 +17,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+    import datetime
+    dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     comm = fdfd_b200.SlabComm()
     rng = np.random.default_rng(42)           # same stream on every rank -> same global arrays
     failures = []

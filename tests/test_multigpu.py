@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _torchrun(script, nproc, timeout=600):
+def _torchrun(script, nproc, timeout=240):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", script)]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
