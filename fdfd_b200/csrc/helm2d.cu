@@ -214,7 +214,14 @@ HelmArgs<C> helm2d_args(const Helm2D& op, const C* x, C* y, const C* b, const C*
 template <typename C>
 int helm2d_launch_args(const Helm2D& op, int mode, HelmArgs<C>& a, cudaStream_t stream) {
     const bool TM = op.pol == FDFD_POL_TM;
-    const Variant v = kVariants[(op.variant >= 0 && op.variant < kNumVariants) ? op.variant : 0];
+    Variant v = kVariants[(op.variant >= 0 && op.variant < kNumVariants) ? op.variant : 0];
+    if (op.variant <= 0) {
+        // automatic shape: small grids (coarse multigrid levels) are latency bound and need more,
+        // shorter CTAs to fill 148 SMs; large grids amortise the halo row over 8 rows
+        const int64_t n = (int64_t)op.Nx * op.Ny;
+        if (n < ((int64_t)1 << 20)) v = Variant{64, 2};
+        else if (n < ((int64_t)1 << 22)) v = Variant{128, 4};
+    }
     int bx = v.bx;
     while (bx > 32 && bx / 2 >= op.Nx) bx /= 2;
     a.rows_per_cta = v.ry;

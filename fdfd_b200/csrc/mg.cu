@@ -25,6 +25,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <map>
+#include <utility>
 #include <vector>
 
 namespace fdfd {
@@ -434,6 +436,7 @@ struct Level {
     C *ca = nullptr, *cb = nullptr, *cd = nullptr;   // owned when own_coefs
     bool own_coefs = false;
     C *x = nullptr, *b = nullptr, *r = nullptr, *t = nullptr;
+    C *x0 = nullptr, *r0 = nullptr, *t0 = nullptr;   // allocation-time roles (restored per apply)
     bool own_xb = true;
     double delta = 1.0;
     LineSet<C> ylines, xlines;
@@ -446,6 +449,10 @@ struct MGPrecond : Precond {
     double shift_re = 1.0, shift_im = 0.5;
     int coarse_its = 8;
     BicgWorkspace coarse_ws;
+    // CUDA-graph replay of the cycle, one executable graph per (input, output) pointer pair
+    cudaStream_t gstream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    std::map<std::pair<const void*, void*>, cudaGraphExec_t> graphs;
 
     // preconditioner of the coarsest-level Krylov solve: one smoothing sweep from a zero guess
     struct SmoothPrecond : Precond {
@@ -466,11 +473,15 @@ struct MGPrecond : Precond {
     } coarse_pre;
 
     ~MGPrecond() override {
+        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        if (gstream) cudaStreamDestroy(gstream);
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_out) cudaEventDestroy(ev_out);
         for (size_t l = 0; l < L.size(); ++l) {
             Level<C>& v = L[l];
             if (v.own_coefs) { cudaFree(v.ca); cudaFree(v.cb); cudaFree(v.cd); }
-            if (l > 0) { cudaFree(v.x); cudaFree(v.b); }
-            cudaFree(v.r); cudaFree(v.t);
+            if (l > 0) cudaFree(v.b);
+            cudaFree(v.x0); cudaFree(v.r0); cudaFree(v.t0);
             v.ylines.release(); v.xlines.release();
         }
     }
@@ -586,16 +597,45 @@ struct MGPrecond : Precond {
         return FDFD_OK;
     }
 
-    int apply(const void* v, void* z, cudaStream_t st) override {
-        ++applies;
+    // the whole cycle as a stream-ordered sequence (no host synchronisation inside)
+    int run_cycle(const void* v, void* z, cudaStream_t st) {
+        for (auto& lv : L) { lv.x = lv.x0; lv.r = lv.r0; lv.t = lv.t0; }
         Level<C>& l0 = L[0];
         const size_t bytes = (size_t)l0.op.n_local() * sizeof(C);
-        // level-0 rhs and solution live in solver-owned buffers; smoothing ping-pongs x <-> t, so
-        // work in the level's own x and copy out at the end
         l0.b = (C*)v;
         FDFD_CUDA(cudaMemsetAsync(l0.x, 0, bytes, st));
         FDFD_TRY(cycle(0, st));
         FDFD_CUDA(cudaMemcpyAsync(z, l0.x, bytes, cudaMemcpyDeviceToDevice, st));
+        return FDFD_OK;
+    }
+
+    int apply(const void* v, void* z, cudaStream_t st) override {
+        ++applies;
+        if (!o.mg_graph) return run_cycle(v, z, st);
+        const auto key = std::make_pair(v, z);
+        auto it = graphs.find(key);
+        if (it == graphs.end()) {
+            if (graphs.size() >= 256) {               // bounded cache (FGMRES uses <= 2*restart pairs)
+                for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+                graphs.clear();
+            }
+            cudaGraph_t g = nullptr;
+            FDFD_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeRelaxed));
+            int s = run_cycle(v, z, gstream);
+            cudaError_t e = cudaStreamEndCapture(gstream, &g);
+            if (s != FDFD_OK) { if (g) cudaGraphDestroy(g); return s; }
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+            cudaGraphExec_t ex = nullptr;
+            e = cudaGraphInstantiate(&ex, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+            it = graphs.emplace(key, ex).first;
+        }
+        FDFD_CUDA(cudaEventRecord(ev_in, st));
+        FDFD_CUDA(cudaStreamWaitEvent(gstream, ev_in, 0));
+        FDFD_CUDA(cudaGraphLaunch(it->second, gstream));
+        FDFD_CUDA(cudaEventRecord(ev_out, gstream));
+        FDFD_CUDA(cudaStreamWaitEvent(st, ev_out, 0));
         return FDFD_OK;
     }
 
@@ -619,6 +659,7 @@ struct MGPrecond : Precond {
             const int Nx = cur.op.Nx, Ny = cur.op.Ny;
             const size_t bytes = (size_t)Nx * Ny * sizeof(C);
             FDFD_CUDA(cudaMalloc(&cur.x, bytes)); FDFD_CUDA(cudaMalloc(&cur.r, bytes)); FDFD_CUDA(cudaMalloc(&cur.t, bytes));
+            cur.x0 = cur.x; cur.r0 = cur.r; cur.t0 = cur.t;
             if (L.size() > 1) FDFD_CUDA(cudaMalloc(&cur.b, bytes));
             FDFD_TRY(setup_lines(cur, cur.ylines, 0, lx_lo, lx_hi, st));
             FDFD_TRY(setup_lines(cur, cur.xlines, 1, ly_lo, ly_hi, st));
@@ -655,6 +696,16 @@ struct MGPrecond : Precond {
             if (o.verbose)
                 fprintf(stderr, "[fdfd] multigrid: %d levels, coarsest %d x %d (k*h = %.3f), coarse mode %d its %d\n",
                         (int)L.size(), c.op.Nx, c.op.Ny, kh, o.mg_coarse_mode, coarse_its);
+        }
+        if (o.mg_coarse_mode == 1) {
+            // the inner solver must not allocate inside the (captured) cycle
+            const Level<C>& c = L.back();
+            FDFD_TRY(coarse_ws.ensure((size_t)c.op.n_local() * sizeof(C), true));
+        }
+        if (o.mg_graph) {
+            FDFD_CUDA(cudaStreamCreateWithFlags(&gstream, cudaStreamNonBlocking));
+            FDFD_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+            FDFD_CUDA(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
         }
         FDFD_CUDA(cudaStreamSynchronize(st));
         return FDFD_OK;
