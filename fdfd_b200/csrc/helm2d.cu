@@ -22,8 +22,8 @@
 
 namespace fdfd {
 
-template <typename C, bool TM, int MODE>
-__global__ void __launch_bounds__(256) helm2d_march_kernel(HelmArgs<C> a) {
+template <typename C, bool TM, int MODE, int MINB = 9>
+__global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) {
     using R = typename real_of<C>::type;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.Nx) return;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) helm2d_march_kernel(HelmArgs<C> a) {
 
 struct Variant { int bx, ry; };
 static const Variant kVariants[] = {
-    {128, 8}, {128, 16}, {128, 32}, {256, 8}, {256, 16}, {64, 8}, {128, 4}, {64, 16}, {256, 4},
+    {128, 8}, {128, 16}, {128, 32}, {64, 4}, {64, 32}, {64, 8}, {128, 4}, {64, 16}, {128, 2},
 };
 static const int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 
@@ -214,8 +214,10 @@ HelmArgs<C> helm2d_args(const Helm2D& op, const C* x, C* y, const C* b, const C*
 template <typename C>
 int helm2d_launch_args(const Helm2D& op, int mode, HelmArgs<C>& a, cudaStream_t stream) {
     const bool TM = op.pol == FDFD_POL_TM;
-    Variant v = kVariants[(op.variant >= 0 && op.variant < kNumVariants) ? op.variant : 0];
-    if (op.variant <= 0) {
+    const int shape = op.variant & 15;
+    const bool tight = (op.variant & 16) != 0;     // experimental: 12 CTAs/SM (<= 40 registers)
+    Variant v = kVariants[(shape >= 0 && shape < kNumVariants) ? shape : 0];
+    if (shape == 0) {
         // automatic shape: small grids (coarse multigrid levels) are latency bound and need more,
         // shorter CTAs to fill 148 SMs; large grids amortise the halo row over 8 rows
         const int64_t n = (int64_t)op.Nx * op.Ny;
@@ -230,7 +232,12 @@ int helm2d_launch_args(const Helm2D& op, int mode, HelmArgs<C>& a, cudaStream_t 
 #define LAUNCH(TMv, MODEv) helm2d_march_kernel<C, TMv, MODEv><<<grid, bx, 0, stream>>>(a)
 #define LAUNCH_MODE(MODEv) do { if (TM) LAUNCH(true, MODEv); else LAUNCH(false, MODEv); } while (0)
     switch (mode) {
-        case APPLY_AX: LAUNCH_MODE(APPLY_AX); break;
+        case APPLY_AX:
+            if (tight) {
+                if (TM) helm2d_march_kernel<C, true, APPLY_AX, 12><<<grid, bx, 0, stream>>>(a);
+                else helm2d_march_kernel<C, false, APPLY_AX, 12><<<grid, bx, 0, stream>>>(a);
+            } else LAUNCH_MODE(APPLY_AX);
+            break;
         case APPLY_RESID: LAUNCH_MODE(APPLY_RESID); break;
         case APPLY_JACOBI: LAUNCH_MODE(APPLY_JACOBI); break;
         case APPLY_DINV_AX: LAUNCH_MODE(APPLY_DINV_AX); break;

@@ -452,7 +452,9 @@ struct MGPrecond : Precond {
     // CUDA-graph replay of the cycle, one executable graph per (input, output) pointer pair
     cudaStream_t gstream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-    std::map<std::pair<const void*, void*>, cudaGraphExec_t> graphs;
+    cudaGraphExec_t graph = nullptr;
+    C* in_buf = nullptr;       // fixed right-hand-side buffer of the captured cycle
+    C* out_ptr = nullptr;      // where the captured cycle leaves its result (level-0 x after the swaps)
 
     // preconditioner of the coarsest-level Krylov solve: one smoothing sweep from a zero guess
     struct SmoothPrecond : Precond {
@@ -473,7 +475,8 @@ struct MGPrecond : Precond {
     } coarse_pre;
 
     ~MGPrecond() override {
-        for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
+        if (graph) cudaGraphExecDestroy(graph);
+        cudaFree(in_buf);
         if (gstream) cudaStreamDestroy(gstream);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
@@ -597,45 +600,46 @@ struct MGPrecond : Precond {
         return FDFD_OK;
     }
 
-    // the whole cycle as a stream-ordered sequence (no host synchronisation inside)
-    int run_cycle(const void* v, void* z, cudaStream_t st) {
+    // the whole cycle as a stream-ordered sequence (no host synchronisation inside); the result
+    // is left in L[0].x
+    int run_cycle(const C* v, cudaStream_t st) {
         for (auto& lv : L) { lv.x = lv.x0; lv.r = lv.r0; lv.t = lv.t0; }
         Level<C>& l0 = L[0];
-        const size_t bytes = (size_t)l0.op.n_local() * sizeof(C);
         l0.b = (C*)v;
-        FDFD_CUDA(cudaMemsetAsync(l0.x, 0, bytes, st));
-        FDFD_TRY(cycle(0, st));
-        FDFD_CUDA(cudaMemcpyAsync(z, l0.x, bytes, cudaMemcpyDeviceToDevice, st));
-        return FDFD_OK;
+        FDFD_CUDA(cudaMemsetAsync(l0.x, 0, (size_t)l0.op.n_local() * sizeof(C), st));
+        return cycle(0, st);
     }
 
     int apply(const void* v, void* z, cudaStream_t st) override {
         ++applies;
-        if (!o.mg_graph) return run_cycle(v, z, st);
-        const auto key = std::make_pair(v, z);
-        auto it = graphs.find(key);
-        if (it == graphs.end()) {
-            if (graphs.size() >= 256) {               // bounded cache (FGMRES uses <= 2*restart pairs)
-                for (auto& kv : graphs) cudaGraphExecDestroy(kv.second);
-                graphs.clear();
-            }
+        Level<C>& l0 = L[0];
+        const size_t bytes = (size_t)l0.op.n_local() * sizeof(C);
+        if (!o.mg_graph) {
+            FDFD_TRY(run_cycle((const C*)v, st));
+            FDFD_CUDA(cudaMemcpyAsync(z, l0.x, bytes, cudaMemcpyDeviceToDevice, st));
+            return FDFD_OK;
+        }
+        if (!graph) {
+            // capture once: the cycle reads its right-hand side from in_buf and its kernel
+            // sequence / buffer roles are identical for every application
             cudaGraph_t g = nullptr;
             FDFD_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeRelaxed));
-            int s = run_cycle(v, z, gstream);
+            int s = run_cycle(in_buf, gstream);
             cudaError_t e = cudaStreamEndCapture(gstream, &g);
             if (s != FDFD_OK) { if (g) cudaGraphDestroy(g); return s; }
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
-            cudaGraphExec_t ex = nullptr;
-            e = cudaGraphInstantiate(&ex, g, 0);
+            e = cudaGraphInstantiate(&graph, g, 0);
             cudaGraphDestroy(g);
-            if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
-            it = graphs.emplace(key, ex).first;
+            if (e != cudaSuccess) { graph = nullptr; return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+            out_ptr = l0.x;
         }
+        FDFD_CUDA(cudaMemcpyAsync(in_buf, v, bytes, cudaMemcpyDeviceToDevice, st));
         FDFD_CUDA(cudaEventRecord(ev_in, st));
         FDFD_CUDA(cudaStreamWaitEvent(gstream, ev_in, 0));
-        FDFD_CUDA(cudaGraphLaunch(it->second, gstream));
+        FDFD_CUDA(cudaGraphLaunch(graph, gstream));
         FDFD_CUDA(cudaEventRecord(ev_out, gstream));
         FDFD_CUDA(cudaStreamWaitEvent(st, ev_out, 0));
+        FDFD_CUDA(cudaMemcpyAsync(z, out_ptr, bytes, cudaMemcpyDeviceToDevice, st));
         return FDFD_OK;
     }
 
@@ -703,6 +707,7 @@ struct MGPrecond : Precond {
             FDFD_TRY(coarse_ws.ensure((size_t)c.op.n_local() * sizeof(C), true));
         }
         if (o.mg_graph) {
+            FDFD_CUDA(cudaMalloc(&in_buf, (size_t)L[0].op.n_local() * sizeof(C)));
             FDFD_CUDA(cudaStreamCreateWithFlags(&gstream, cudaStreamNonBlocking));
             FDFD_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
             FDFD_CUDA(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));

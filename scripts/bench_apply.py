@@ -30,7 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--N", type=int, nargs="+", default=[4096])
     ap.add_argument("--dtypes", nargs="+", default=["complex128", "complex64"])
-    ap.add_argument("--variants", type=int, nargs="+", default=list(range(9)))
+    ap.add_argument("--variants", type=int, nargs="+", default=list(range(9)) + [16, 17, 22])
     args = ap.parse_args()
     peaks = {}
     try:
