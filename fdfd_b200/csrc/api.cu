@@ -158,11 +158,11 @@ extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
     o->precond = FDFD_PRECOND_JACOBI;
     o->rtol = 1e-8;
     o->maxit = 100000;
-    o->restart = 30;
+    o->restart = 20;
     o->mg_levels = 0;
     o->mg_pre = 1; o->mg_post = 1;
-    o->mg_shift_re = 1.0; o->mg_shift_im = 0.5;
-    o->mg_omega = 0.8;
+    o->mg_shift_re = 1.0; o->mg_shift_im = 0.4;
+    o->mg_omega = 0.7;
     o->mg_cycle = 1;
     o->mg_coarse_its = 0;          /* 0 = automatic from k*h of the coarsest level */
     o->mg_coarse_mode = 1;
@@ -172,7 +172,7 @@ extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
     o->line_x_lo = o->line_x_hi = o->line_y_lo = o->line_y_hi = 0;
     o->mg_wfrom = 3;
     o->mg_min_n = 32;
-    o->reorth = 1;
+    o->reorth = 0;
 }
 
 extern "C" int fdfd_krylov_solve(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts, const void* b,

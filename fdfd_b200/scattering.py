@@ -35,7 +35,7 @@ class FDFD2DScatteringSolver:
     eps0 = 8.854187817e-12        # Scattering_Solver_2D.py:25
 
     #: default solver settings; override per instance (``sim.solver_options.update(...)``)
-    DEFAULT_SOLVER = dict(method="fgmres", precond="mg", rtol=1e-8, maxit=5000, restart=30, reorth=0)
+    DEFAULT_SOLVER = dict(method="fgmres", precond="mg", rtol=1e-8, maxit=5000)
 
     def __init__(self, frequency, x_range, y_range, Nx, Ny, *, dtype="complex128", device=None):
         self.frequency = float(frequency)

@@ -54,6 +54,7 @@ def test_precond_apply_matches_oracle(pol, cfg):
     ref = Mo(v)
     A = fdfd_b200.HelmholtzOperator2D(pol, N, N, ca, cb, cd, sx, sy)
     z = A.precond_apply(torch.from_numpy(v).cuda(), precond="mg", mg_levels=levels, mg_min_n=min_n,
+                        mg_shift_re=1.0, mg_shift_im=0.5, mg_omega=0.8,
                         mg_coarse_its=cfg["coarse_its"], mg_wfrom=wfrom, mg_coarse_mode=cmode, mg_kh_max=kh_max,
                         line_x_lo=lines[0], line_x_hi=lines[1],
                         line_y_lo=lines[2], line_y_hi=lines[3]).cpu().numpy()
@@ -73,6 +74,7 @@ def test_precond_reduces_shifted_residual():
     g = torch.Generator(device="cuda").manual_seed(1)
     v = torch.complex(torch.randn(N * N, generator=g, device="cuda", dtype=torch.float64),
                       torch.randn(N * N, generator=g, device="cuda", dtype=torch.float64))
-    z = A.precond_apply(v, precond="mg", line_x_lo=24, line_x_hi=24, line_y_lo=24, line_y_hi=24)
+    z = A.precond_apply(v, precond="mg", line_x_lo=24, line_x_hi=24, line_y_lo=24, line_y_hi=24,
+                        mg_shift_re=1.0, mg_shift_im=0.5)
     res = torch.linalg.vector_norm(v - Ms.apply(z)) / torch.linalg.vector_norm(v)
     assert res.item() < 0.5
