@@ -22,13 +22,14 @@
 
 namespace fdfd {
 
-// Face multipliers that realise walls / Bloch wrap (see file header); evaluated on the fly for
-// the few threads / rows that touch a boundary so that they do not occupy registers in the
-// interior fast path.
-template <typename R>
-struct FaceFlags { R w_on, e_on, w_c2, e_c2, s_on, n_on, s_c2, n_c2; };
+// Register budget: the loop needs ~70 registers (c128) to keep all seven loads of a row in flight;
+// capping it lower makes ptxas serialise the loads into 3-4 dependent round trips per row
+// (measured: 56 regs / 9 CTAs per SM = 5.3 TB/s, 70 regs / 7 CTAs = 6.35 TB/s at 4096^2).
+template <typename C> __host__ __device__ constexpr int default_min_blocks(int mode) {
+    return sizeof(C) == 16 ? (mode >= APPLY_JACOBI ? 6 : 7) : (mode >= APPLY_JACOBI ? 8 : 9);
+}
 
-template <typename C, bool TM, int MODE, int MINB = (MODE >= APPLY_JACOBI ? 8 : 9)>
+template <typename C, bool TM, int MODE, int MINB = default_min_blocks<C>(MODE)>
 __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) {
     using R = typename real_of<C>::type;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -38,9 +39,24 @@ __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) 
     const int je = min(jb + a.rows_per_cta, Ny);
     if (jb >= je) return;
 
-    const bool col_edge = (i == 0) || (i == Nx - 1);
-    const int iw = (i == 0) ? Nx - 1 : i - 1;
-    const int ie = (i == Nx - 1) ? 0 : i + 1;
+    // x-direction neighbour bookkeeping (column constants)
+    const bool west_edge = (i == 0), east_edge = (i == Nx - 1);
+    const int iw = west_edge ? Nx - 1 : i - 1;
+    const int ie = east_edge ? 0 : i + 1;
+    // multipliers that realise wall / Bloch behaviour on the two x faces
+    R w_on = 1, e_on = 1;      // face present?
+    R w_c2 = 1, e_c2 = 1;      // centre weight on that face
+    bool w_ph = false, e_ph = false;
+    if (west_edge) {
+        if (a.bcx) { w_ph = true; if (!TM) w_c2 = a.phx2; }
+        else if (!TM) w_on = 0;          // TE: no flux through the near wall
+    }
+    if (east_edge) {
+        if (a.bcx) { e_ph = true; if (TM) e_c2 = a.phx2; }
+        else if (TM) e_on = 0;           // TM: no flux through the far wall
+    }
+    const bool west_wall_val = west_edge && !a.bcx;   // x_-1 = 0
+    const bool east_wall_val = east_edge && !a.bcx;   // x_N  = 0
 
     const C* xcol = a.x + i;
     const C* cbcol = a.cb + i;
@@ -74,74 +90,52 @@ __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) 
 
     for (int j = jb; j < je; ++j) {
         const int64_t row = (int64_t)j * Nx;
-        const bool plain = !col_edge && (j + 1 < Ny) && (j > 0);
-        C xn, cb_hi, xw, xe, ca_w, ca_e, ax, dg;
-        if (plain) {
-            // ---- interior fast path: no walls, no wrap ------------------------------------------
+        // north value and the second cb of this row
+        C xn, cb_hi;
+        R n_on = 1, s_c2 = 1, n_c2 = 1;
+        if (j + 1 < Ny) {
             xn = xcol[row + Nx];
             cb_hi = TM ? ld_stream(cbcol + row + Nx) : ld_stream(cbcol + row);
-            xw = a.x[row + i - 1];
-            xe = a.x[row + i + 1];
-            if (TM) { ca_w = a.ca[row + i]; ca_e = a.ca[row + i + 1]; }
-            else    { ca_w = a.ca[row + i - 1]; ca_e = a.ca[row + i]; }
-            const C tx = csub(cmul(ca_e, csub(xe, xc)), cmul(ca_w, csub(xc, xw)));
-            const C ty = csub(cmul(cb_hi, csub(xn, xc)), cmul(cb_lo, csub(xc, xs)));
-            ax = cadd(cscale(a.sx, tx), cscale(a.sy, ty));
-            if (MODE >= APPLY_JACOBI)
-                dg = cadd(cscale(-a.sx, cadd(ca_e, ca_w)), cscale(-a.sy, cadd(cb_hi, cb_lo)));
         } else {
-            // ---- boundary path ----------------------------------------------------------------------
-            FaceFlags<R> f = {1, 1, 1, 1, 1, 1, 1, 1};
-            bool w_ph = false, e_ph = false;
-            if (i == 0) {
-                if (a.bcx) { w_ph = true; if (!TM) f.w_c2 = a.phx2; }
-                else if (!TM) f.w_on = 0;          // TE: no flux through the near wall
-            }
-            if (i == Nx - 1) {
-                if (a.bcx) { e_ph = true; if (TM) f.e_c2 = a.phx2; }
-                else if (TM) f.e_on = 0;           // TM: no flux through the far wall
-            }
-            if (j + 1 < Ny) {
-                xn = xcol[row + Nx];
-                cb_hi = TM ? ld_stream(cbcol + row + Nx) : ld_stream(cbcol + row);
+            if (a.x_north) {
+                xn = a.x_north[i];
+                if (a.north_wrap) { xn = cmul(a.phy, xn); if (TM) n_c2 = a.phy2; }
             } else {
-                if (a.x_north) {
-                    xn = a.x_north[i];
-                    if (a.north_wrap) { xn = cmul(a.phy, xn); if (TM) f.n_c2 = a.phy2; }
-                } else {
-                    xn = czero<C>();
-                }
-                if (TM) {
-                    if (a.cb_ghost) cb_hi = a.cb_ghost[i];
-                    else { cb_hi = czero<C>(); f.n_on = 0; }   // TM: no flux through the far wall
-                } else {
-                    cb_hi = ld_stream(cbcol + row);
-                }
+                xn = czero<C>();
             }
-            if (!TM && j == 0 && a.south_wrap) f.s_c2 = a.phy2;
-            xw = a.x[row + iw];
-            xe = a.x[row + ie];
-            if (w_ph) xw = cmulc(a.phx, xw);
-            if (e_ph) xe = cmul(a.phx, xe);
-            if (i == 0 && !a.bcx) xw = czero<C>();         // x_-1 = 0
-            if (i == Nx - 1 && !a.bcx) xe = czero<C>();    // x_N  = 0
-            if (TM) { ca_w = a.ca[row + i]; ca_e = a.ca[row + ie]; }
-            else    { ca_w = a.ca[row + iw]; ca_e = a.ca[row + i]; }
-            const C fe = cmul(ca_e, csub(xe, cscale(f.e_c2, xc)));
-            const C fw = cmul(ca_w, csub(cscale(f.w_c2, xc), xw));
-            const C tx = csub(cscale(f.e_on, fe), cscale(f.w_on, fw));
-            const C fn = cmul(cb_hi, csub(xn, cscale(f.n_c2, xc)));
-            const C fs = cmul(cb_lo, csub(cscale(f.s_c2, xc), xs));
-            const C ty = csub(cscale(f.n_on, fn), fs);
-            ax = cadd(cscale(a.sx, tx), cscale(a.sy, ty));
-            if (MODE >= APPLY_JACOBI)
-                dg = cadd(cscale(-a.sx, cadd(cscale(f.e_on * f.e_c2, ca_e), cscale(f.w_on * f.w_c2, ca_w))),
-                          cscale(-a.sy, cadd(cscale(f.n_on * f.n_c2, cb_hi), cscale(f.s_c2, cb_lo))));
+            if (TM) {
+                if (a.cb_ghost) cb_hi = a.cb_ghost[i];
+                else { cb_hi = czero<C>(); n_on = 0; }   // TM: no flux through the far wall
+            } else {
+                cb_hi = ld_stream(cbcol + row);
+            }
         }
+        if (!TM && j == 0 && a.south_wrap) s_c2 = a.phy2;
+
+        // x neighbours of the centre row (L1 hits) and the two ca values
+        C xw = a.x[row + iw], xe = a.x[row + ie];
+        if (w_ph) xw = cmulc(a.phx, xw);
+        if (e_ph) xe = cmul(a.phx, xe);
+        if (west_wall_val) xw = czero<C>();
+        if (east_wall_val) xe = czero<C>();
+        C ca_w, ca_e;
+        if (TM) { ca_w = a.ca[row + i]; ca_e = a.ca[row + ie]; }
+        else    { ca_w = a.ca[row + iw]; ca_e = a.ca[row + i]; }
+
+        // fluxes
+        C fe = cmul(ca_e, csub(xe, cscale(e_c2, xc)));
+        C fw = cmul(ca_w, csub(cscale(w_c2, xc), xw));
+        C tx = csub(cscale(e_on, fe), cscale(w_on, fw));
+        C c_s = TM ? cb_lo : cb_lo;      // south face coefficient: TE cb[j-1], TM cb[j]
+        C c_n = cb_hi;                   // north face coefficient: TE cb[j],   TM cb[j+1]
+        C fn = cmul(c_n, csub(xn, cscale(n_c2, xc)));
+        C fs = cmul(c_s, csub(cscale(s_c2, xc), xs));
+        C ty = csub(cscale(n_on, fn), fs);
+        C ax = cadd(cscale(a.sx, tx), cscale(a.sy, ty));
+        C dterm = czero<C>();
         if (a.cd) {
-            const C dterm = cmul(a.shift, ld_stream(a.cd + row + i));
+            dterm = cmul(a.shift, ld_stream(a.cd + row + i));
             ax = cfma(dterm, xc, ax);
-            if (MODE >= APPLY_JACOBI) dg = cadd(dg, dterm);
         }
 
         C out;
@@ -149,27 +143,33 @@ __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) 
             out = ax;
         } else if (MODE == APPLY_RESID) {
             out = csub(ld_stream(a.b + row + i), ax);
-        } else if (MODE == APPLY_JACOBI) {
-            const C r = csub(ld_stream(a.b + row + i), ax);
-            out = cadd(xc, cscale(a.omega, cdiv(r, dg)));
-        } else if (MODE == APPLY_SMOOTH) {
-            const C r = csub(ld_stream(a.b + row + i), ax);
-            if (in_strip) {
-                out = xc;
-                a.line_rhs[(int64_t)(a.row0 + j) * line_nl + line_idx] = r;
-            } else {
-                out = cadd(xc, cscale(a.omega, cdiv(r, dg)));
-            }
-        } else if (MODE == APPLY_DINV) {
-            out = cdiv(mk<C>(1, 0), dg);
         } else {
-            out = cdiv(ax, dg);
+            // diagonal of A at this point
+            C dg = cadd(cscale(-a.sx, cadd(cscale(e_on * e_c2, ca_e), cscale(w_on * w_c2, ca_w))),
+                        cscale(-a.sy, cadd(cscale(n_on * n_c2, c_n), cscale(s_c2, c_s))));
+            dg = cadd(dg, dterm);
+            if (MODE == APPLY_JACOBI) {
+                C r = csub(ld_stream(a.b + row + i), ax);
+                out = cadd(xc, cscale(a.omega, cdiv(r, dg)));
+            } else if (MODE == APPLY_SMOOTH) {
+                C r = csub(ld_stream(a.b + row + i), ax);
+                if (in_strip) {
+                    out = xc;
+                    a.line_rhs[(int64_t)(a.row0 + j) * line_nl + line_idx] = r;
+                } else {
+                    out = cadd(xc, cscale(a.omega, cdiv(r, dg)));
+                }
+            } else if (MODE == APPLY_DINV) {
+                out = cdiv(mk<C>(1, 0), dg);
+            } else {
+                out = cdiv(ax, dg);
+            }
         }
         a.y[row + i] = out;
 
         // rotate the window
         xs = xc; xc = xn;
-        cb_lo = cb_hi;
+        cb_lo = TM ? cb_hi : cb_hi;
     }
 }
 
@@ -221,8 +221,7 @@ HelmArgs<C> helm2d_args(const Helm2D& op, const C* x, C* y, const C* b, const C*
 template <typename C>
 int helm2d_launch_args(const Helm2D& op, int mode, HelmArgs<C>& a, cudaStream_t stream) {
     const bool TM = op.pol == FDFD_POL_TM;
-    const int shape = op.variant & 15;
-    const bool tight = (op.variant & 16) != 0;     // experimental: 10 CTAs/SM (<= 51 registers)
+    const int shape = op.variant;
     Variant v = kVariants[(shape >= 0 && shape < kNumVariants) ? shape : 0];
     if (shape == 0) {
         // automatic shape: small grids (coarse multigrid levels) are latency bound and need more,
@@ -239,12 +238,7 @@ int helm2d_launch_args(const Helm2D& op, int mode, HelmArgs<C>& a, cudaStream_t 
 #define LAUNCH(TMv, MODEv) helm2d_march_kernel<C, TMv, MODEv><<<grid, bx, 0, stream>>>(a)
 #define LAUNCH_MODE(MODEv) do { if (TM) LAUNCH(true, MODEv); else LAUNCH(false, MODEv); } while (0)
     switch (mode) {
-        case APPLY_AX:
-            if (tight) {
-                if (TM) helm2d_march_kernel<C, true, APPLY_AX, 10><<<grid, bx, 0, stream>>>(a);
-                else helm2d_march_kernel<C, false, APPLY_AX, 10><<<grid, bx, 0, stream>>>(a);
-            } else LAUNCH_MODE(APPLY_AX);
-            break;
+        case APPLY_AX: LAUNCH_MODE(APPLY_AX); break;
         case APPLY_RESID: LAUNCH_MODE(APPLY_RESID); break;
         case APPLY_JACOBI: LAUNCH_MODE(APPLY_JACOBI); break;
         case APPLY_DINV_AX: LAUNCH_MODE(APPLY_DINV_AX); break;

@@ -30,7 +30,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--N", type=int, nargs="+", default=[4096])
     ap.add_argument("--dtypes", nargs="+", default=["complex128", "complex64"])
-    ap.add_argument("--variants", type=int, nargs="+", default=list(range(9)) + [16, 17, 22])
+    ap.add_argument("--variants", type=int, nargs="+", default=list(range(9)))
+    ap.add_argument("--pads", type=int, nargs="+", default=[0], help="extra bytes between the 5 arrays (alignment experiment)")
     args = ap.parse_args()
     peaks = {}
     try:
@@ -46,17 +47,25 @@ def main():
             def rnd():
                 return torch.complex(torch.rand(N, N, generator=g, device="cuda", dtype=rd) + 0.5,
                                      torch.rand(N, N, generator=g, device="cuda", dtype=rd) - 0.5)
-            ca, cb, cd, x = rnd(), rnd(), rnd(), rnd()
-            y = torch.empty_like(x)
-            for pol in ("TE", "TM"):
-                A = fdfd_b200.HelmholtzOperator2D(pol, N, N, ca, cb, cd, 63.3, 63.3, dtype=dtype)
-                for v in args.variants:
-                    A.set_variant(v)
-                    med, best = timeit(lambda: A.apply(x, out=y))
-                    gbs = A.bytes_per_apply / med / 1e6
-                    print(json.dumps(dict(kernel="helm2d_apply", N=N, dtype=dtype, pol=pol, variant=v,
-                                          ms=round(med, 4), best_ms=round(best, 4), GBps=round(gbs, 1),
-                                          frac_of_measured_peak=round(gbs / peak, 3))), flush=True)
+            for pad in args.pads:
+                # carve the five arrays out of one pool with `pad` extra bytes between them
+                nbytes = N * N * (16 if dtype == "complex128" else 8)
+                pool = torch.empty(5 * (nbytes + pad) + 4096, dtype=torch.uint8, device="cuda")
+                def carve(k):
+                    return pool[k * (nbytes + pad): k * (nbytes + pad) + nbytes].view(td).view(N, N)
+                ca, cb, cd, x, y = (carve(k) for k in range(5))
+                for t in (ca, cb, cd, x):
+                    t.copy_(rnd())
+                for pol in ("TE", "TM"):
+                    A = fdfd_b200.HelmholtzOperator2D(pol, N, N, ca, cb, cd, 63.3, 63.3, dtype=dtype)
+                    for v in args.variants:
+                        A.set_variant(v)
+                        med, best = timeit(lambda: A.apply(x, out=y))
+                        gbs = A.bytes_per_apply / med / 1e6
+                        print(json.dumps(dict(kernel="helm2d_apply", N=N, dtype=dtype, pol=pol, variant=v, pad=pad,
+                                              ms=round(med, 4), best_ms=round(best, 4), GBps=round(gbs, 1),
+                                              frac_of_measured_peak=round(gbs / peak, 3))), flush=True)
+            x = x.clone(); y = torch.empty_like(x)
             # reference points: torch copy (the MEASURED_PEAKS methodology) and a 3-read/1-write elementwise op
             med, best = timeit(lambda: y.copy_(x))
             print(json.dumps(dict(kernel="torch_copy", N=N, dtype=dtype, ms=round(med, 4),
