@@ -233,13 +233,21 @@ int fgmres_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x,
     Scalars sc;
     ScalarsGuard guard{sc};
     FDFD_TRY(sc.alloc());
-    DeviceBuf bV, bZ, bw;
+    // LGMRES-style augmentation: the last `kaug` slots of every cycle are filled with the
+    // (normalised) corrections of the previous cycles instead of new Krylov directions; this
+    // removes most of the stagnation that restarting causes on the indefinite Helmholtz operator
+    int kaug = o.lgmres_k > 0 ? o.lgmres_k : 0;
+    if (kaug > m / 2) kaug = m / 2;
+    DeviceBuf bV, bZ, bw, bE;
     FDFD_TRY(bV.alloc(bytes * (m + 1)));
-    if (M) FDFD_TRY(bZ.alloc(bytes * m));
+    if (M || kaug) FDFD_TRY(bZ.alloc(bytes * m));
+    if (kaug) FDFD_TRY(bE.alloc(bytes * kaug));
     FDFD_TRY(bw.alloc(bytes));
     C* V = (C*)bV.p;
-    C* Z = M ? (C*)bZ.p : V;
+    C* Z = (M || kaug) ? (C*)bZ.p : V;
+    C* E = (C*)bE.p;
     C* w = (C*)bw.p;
+    int naug = 0, aug_next = 0;
     Comm* comm = A.comm;
     std::vector<double2> hbuf(m + 8);
     std::vector<cd> H((size_t)(m + 1) * m), g(m + 1), cs(m), sn(m), y(m);
@@ -273,7 +281,15 @@ int fgmres_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x,
         for (int j = 0; j < m; ++j) {
             C* vj = V + (int64_t)j * n;
             C* zj = Z + (int64_t)j * n;
-            if (M) { FDFD_TRY(M->apply(vj, zj, stream)); ++info.precond_applies; }
+            if (j >= m - naug) {
+                // augmented direction: a previous correction (oldest first)
+                const int q = (aug_next + kaug - naug + (j - (m - naug))) % kaug;
+                FDFD_CUDA(cudaMemcpyAsync(zj, E + (int64_t)q * n, bytes, cudaMemcpyDeviceToDevice, stream));
+            } else if (M) {
+                FDFD_TRY(M->apply(vj, zj, stream)); ++info.precond_applies;
+            } else if (kaug) {
+                FDFD_CUDA(cudaMemcpyAsync(zj, vj, bytes, cudaMemcpyDeviceToDevice, stream));
+            }
             FDFD_TRY(helm2d_apply(A, APPLY_AX, zj, w, nullptr, 0.0, stream)); ++info.op_applies;
             // classical Gram-Schmidt with one re-orthogonalisation pass, fused multi-vector kernels
             const int passes = o.reorth ? 2 : 1;
@@ -325,7 +341,19 @@ int fgmres_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x,
         }
         for (int i = 0; i < k; ++i) hbuf[i] = make_double2(y[i].real(), y[i].imag());
         FDFD_CUDA(cudaMemcpyAsync(sc.slot + S_H0, hbuf.data(), sizeof(double2) * k, cudaMemcpyHostToDevice, stream));
-        FDFD_TRY(multi_axpy<C>(n, k, Z, n, x, S_H0, 1.0, -1, sc, stream));
+        if (kaug) {
+            // dx = Z y kept (normalised) as an augmentation vector for the next cycles
+            C* e = E + (int64_t)aug_next * n;
+            FDFD_CUDA(cudaMemsetAsync(e, 0, bytes, stream));
+            FDFD_TRY(multi_axpy<C>(n, k, Z, n, e, S_H0, 1.0, S_TMP1, sc, stream));
+            FDFD_TRY(allreduce_slots(comm, sc, S_TMP1, 1, stream));
+            FDFD_TRY(lincomb<C>(n, x, nullptr, x, nullptr, e, nullptr, nullptr, 0, nullptr, -1, -1, sc, stream));
+            FDFD_TRY(scale_inv_sqrt<C>(n, e, e, S_TMP1, sc, stream));
+            aug_next = (aug_next + 1) % kaug;
+            if (naug < kaug) ++naug;
+        } else {
+            FDFD_TRY(multi_axpy<C>(n, k, Z, n, x, S_H0, 1.0, -1, sc, stream));
+        }
         FDFD_CUDA(cudaStreamSynchronize(stream));
     }
     // true residual

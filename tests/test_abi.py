@@ -37,7 +37,7 @@ def test_header_symbols_exported(lib):
 def test_opts_struct_layout(lib):
     from fdfd_b200 import _lib
     o = _lib.default_opts()
-    assert o.rtol == 1e-8 and o.restart == 20 and o.mg_shift_im == 0.4 and o.reorth == 0 and o.mg_graph == 1
+    assert o.rtol == 1e-8 and o.restart == 30 and o.lgmres_k == 0 and o.mg_shift_im == 0.4 and o.reorth == 0 and o.mg_graph == 1
     # the C side zero-fills beyond the fields it knows; a size mismatch would corrupt the tail
     assert C.sizeof(_lib.KrylovOpts) % 8 == 0
 
