@@ -3,12 +3,14 @@
 Public surface (names as in SolverNotConverging/FDFD):
     yeeder2d(NS, RES, BC, kinc=None)          GPU assembly of the Yee derivative operators
     FDFD2DScatteringSolver                    2-D TEz/TMz scattering, matrix-free GPU Krylov solve
+    BandDiagramSolver2D                       photonic band structure, GPU Krylov-Schur shift-invert
     HelmholtzOperator2D                       the matrix-free operator + solver handle
 """
 from ._lib import FdfdError, NoConvergence, LIB_PATH  # noqa: F401
 from .yee_derivative import yeeder2d, yeeder2d_device  # noqa: F401
 from .operators import HelmholtzOperator2D, SlabComm, slab_rows  # noqa: F401
 from .scattering import FDFD2DScatteringSolver  # noqa: F401
+from .band_diagram import BandDiagramSolver2D, BandStructureResult  # noqa: F401
 
 __all__ = ["yeeder2d", "yeeder2d_device", "HelmholtzOperator2D", "SlabComm", "slab_rows",
-           "FDFD2DScatteringSolver", "FdfdError", "NoConvergence"]
+           "FDFD2DScatteringSolver", "BandDiagramSolver2D", "BandStructureResult", "FdfdError", "NoConvergence"]

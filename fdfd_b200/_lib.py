@@ -68,6 +68,12 @@ _PROTOTYPES = {
     "fdfd_krylov_default_opts": (None, [C.POINTER(KrylovOpts)]),
     "fdfd_krylov_solve": (C.c_int, [C.c_void_p, C.POINTER(KrylovOpts), C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),
     "fdfd_krylov_solve_host": (C.c_int, [C.c_void_p, C.POINTER(KrylovOpts), C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "fdfd_blas_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "fdfd_blas_destroy": (None, [C.c_void_p]),
+    "fdfd_blas_multi_dot": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "fdfd_blas_multi_axpy": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "fdfd_precond_apply": (C.c_int, [C.c_void_p, C.POINTER(KrylovOpts), C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdfd_comm_unique_id": (C.c_int, [C.c_void_p]),
     "fdfd_comm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),

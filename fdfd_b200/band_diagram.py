@@ -1,0 +1,278 @@
+"""GPU drop-in for the reference's ``BandDiagramSolver2D``
+(Band_Diagram_Solver/Band_Diagram_Solver.py:58-560): same constructor, geometry helpers, Bloch
+path utilities and ``compute_band_structure`` contract (``BandStructureResult`` with
+``frequencies[pol]`` (num_bands, N) = a/lambda and ``eigenvalues[pol]`` = (omega/c)^2).
+
+What changed underneath:
+  * per Bloch vector the reference rebuilds four sparse operators with ``yeeder2d`` and two
+    sparse products (Band_Diagram_Solver.py:304-319); here the pencil is the matrix-free K2
+    operator (only the two Bloch phases change between path points);
+  * ``eigs(A, M=M, k, sigma)`` (ARPACK mode 3 + SuperLU, :313/:320) is replaced by the GPU
+    Krylov-Schur solver of ``fdfd_b200/eigs.py`` around a shifted solve on the device: a dense
+    LU of the (few thousand unknown) unit-cell operator, assembled on the GPU from five
+    phase-independent pieces, or the K3 Krylov solver for large cells.
+The shift actually used is ``eig_sigma - delta`` (delta > 0): the pencil's eigenvalues do not
+depend on it, and it keeps the shifted operator non-singular at Gamma where the reference's
+``sigma = 0`` is exactly singular (the reference relies on SuperLU surviving that).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Iterable, Sequence
+
+import numpy as np
+
+from . import eigs as _eigs
+from .operators import HelmholtzOperator2D
+
+MaskLike = "np.ndarray | Callable[[np.ndarray, np.ndarray], np.ndarray]"
+
+
+@dataclass
+class BandStructureResult:
+    """Same container as the reference (Band_Diagram_Solver.py:30-55)."""
+    beta_path: np.ndarray
+    tick_positions: list
+    tick_labels: list
+    frequencies: dict
+    eigenvalues: dict
+
+
+class BandDiagramSolver2D:
+    #: unit cells up to this many unknowns use the dense-LU shifted solve
+    DENSE_LIMIT = 6000
+
+    def __init__(self, a, Nx, Ny=None, *, b=None, background_er=1.0, background_ur=1.0,
+                 boundary_conditions=(1, 1), device=None):
+        self.a = float(a)
+        self.b = float(b) if b is not None else float(a)
+        self.Nx = int(Nx)
+        self.Ny = int(Ny) if Ny is not None else int(Nx)
+        self.boundary_conditions = tuple(boundary_conditions)
+        self.dx, self.dy = self.a / self.Nx, self.b / self.Ny
+        self.Nx2, self.Ny2 = 2 * self.Nx, 2 * self.Ny
+        self.dx2, self.dy2 = self.dx / 2, self.dy / 2
+        xa2 = np.arange(1, self.Nx2 + 1) * self.dx2
+        ya2 = np.arange(1, self.Ny2 + 1) * self.dy2
+        self.xa2 = xa2 - np.mean(xa2)
+        self.ya2 = ya2 - np.mean(ya2)
+        self.X2, self.Y2 = np.meshgrid(self.xa2, self.ya2, indexing="ij")
+        self.ER2 = np.full((self.Nx2, self.Ny2), background_er, dtype=complex)
+        self.UR2 = np.full((self.Nx2, self.Ny2), background_ur, dtype=complex)
+        self._beta_path = None
+        self._results = None
+        self.device = device
+        self.solver_info = {}
+
+    # ---- geometry (host, as the reference: Band_Diagram_Solver.py:119-181) ---------------------
+    def add_object(self, mask, *, er=None, ur=None):
+        sel = np.asarray(mask(self.X2, self.Y2) if callable(mask) else mask, dtype=bool)
+        if sel.shape != self.ER2.shape:
+            raise ValueError("Mask must match the helper grid shape (2× resolution).")
+        for name, val in (("ER2", er), ("UR2", ur)):
+            if val is None:
+                continue
+            arr = np.asarray(val, dtype=complex)
+            if arr.shape not in ((), sel.shape):
+                raise ValueError(f"{name[:2].lower()} must be a scalar or have the same shape as the mask.")
+            setattr(self, name, np.where(sel, arr, getattr(self, name)))
+
+    def add_circular_inclusion(self, radius, *, center=(0.0, 0.0), er=None, ur=None):
+        cx, cy = center
+        self.add_object((self.X2 - cx) ** 2 + (self.Y2 - cy) ** 2 <= radius ** 2, er=er, ur=ur)
+
+    # ---- Bloch path (Band_Diagram_Solver.py:183-251, :338-355) --------------------------------------
+    def default_rectangular_lattice_path(self):
+        gx, gy = 2 * np.pi / self.a, 2 * np.pi / self.b
+        pts = [np.array([0.0, 0.0]), 0.5 * np.array([gx, 0.0]), 0.5 * np.array([gx, gy]), np.array([0.0, 0.0])]
+        return pts, ["Γ", "X", "M", "Γ"]
+
+    def generate_bloch_path(self, symmetry_points, total_points):
+        if total_points < len(symmetry_points):
+            raise ValueError("total_points must be at least the number of symmetry points.")
+        pts = np.asarray(symmetry_points, dtype=float)
+        if pts.ndim != 2 or pts.shape[1] != 2:
+            raise ValueError("symmetry_points must be an iterable of 2D coordinates.")
+        seg = np.linalg.norm(np.diff(pts, axis=0), axis=1)
+        total = seg.sum()
+        if total == 0:
+            seg = np.ones_like(seg)
+            total = seg.sum()
+        remaining = total_points - 1
+        counts = [max(1, int(round(remaining * (length / total)))) for length in seg]
+        diff, idx = remaining - sum(counts), 0
+        while diff != 0 and counts:
+            c = idx % len(counts)
+            if diff > 0:
+                counts[c] += 1
+                diff -= 1
+            elif counts[c] > 1:
+                counts[c] -= 1
+                diff += 1
+            idx += 1
+        betas, ticks, acc = [pts[0]], [0], 0
+        for start, stop, n_seg in zip(pts[:-1], pts[1:], counts):
+            betas.extend(start + (s / n_seg) * (stop - start) for s in range(1, n_seg + 1))
+            acc += n_seg
+            ticks.append(acc)
+        beta_path = np.column_stack(betas)
+        self._beta_path = beta_path
+        self._tick_positions = list(ticks)
+        return beta_path, ticks
+
+    def set_tick_labels(self, labels, positions):
+        if len(labels) != len(positions):
+            raise ValueError("labels and positions must have the same length.")
+        self._tick_labels = list(labels)
+        self._tick_positions = list(positions)
+
+    def _tick_positions_from_path(self, beta_path):
+        if self._beta_path is None or not np.array_equal(beta_path, self._beta_path):
+            return list(range(beta_path.shape[1]))
+        return list(getattr(self, "_tick_positions", range(beta_path.shape[1])))
+
+    # ---- materials on the Yee grid (Band_Diagram_Solver.py:536-550) ---------------------------------
+    def _yee_tensors(self):
+        return dict(ERxx=self.ER2[1::2, ::2], ERyy=self.ER2[::2, 1::2], ERzz=self.ER2[::2, 1::2],
+                    URxx=self.UR2[1::2, ::2], URyy=self.UR2[::2, 1::2], URzz=self.UR2[::2, 1::2])
+
+    def _pencil_arrays(self, pol):
+        """(K2 operator type, ca, cb, M) as (Ny, Nx) arrays: the reference flattens its (Nx, Ny)
+        arrays with order='F' (:286-291), i.e. n = i + Nx*j = C-order of the transpose."""
+        t = self._yee_tensors()
+        tr = lambda a: np.ascontiguousarray(a.T)  # noqa: E731
+        if pol == "TM":   # A_tm = -DHX URyy^-1 DEX - DHY URxx^-1 DEY, M = ERzz   (:312-313)
+            return "TE", tr(1.0 / t["URyy"]), tr(1.0 / t["URxx"]), tr(t["ERzz"])
+        return "TM", tr(1.0 / t["ERyy"]), tr(1.0 / t["ERxx"]), tr(t["URzz"])  # (:319-320)
+
+    def _operator(self, kind, ca, cb, cd, phase):
+        return HelmholtzOperator2D(kind, self.Nx, self.Ny, ca, cb, cd, -1.0 / self.dx ** 2, -1.0 / self.dy ** 2,
+                                   bc=self.boundary_conditions, phase=phase, device=self.device)
+
+    def _phases(self, beta):
+        # exp(-1j*k*N*d) exactly as yeeder2d evaluates it (yee_derivative.py:56,67)
+        return (np.exp(-1j * beta[0] * self.Nx * self.dx), np.exp(-1j * beta[1] * self.Ny * self.dy))
+
+    def _dense(self, op):
+        """Dense matrix of a K2 operator: one stencil apply per unit vector (unit cells only)."""
+        import torch
+        n = op.n
+        D = torch.empty((n, n), dtype=op.tdtype, device=op.device)
+        e = torch.zeros(n, dtype=op.tdtype, device=op.device)
+        for c in range(n):
+            e[c] = 1.0
+            op.apply(e, out=D[c])          # row c of D^T = column c of the operator
+            e[c] = 0.0
+        return D.T.contiguous()
+
+    def _dense_pieces(self, kind, ca, cb, cdev):
+        """The shifted operator is affine in (phx, conj phx, phy, conj phy):
+        S(phx, phy) = C0 + phx*Cx + conj(phx)*Cx' + phy*Cy + conj(phy)*Cy'.  Five assemblies at fixed
+        phases determine the pieces once per polarisation; every path point is then a 5-term
+        elementwise combination on the device."""
+        S = {ph: self._dense(self._operator(kind, ca, cb, cdev, ph))
+             for ph in ((1, 1), (-1, 1), (1j, 1), (1, -1), (1, 1j))}
+        sx_sum = (S[(1, 1)] - S[(-1, 1)]) / 2            # Cx + Cx'
+        base_x = (S[(1, 1)] + S[(-1, 1)]) / 2            # C0 + Cy + Cy'
+        sx_dif = (S[(1j, 1)] - base_x) / 1j              # Cx - Cx'
+        sy_sum = (S[(1, 1)] - S[(1, -1)]) / 2
+        base_y = (S[(1, 1)] + S[(1, -1)]) / 2            # C0 + Cx + Cx'
+        sy_dif = (S[(1, 1j)] - base_y) / 1j
+        Cx, Cxp = (sx_sum + sx_dif) / 2, (sx_sum - sx_dif) / 2
+        Cy, Cyp = (sy_sum + sy_dif) / 2, (sy_sum - sy_dif) / 2
+        C0 = S[(1, 1)] - sx_sum - sy_sum
+        return C0, Cx, Cxp, Cy, Cyp
+
+    # ---- solver core (Band_Diagram_Solver.py:256-336) ------------------------------------------------
+    def compute_band_structure(self, beta_path, *, num_bands, polarisations: Iterable[str] = ("TE", "TM"),
+                               eig_sigma=0.0, tol=1e-11, inner="auto"):
+        import torch
+
+        polarisations = tuple(p.upper() for p in polarisations)
+        allowed = {"TE", "TM"}
+        if any(p not in allowed for p in polarisations):
+            raise ValueError(f"polarisations must be drawn from {allowed}.")
+        beta_path = np.asarray(beta_path)
+        if beta_path.shape[0] != 2:
+            raise ValueError("beta_path must be a 2×N array of Bloch vectors.")
+        ns = beta_path.shape[1]
+        n = self.Nx * self.Ny
+        frequencies = {p: np.zeros((num_bands, ns), dtype=float) for p in polarisations}
+        eigenvalues = {p: np.zeros((num_bands, ns), dtype=complex) for p in polarisations}
+        blas = _eigs.DeviceBlas(self.device)
+        dense = inner == "lu" or (inner == "auto" and n <= self.DENSE_LIMIT)
+        # effective shift: left of the (non-negative) spectrum when the requested shift is 0
+        delta = (2 * np.pi * 0.05 / self.a) ** 2
+        sigma = float(np.real(eig_sigma)) - delta if np.imag(eig_sigma) == 0 else eig_sigma - delta
+        info = dict(restarts=0, inner="lu" if dense else "krylov", eigensolves=0, max_residual=0.0)
+        for pol in ("TM", "TE"):          # reference order inside the loop (:311-323)
+            if pol not in polarisations:
+                continue
+            kind, ca, cb, M = self._pencil_arrays(pol)
+            A0 = self._operator(kind, ca, cb, None, (1, 1))
+            dev, tdt = A0.device, A0.tdtype
+            Mdev = torch.from_numpy(M).to(dev).to(tdt).reshape(-1)
+            cdev = (-sigma) * Mdev.reshape(self.Ny, self.Nx)
+            pieces = self._dense_pieces(kind, A0.ca, A0.cb, cdev) if dense else None
+            v0 = None
+            for idx in range(ns):
+                ph = self._phases(beta_path[:, idx])
+                A = self._operator(kind, A0.ca, A0.cb, None, ph)
+                if dense:
+                    C0, Cx, Cxp, Cy, Cyp = pieces
+                    px, py = complex(ph[0]), complex(ph[1])
+                    S = C0 + px * Cx + px.conjugate() * Cxp + py * Cy + py.conjugate() * Cyp
+                    LU, piv = torch.linalg.lu_factor(S)
+                    solve = lambda r: torch.linalg.lu_solve(LU, piv, r.reshape(-1, 1)).reshape(-1)  # noqa: E731
+                else:
+                    As = self._operator(kind, A0.ca, A0.cb, cdev, ph)
+                    solve = lambda r: As.solve(r, method="bicgstab", precond="jacobi", rtol=1e-13,  # noqa: E731
+                                               maxit=20000)[0]
+                lam, X, res, rs = _eigs.eigs_shift_invert(A.apply, lambda v: Mdev * v.reshape(-1), solve, n,
+                                                           num_bands, sigma, tol=tol, v0=v0, device=dev, dtype=tdt,
+                                                           blas=blas, seed=idx)
+                v0 = X.sum(dim=0)          # warm start for the next path point
+                order = np.argsort(np.real(lam))
+                vals = lam[order][:num_bands]
+                eigenvalues[pol][:, idx] = vals
+                frequencies[pol][:, idx] = self._normalise_eigenvalues(vals)
+                info["restarts"] += rs
+                info["eigensolves"] += 1
+                info["max_residual"] = max(info["max_residual"], float(np.max(res[np.abs(lam) > 1e-6 * delta], initial=0.0)))
+                A.close()
+        self.solver_info = info
+        result = BandStructureResult(beta_path=beta_path, tick_positions=self._tick_positions_from_path(beta_path),
+                                     tick_labels=getattr(self, "_tick_labels", []) or
+                                     [""] * len(self._tick_positions_from_path(beta_path)),
+                                     frequencies=frequencies, eigenvalues=eigenvalues)
+        self._results = result
+        return result
+
+    def _sort_eigenvalues(self, values, num_bands):
+        return values[np.argsort(np.real(values))][:num_bands]
+
+    def _normalise_eigenvalues(self, values):
+        vals = np.clip(np.real_if_close(values).real, 0.0, None)
+        return self.a / (2 * np.pi) * np.sqrt(vals)
+
+    # ---- plotting: optional host-side matplotlib (Band_Diagram_Solver.py:357-531) ---------------------
+    def plot_band_diagram(self, result=None, *, wnmax=None, ax=None, show=True):
+        import matplotlib.pyplot as plt
+        result = result or self._results
+        if result is None:
+            raise RuntimeError("Run compute_band_structure() first")
+        if ax is None:
+            _, ax = plt.subplots(figsize=(7, 5))
+        xs = np.arange(result.beta_path.shape[1])
+        for pol, style in (("TM", "b-"), ("TE", "r--")):
+            if pol in result.frequencies:
+                for band in result.frequencies[pol]:
+                    ax.plot(xs, band, style, lw=1)
+        ax.set_xticks(result.tick_positions)
+        ax.set_xticklabels(result.tick_labels)
+        ax.set_ylabel("a/λ")
+        if wnmax is not None:
+            ax.set_ylim(0, wnmax)
+        if show:
+            plt.show()
+        return ax

@@ -243,3 +243,57 @@ extern "C" int fdfd_krylov_solve_host(fdfd_helm2d_t* h, const fdfd_krylov_opts* 
     FDFD_CUDA(cudaStreamSynchronize(0));
     return s;
 }
+
+// ---- K6 building blocks ------------------------------------------------------------------------
+struct fdfd_blas { Scalars sc; };
+
+extern "C" int fdfd_blas_create(fdfd_blas_t** out) {
+    FDFD_CHECK_ARG(out, "null out");
+    if (fdfd_device_count() <= 0) { set_error("no CUDA device visible: fdfd_b200 has no CPU path"); return FDFD_ERR_CUDA; }
+    fdfd_blas* b = new fdfd_blas();
+    int s = b->sc.alloc();
+    if (s != FDFD_OK) { delete b; return s; }
+    *out = b;
+    return FDFD_OK;
+}
+extern "C" void fdfd_blas_destroy(fdfd_blas_t* b) {
+    if (!b) return;
+    b->sc.release();
+    delete b;
+}
+
+static const int kBlasSlot0 = 16;   // slots [16, 16+k) hold h, slot 8 the squared norm
+
+extern "C" int fdfd_blas_multi_dot(fdfd_blas_t* b, int dtype, int64_t n, int k, const void* V, int64_t ldv,
+                                   const void* w, double* h_host, void* stream) {
+    FDFD_CHECK_ARG(b && V && w && h_host, "null pointer");
+    FDFD_CHECK_ARG(k >= 1 && k <= Scalars::kSlots - kBlasSlot0 - 8, "k out of range");
+    FDFD_CHECK_ARG(n >= 1 && ldv >= n, "bad vector shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FDFD_C128) FDFD_TRY(multi_dot<double2>(n, k, (const double2*)V, ldv, (const double2*)w, kBlasSlot0, b->sc, st));
+    else if (dtype == FDFD_C64) FDFD_TRY(multi_dot<float2>(n, k, (const float2*)V, ldv, (const float2*)w, kBlasSlot0, b->sc, st));
+    else { set_error("bad dtype"); return FDFD_ERR_ARG; }
+    FDFD_CUDA(cudaMemcpyAsync(h_host, b->sc.slot + kBlasSlot0, sizeof(double2) * k, cudaMemcpyDeviceToHost, st));
+    FDFD_CUDA(cudaStreamSynchronize(st));
+    return FDFD_OK;
+}
+
+extern "C" int fdfd_blas_multi_axpy(fdfd_blas_t* b, int dtype, int64_t n, int k, const void* V, int64_t ldv,
+                                    void* w, const double* h_host, double sign, double* nrm2_host, void* stream) {
+    FDFD_CHECK_ARG(b && V && w && h_host, "null pointer");
+    FDFD_CHECK_ARG(k >= 1 && k <= Scalars::kSlots - kBlasSlot0 - 8, "k out of range");
+    FDFD_CHECK_ARG(n >= 1 && ldv >= n, "bad vector shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    FDFD_CUDA(cudaMemcpyAsync(b->sc.slot + kBlasSlot0, h_host, sizeof(double2) * k, cudaMemcpyHostToDevice, st));
+    const int nslot = nrm2_host ? 8 : -1;
+    if (dtype == FDFD_C128) FDFD_TRY(multi_axpy<double2>(n, k, (const double2*)V, ldv, (double2*)w, kBlasSlot0, sign, nslot, b->sc, st));
+    else if (dtype == FDFD_C64) FDFD_TRY(multi_axpy<float2>(n, k, (const float2*)V, ldv, (float2*)w, kBlasSlot0, sign, nslot, b->sc, st));
+    else { set_error("bad dtype"); return FDFD_ERR_ARG; }
+    if (nrm2_host) {
+        double2 t;
+        FDFD_CUDA(cudaMemcpyAsync(&t, b->sc.slot + 8, sizeof(double2), cudaMemcpyDeviceToHost, st));
+        FDFD_CUDA(cudaStreamSynchronize(st));
+        *nrm2_host = t.x;
+    }
+    return FDFD_OK;
+}

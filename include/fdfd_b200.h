@@ -148,6 +148,23 @@ int fdfd_krylov_solve(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts,
 int fdfd_krylov_solve_host(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts,
                            const void* b_host, void* x_host, double* info);
 
+/* ------------------------------------------------------------------------------------------
+ * K6  building blocks of the GPU Arnoldi / Krylov-Schur eigen-solver (fused tall-skinny kernels
+ *     of K4 exposed for the host-side driver fdfd_b200/eigs.py) — replaces the ARPACK calls
+ *     eigs(A, M=..., k, sigma) of Band_Diagram_Solver.py:313,320 and the Gram-Schmidt loops of
+ *     refined_shift_invert_arnoldi.py:22-50.
+ *   V: device, k vectors of n complex numbers at stride ldv (elements); w: device vector.
+ *   fdfd_blas_multi_dot : h[i] = sum conj(V_i) * w          -> host (2k doubles), synchronises
+ *   fdfd_blas_multi_axpy: w += sign * sum_i h[i] * V_i      (h from host); optional ||w||^2 -> host
+ * ------------------------------------------------------------------------------------------ */
+typedef struct fdfd_blas fdfd_blas_t;
+int fdfd_blas_create(fdfd_blas_t** out);
+void fdfd_blas_destroy(fdfd_blas_t*);
+int fdfd_blas_multi_dot(fdfd_blas_t*, int dtype, int64_t n, int k, const void* V, int64_t ldv,
+                        const void* w, double* h_host, void* stream);
+int fdfd_blas_multi_axpy(fdfd_blas_t*, int dtype, int64_t n, int k, const void* V, int64_t ldv,
+                         void* w, const double* h_host, double sign, double* nrm2_host, void* stream);
+
 /* z = M^-1 v: one application of the preconditioner `opts->precond` selects (device pointers).
  * Exposed so the preconditioner can be validated on its own (tests/test_mg_gpu.py). */
 int fdfd_precond_apply(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts, const void* v, void* z,

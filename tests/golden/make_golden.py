@@ -89,8 +89,38 @@ def scatter_cfg1():
     np.savez_compressed(os.path.join(HERE, "scatter_cfg1.npz"), **out)
 
 
+def band_fixture():
+    """BASELINE config 3 (example_square_lattice.py: a=1, 40x40, eps_bg=10.2, air hole r=0.4, 200-point
+    Gamma-X-M-Gamma path, 5 bands) at path indices 0, 33, 59, 100, 117, 199, and the rectangular
+    example (example_rectangular_unitcell.py: 48x64, b=1.4) at 5 indices of its 240-point path."""
+    mod = ref_loader.load("Band_Diagram_Solver")
+    out = {}
+    s = mod.BandDiagramSolver2D(a=1.0, Nx=40, background_er=10.2)
+    s.add_circular_inclusion(radius=0.4, er=1.0)
+    pts, _ = s.default_rectangular_lattice_path()
+    bp, ticks = s.generate_bloch_path(pts, total_points=200)
+    idx = np.array([0, 33, 59, 100, 117, 199])
+    r = s.compute_band_structure(bp[:, idx], num_bands=5)
+    out.update(sq_path=bp, sq_ticks=np.array(ticks), sq_idx=idx, sq_ev_TM=r.eigenvalues["TM"], sq_ev_TE=r.eigenvalues["TE"],
+               sq_f_TM=r.frequencies["TM"], sq_f_TE=r.frequencies["TE"])
+    s = mod.BandDiagramSolver2D(a=1.0, b=1.4, Nx=48, Ny=64, background_er=11.9)
+    s.add_object(lambda X, Y: (np.abs(X) < 0.15) & (Y > -0.2) & (Y < 0.45), er=4.2)
+    s.add_circular_inclusion(radius=0.28, center=(-0.15, 0.0), er=1.0)
+    pts, _ = s.default_rectangular_lattice_path()
+    bp, ticks = s.generate_bloch_path(pts, total_points=240)
+    idx = np.array([5, 60, 120, 180, 230])
+    r = s.compute_band_structure(bp[:, idx], num_bands=6)
+    out.update(rect_path=bp, rect_idx=idx, rect_ev_TM=r.eigenvalues["TM"], rect_ev_TE=r.eigenvalues["TE"],
+               rect_f_TM=r.frequencies["TM"], rect_f_TE=r.frequencies["TE"])
+    np.savez_compressed(os.path.join(HERE, "band_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--band-only" in sys.argv:
+        band_fixture()
+        sys.exit(0)
     yee_fixture()
+    band_fixture()
     scatter_small()
     scatter_cfg1()
     for f in sorted(os.listdir(HERE)):

@@ -1,0 +1,79 @@
+"""GPU parity of the band-diagram path (K2 Bloch operators + K6 Krylov-Schur shift-invert) against
+golden eigenvalues produced by the unmodified reference and against the oracle.
+Bar (BASELINE.json): eigenvalues within 1e-8 relative."""
+import numpy as np
+import pytest
+
+from oracle import band_oracle as bo
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b, floor):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))
+
+
+def test_square_lattice_cfg3_golden(golden):
+    """BASELINE config 3 at six path points incl. Gamma (singular shift), X and M."""
+    import fdfd_b200
+    g = golden("band_golden.npz")
+    s = fdfd_b200.BandDiagramSolver2D(a=1.0, Nx=40, background_er=10.2)
+    s.add_circular_inclusion(radius=0.4, er=1.0)
+    pts, labels = s.default_rectangular_lattice_path()
+    bp, ticks = s.generate_bloch_path(pts, total_points=200)
+    assert np.array_equal(bp, g["sq_path"]) and list(ticks) == list(g["sq_ticks"]) == [0, 59, 117, 199]
+    s.set_tick_labels(labels, ticks)
+    idx = g["sq_idx"]
+    r = s.compute_band_structure(bp[:, idx], num_bands=5)
+    floor = 1e-3 * np.abs(g["sq_ev_TM"]).max()     # the zero band at Gamma is compared absolutely
+    for pol in ("TM", "TE"):
+        assert r.eigenvalues[pol].shape == (5, len(idx)) and r.frequencies[pol].dtype == float
+        assert _rel(r.eigenvalues[pol], g[f"sq_ev_{pol}"], floor) <= 1e-8
+        assert np.max(np.abs(r.frequencies[pol] - g[f"sq_f_{pol}"])) <= 1e-7
+    # SURVEY.md §8c literal values
+    assert np.allclose(r.frequencies["TM"][:, 1], [0.1161753797, 0.2956241914, 0.3903181775, 0.3991116489, 0.4862472813], atol=1e-9)
+    assert np.allclose(r.frequencies["TE"][:, 3], [0.2607123463, 0.3193415028, 0.4489926802, 0.4650632201, 0.6076898080], atol=1e-9)
+    assert r.frequencies["TM"][0, 0] < 1e-5 and r.frequencies["TE"][0, 5] < 1e-5     # Gamma
+
+
+def test_rectangular_cell_golden(golden):
+    import fdfd_b200
+    g = golden("band_golden.npz")
+    s = fdfd_b200.BandDiagramSolver2D(a=1.0, b=1.4, Nx=48, Ny=64, background_er=11.9)
+    s.add_object(lambda X, Y: (np.abs(X) < 0.15) & (Y > -0.2) & (Y < 0.45), er=4.2)
+    s.add_circular_inclusion(radius=0.28, center=(-0.15, 0.0), er=1.0)
+    pts, _ = s.default_rectangular_lattice_path()
+    bp, _ = s.generate_bloch_path(pts, total_points=240)
+    assert np.array_equal(bp, g["rect_path"])
+    r = s.compute_band_structure(bp[:, g["rect_idx"]], num_bands=6)
+    for pol in ("TM", "TE"):
+        assert _rel(r.eigenvalues[pol], g[f"rect_ev_{pol}"], 1e-3) <= 1e-8
+
+
+@pytest.mark.parametrize("inner", ["lu", "krylov"])
+def test_small_cell_vs_oracle(inner):
+    """16 x 12 cell with anisotropic-ish inclusions, both shifted-solve back ends, vs scipy eigs."""
+    import fdfd_b200
+    s = fdfd_b200.BandDiagramSolver2D(a=1.0, b=0.8, Nx=16, Ny=12, background_er=4.0, background_ur=1.5)
+    p = bo.BandProblem(1.0, 16, 12, b=0.8, background_er=4.0, background_ur=1.5)
+    for obj in (s, p):
+        obj.add_object(lambda X, Y: (np.abs(X) < 0.2) & (np.abs(Y) < 0.25), er=9.0, ur=1.0)
+    betas = np.array([[0.3, 2.0, 3.1], [0.2, -1.0, 3.9]])
+    r = s.compute_band_structure(betas, num_bands=4, inner=inner)
+    o = bo.band_structure(p, betas, 4)
+    for pol in ("TE", "TM"):
+        assert _rel(r.eigenvalues[pol], o[pol][0], 1e-6) <= 1e-8
+    assert s.solver_info["inner"] == inner
+
+
+def test_bad_arguments():
+    import fdfd_b200
+    s = fdfd_b200.BandDiagramSolver2D(a=1.0, Nx=8)
+    with pytest.raises(ValueError):
+        s.compute_band_structure(np.zeros((3, 2)), num_bands=2)
+    with pytest.raises(ValueError):
+        s.compute_band_structure(np.zeros((2, 2)), num_bands=2, polarisations=("XX",))
+    with pytest.raises(ValueError):
+        s.add_object(np.ones((3, 3), bool), er=2.0)
+    with pytest.raises(ValueError):
+        s.generate_bloch_path([[0, 0], [1, 1]], total_points=1)

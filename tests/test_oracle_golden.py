@@ -63,3 +63,18 @@ def test_scatter_cfg1_golden(golden):
     assert abs(Hz[150, 75] - g["probe_TM"]) < 1e-12
     assert abs(np.abs(Hz).max() - 1.9723) < 1e-3
     assert np.linalg.norm(Hz[::10, ::10] - g["dec_TM"]) <= 1e-11 * np.linalg.norm(g["dec_TM"])
+
+
+def test_band_golden(golden):
+    """Band oracle vs golden eigenvalues of the reference (config 3 at six path points)."""
+    from oracle import band_oracle as bo
+    g = golden("band_golden.npz")
+    p = bo.BandProblem(1.0, 40, background_er=10.2)
+    p.add_circle(0.4, er=1.0)
+    bp, ticks = bo.bloch_path(bo.gamma_x_m_gamma(1.0, 1.0), 200)
+    assert np.array_equal(bp, g["sq_path"]) and ticks == [0, 59, 117, 199]
+    o = bo.band_structure(p, bp[:, g["sq_idx"][[1, 3]]], 5)
+    for pol in ("TM", "TE"):
+        ref = g[f"sq_ev_{pol}"][:, [1, 3]]
+        assert np.max(np.abs(o[pol][0] - ref)) <= 1e-9 * np.abs(ref).max()
+    assert np.allclose(o["TM"][1][:, 0], [0.1161753797, 0.2956241914, 0.3903181775, 0.3991116489, 0.4862472813], atol=1e-9)

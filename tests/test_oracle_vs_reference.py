@@ -70,3 +70,24 @@ def test_point_source_matches():
         sim.add_source("point", polarization=pol, location=(0.001, -0.002), amplitude=2.0)
         so.add_source(p, "point", polarization=pol, location=(0.001, -0.002), amplitude=2.0)
         assert np.array_equal(sim.source, p.source)
+
+
+def test_band_oracle_matches_reference():
+    """Band-diagram oracle vs the unmodified reference class on a small cell (path, materials, eigenvalues)."""
+    from oracle import band_oracle as bo
+    mod = ref_loader.load("Band_Diagram_Solver")
+    s = mod.BandDiagramSolver2D(a=1.0, Nx=20, Ny=16, b=0.9, background_er=10.2)
+    s.add_circular_inclusion(radius=0.3, er=1.0)
+    p = bo.BandProblem(1.0, 20, 16, b=0.9, background_er=10.2)
+    p.add_circle(0.3, er=1.0)
+    assert np.array_equal(s.ER2, p.ER2)
+    pts, _ = s.default_rectangular_lattice_path()
+    bp, ticks = s.generate_bloch_path(pts, total_points=23)
+    bp2, ticks2 = bo.bloch_path(bo.gamma_x_m_gamma(1.0, 0.9), 23)
+    assert np.array_equal(bp, bp2) and list(ticks) == list(ticks2)
+    sub = bp[:, [1, 7, 15]]
+    r = s.compute_band_structure(sub, num_bands=4)
+    o = bo.band_structure(p, sub, 4)
+    for pol in ("TE", "TM"):
+        assert np.max(np.abs(r.eigenvalues[pol] - o[pol][0])) <= 1e-9 * np.abs(o[pol][0]).max()
+        assert np.max(np.abs(r.frequencies[pol] - o[pol][1])) <= 1e-10
