@@ -193,8 +193,9 @@ extern "C" int fdfd_krylov_solve(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts,
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, st);
-    if (opts->method == FDFD_KRYLOV_BICGSTAB) s = bicgstab_solve(A, M, *opts, b, x, info, st);
-    else if (opts->method == FDFD_KRYLOV_FGMRES) s = fgmres_solve(A, M, *opts, b, x, info, st);
+    HelmOp op(A);
+    if (opts->method == FDFD_KRYLOV_BICGSTAB) s = bicgstab_solve(op, M, *opts, b, x, info, st);
+    else if (opts->method == FDFD_KRYLOV_FGMRES) s = fgmres_solve(op, M, *opts, b, x, info, st);
     else { set_error("unknown Krylov method %d", opts->method); s = FDFD_ERR_ARG; }
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);

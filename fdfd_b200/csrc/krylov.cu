@@ -37,14 +37,16 @@ struct ScalarsGuard {
 };
 
 struct JacobiPrecond : Precond {
-    Helm2D* A = nullptr;
+    int dtype = FDFD_C128;
+    int64_t n = 0;
     void* dinv = nullptr;
-    ~JacobiPrecond() override { if (dinv) cudaFree(dinv); }
+    bool owned = true;
+    ~JacobiPrecond() override { if (dinv && owned) cudaFree(dinv); }
     int apply(const void* v, void* z, cudaStream_t stream) override {
         ++applies;
-        if (A->dtype == FDFD_C128)
-            return pointwise_mul<double2>(A->n_local(), (double2*)z, (const double2*)v, (const double2*)dinv, stream);
-        return pointwise_mul<float2>(A->n_local(), (float2*)z, (const float2*)v, (const float2*)dinv, stream);
+        if (dtype == FDFD_C128)
+            return pointwise_mul<double2>(n, (double2*)z, (const double2*)v, (const double2*)dinv, stream);
+        return pointwise_mul<float2>(n, (float2*)z, (const float2*)v, (const float2*)dinv, stream);
     }
 };
 
@@ -73,7 +75,7 @@ enum { S_RHO = 0, S_RHO_OLD, S_ALPHA, S_OMEGA, S_BETA, S_NBO, S_RV, S_TS, S_TT, 
        S_TMP0, S_TMP1, S_TMP2, S_TMP3, S_H0 = 32 /* Hessenberg column / GMRES y (<= 200 entries) */ };
 
 template <typename C>
-int bicgstab_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, SolveInfo& info,
+int bicgstab_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, SolveInfo& info,
                cudaStream_t stream, BicgWorkspace* ext_ws = nullptr, bool fixed_its = false) {
     const int64_t n = A.n_local();
     const size_t bytes = (size_t)n * sizeof(C);
@@ -90,7 +92,7 @@ int bicgstab_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* 
 
     auto restart = [&]() -> int {
         // r = b - A x ; r^ = r ; p = v = 0 ; rho_old = alpha = omega = 1
-        FDFD_TRY(helm2d_apply(A, APPLY_RESID, x, r, b, 0.0, stream)); ++info.op_applies;
+        FDFD_TRY(A.residual(x, r, b, stream)); ++info.op_applies;
         FDFD_CUDA(cudaMemcpyAsync(rh, r, bytes, cudaMemcpyDeviceToDevice, stream));
         FDFD_CUDA(cudaMemsetAsync(p, 0, bytes, stream));
         FDFD_CUDA(cudaMemsetAsync(v, 0, bytes, stream));
@@ -112,13 +114,13 @@ int bicgstab_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* 
             FDFD_TRY(scalar_op(SOP_BICG_BETA, S_BETA, S_RHO, S_RHO_OLD, S_ALPHA, S_OMEGA, 0, 0, sc, stream));
             FDFD_TRY(lincomb<C>(n, p, nullptr, r, sc.slot + S_BETA, p, sc.slot + S_NBO, v, 0, nullptr, -1, -1, sc, stream));
             if (M) { FDFD_TRY(M->apply(p, ph, stream)); ++info.precond_applies; }
-            FDFD_TRY(helm2d_apply(A, APPLY_AX, ph, v, nullptr, 0.0, stream)); ++info.op_applies;
+            FDFD_TRY(A.apply(ph, v, stream)); ++info.op_applies;
             { const C* xs[1] = {rh}; const C* ys[1] = {v}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_RV, sc, stream)); }
             FDFD_TRY(allreduce_slots(comm, sc, S_RV, 1, stream));
             FDFD_TRY(scalar_op(SOP_DIV, S_ALPHA, S_RHO, S_RV, 0, 0, 0, 0, sc, stream));
             FDFD_TRY(lincomb<C>(n, r, nullptr, r, sc.slot + S_ALPHA, v, nullptr, nullptr, 2, nullptr, -1, -1, sc, stream));
             if (M) { FDFD_TRY(M->apply(r, sh, stream)); ++info.precond_applies; }
-            FDFD_TRY(helm2d_apply(A, APPLY_AX, sh, t, nullptr, 0.0, stream)); ++info.op_applies;
+            FDFD_TRY(A.apply(sh, t, stream)); ++info.op_applies;
             { const C* xs[2] = {t, t}; const C* ys[2] = {r, t}; FDFD_TRY(dots<C>(n, 2, xs, ys, S_TS, sc, stream)); }
             FDFD_TRY(allreduce_slots(comm, sc, S_TS, 2, stream));
             FDFD_TRY(scalar_op(SOP_DIV, S_OMEGA, S_TS, S_TT, 0, 0, 0, 0, sc, stream));
@@ -147,14 +149,14 @@ int bicgstab_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* 
         FDFD_TRY(scalar_op(SOP_BICG_BETA, S_BETA, S_RHO, S_RHO_OLD, S_ALPHA, S_OMEGA, 0, 0, sc, stream));
         FDFD_TRY(lincomb<C>(n, p, nullptr, r, sc.slot + S_BETA, p, sc.slot + S_NBO, v, 0, nullptr, -1, -1, sc, stream));
         if (M) { FDFD_TRY(M->apply(p, ph, stream)); ++info.precond_applies; }
-        FDFD_TRY(helm2d_apply(A, APPLY_AX, ph, v, nullptr, 0.0, stream)); ++info.op_applies;
+        FDFD_TRY(A.apply(ph, v, stream)); ++info.op_applies;
         { const C* xs[1] = {rh}; const C* ys[1] = {v}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_RV, sc, stream)); }
         FDFD_TRY(allreduce_slots(comm, sc, S_RV, 1, stream));
         FDFD_TRY(scalar_op(SOP_DIV, S_ALPHA, S_RHO, S_RV, 0, 0, 0, 0, sc, stream));
         // s = r - alpha v  (in r's storage)
         FDFD_TRY(lincomb<C>(n, r, nullptr, r, sc.slot + S_ALPHA, v, nullptr, nullptr, 2, nullptr, -1, -1, sc, stream));
         if (M) { FDFD_TRY(M->apply(r, sh, stream)); ++info.precond_applies; }
-        FDFD_TRY(helm2d_apply(A, APPLY_AX, sh, t, nullptr, 0.0, stream)); ++info.op_applies;
+        FDFD_TRY(A.apply(sh, t, stream)); ++info.op_applies;
         { const C* xs[2] = {t, t}; const C* ys[2] = {r, t}; FDFD_TRY(dots<C>(n, 2, xs, ys, S_TS, sc, stream)); }
         FDFD_TRY(allreduce_slots(comm, sc, S_TS, 2, stream));
         FDFD_TRY(scalar_op(SOP_DIV, S_OMEGA, S_TS, S_TT, 0, 0, 0, 0, sc, stream));
@@ -193,7 +195,7 @@ int bicgstab_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* 
         }
         if (rr <= target2) {
             // confirm with the true residual before stopping (recurrence drift)
-            FDFD_TRY(helm2d_apply(A, APPLY_RESID, x, t, b, 0.0, stream)); ++info.op_applies;
+            FDFD_TRY(A.residual(x, t, b, stream)); ++info.op_applies;
             const C* xs[1] = {t}; const C* ys[1] = {t};
             FDFD_TRY(dots<C>(n, 1, xs, ys, S_TMP0, sc, stream));
             FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 1, stream));
@@ -208,7 +210,7 @@ int bicgstab_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* 
         }
     }
     // true residual
-    FDFD_TRY(helm2d_apply(A, APPLY_RESID, x, t, b, 0.0, stream)); ++info.op_applies;
+    FDFD_TRY(A.residual(x, t, b, stream)); ++info.op_applies;
     { const C* xs[1] = {t}; const C* ys[1] = {t}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_TMP0, sc, stream)); }
     FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 1, stream));
     FDFD_TRY(read_slots(sc, S_TMP0, 1, h, stream));
@@ -223,7 +225,7 @@ int bicgstab_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* 
 
 // ------------------------------------------------------------------------------------------------
 template <typename C>
-int fgmres_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, SolveInfo& info,
+int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, SolveInfo& info,
              cudaStream_t stream) {
     using cd = std::complex<double>;
     const int64_t n = A.n_local();
@@ -265,7 +267,7 @@ int fgmres_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x,
     bool done = false;
     while (!done) {
         // r = b - A x -> V0 (normalised)
-        FDFD_TRY(helm2d_apply(A, APPLY_RESID, x, w, b, 0.0, stream)); ++info.op_applies;
+        FDFD_TRY(A.residual(x, w, b, stream)); ++info.op_applies;
         { const C* xs[1] = {w}; const C* ys[1] = {w}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_RR, sc, stream)); }
         FDFD_TRY(allreduce_slots(comm, sc, S_RR, 1, stream));
         FDFD_TRY(read_slots(sc, S_RR, 1, hbuf.data(), stream));
@@ -290,7 +292,7 @@ int fgmres_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x,
             } else if (kaug) {
                 FDFD_CUDA(cudaMemcpyAsync(zj, vj, bytes, cudaMemcpyDeviceToDevice, stream));
             }
-            FDFD_TRY(helm2d_apply(A, APPLY_AX, zj, w, nullptr, 0.0, stream)); ++info.op_applies;
+            FDFD_TRY(A.apply(zj, w, stream)); ++info.op_applies;
             // classical Gram-Schmidt with one re-orthogonalisation pass, fused multi-vector kernels
             const int passes = o.reorth ? 2 : 1;
             for (int pass = 0; pass < passes; ++pass) {
@@ -357,7 +359,7 @@ int fgmres_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x,
         FDFD_CUDA(cudaStreamSynchronize(stream));
     }
     // true residual
-    FDFD_TRY(helm2d_apply(A, APPLY_RESID, x, w, b, 0.0, stream)); ++info.op_applies;
+    FDFD_TRY(A.residual(x, w, b, stream)); ++info.op_applies;
     { const C* xs[1] = {w}; const C* ys[1] = {w}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_RR, sc, stream)); }
     FDFD_TRY(allreduce_slots(comm, sc, S_RR, 1, stream));
     FDFD_TRY(read_slots(sc, S_RR, 1, hbuf.data(), stream));
@@ -374,7 +376,7 @@ int fgmres_t(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x,
 
 int make_jacobi_precond(Helm2D& A, Precond** out, cudaStream_t stream) {
     JacobiPrecond* P = new JacobiPrecond();
-    P->A = &A;
+    P->dtype = A.dtype; P->n = A.n_local();
     cudaError_t e = cudaMalloc(&P->dinv, (size_t)A.n_local() * A.elem());
     if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaMalloc(dinv)", __FILE__, __LINE__); }
     // halo not needed: the diagonal only depends on coefficients
@@ -390,12 +392,19 @@ int make_jacobi_precond(Helm2D& A, Precond** out, cudaStream_t stream) {
     return FDFD_OK;
 }
 
-int bicgstab_solve(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
+int make_diag_precond(int dtype, int64_t n, const void* d, Precond** out) {
+    JacobiPrecond* P = new JacobiPrecond();
+    P->dtype = dtype; P->n = n; P->dinv = const_cast<void*>(d); P->owned = false;
+    *out = P;
+    return FDFD_OK;
+}
+
+int bicgstab_solve(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
                    SolveInfo& info, cudaStream_t stream, BicgWorkspace* ws, bool fixed_its) {
     if (A.dtype == FDFD_C128) return bicgstab_t<double2>(A, M, o, (const double2*)b, (double2*)x, info, stream, ws, fixed_its);
     return bicgstab_t<float2>(A, M, o, (const float2*)b, (float2*)x, info, stream, ws, fixed_its);
 }
-int fgmres_solve(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
+int fgmres_solve(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
                  SolveInfo& info, cudaStream_t stream) {
     if (A.dtype == FDFD_C128) return fgmres_t<double2>(A, M, o, (const double2*)b, (double2*)x, info, stream);
     return fgmres_t<float2>(A, M, o, (const float2*)b, (float2*)x, info, stream);

@@ -5,6 +5,30 @@
 
 namespace fdfd {
 
+// Abstract linear operator the Krylov solvers iterate on: the matrix-free Helmholtz stencil (K2)
+// or a product of device CSR matrices (mode-solver operator Omega = P Q, csr_ops.cu).
+struct LinOp {
+    int dtype = FDFD_C128;
+    Comm* comm = nullptr;
+    virtual ~LinOp() {}
+    virtual int64_t n_local() const = 0;
+    virtual int apply(const void* x, void* y, cudaStream_t stream) = 0;                         // y = A x
+    virtual int residual(const void* x, void* r, const void* b, cudaStream_t stream) = 0;       // r = b - A x
+    size_t elem() const { return dtype == FDFD_C128 ? 16 : 8; }
+};
+
+struct HelmOp : LinOp {
+    Helm2D& A;
+    explicit HelmOp(Helm2D& a) : A(a) { dtype = a.dtype; comm = a.comm; }
+    int64_t n_local() const override { return A.n_local(); }
+    int apply(const void* x, void* y, cudaStream_t stream) override {
+        return helm2d_apply(A, APPLY_AX, x, y, nullptr, 0.0, stream);
+    }
+    int residual(const void* x, void* r, const void* b, cudaStream_t stream) override {
+        return helm2d_apply(A, APPLY_RESID, x, r, b, 0.0, stream);
+    }
+};
+
 // z = M^-1 v.  Implementations: identity, Jacobi (1/diag), shifted-Laplacian multigrid (mg.cu).
 struct Precond {
     virtual ~Precond() {}
@@ -22,6 +46,8 @@ struct SolveInfo {
 };
 
 int make_jacobi_precond(Helm2D& A, Precond** out, cudaStream_t stream);
+// z = d .* v with a caller-owned device array d (n elements of the operator dtype)
+int make_diag_precond(int dtype, int64_t n, const void* d, Precond** out);
 int make_mg_precond(Helm2D& A, const fdfd_krylov_opts& opts, Precond** out, cudaStream_t stream);
 
 // scratch vectors + scalar slots of BiCGSTAB, reusable across solves (inner coarse-level solves
@@ -36,10 +62,10 @@ struct BicgWorkspace {
 };
 
 // fixed_its: run exactly o.maxit iterations without any host synchronisation (inner solves).
-int bicgstab_solve(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
+int bicgstab_solve(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
                    SolveInfo& info, cudaStream_t stream, BicgWorkspace* ws = nullptr,
                    bool fixed_its = false);
-int fgmres_solve(Helm2D& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
+int fgmres_solve(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
                  SolveInfo& info, cudaStream_t stream);
 
 }  // namespace fdfd

@@ -574,7 +574,8 @@ struct MGPrecond : Precond {
                 io.maxit = coarse_its;
                 SolveInfo ii;
                 coarse_pre.mg = this; coarse_pre.level = l;
-                FDFD_TRY(bicgstab_solve(lv.op, &coarse_pre, io, lv.b, lv.r, ii, st, &coarse_ws, true));
+                HelmOp cop(lv.op);
+                FDFD_TRY(bicgstab_solve(cop, &coarse_pre, io, lv.b, lv.r, ii, st, &coarse_ws, true));
                 std::swap(lv.x, lv.r);
             } else {
                 for (int s = 0; s < coarse_its; ++s) FDFD_TRY(smooth(l, st));

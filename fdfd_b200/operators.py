@@ -169,6 +169,81 @@ class HelmholtzOperator2D:
         return z
 
 
+class CsrProductOperator:
+    """y = P (Q x) + shift * x with P (n x m) and Q (m x n) scipy CSR matrices uploaded once — the
+    mode-solver operator Omega = P_red @ Q_red (Mode_Solver_2D.py:771-774) kept factored on the GPU.
+    ``solve`` applies (P Q + shift I)^-1 with the K3 Krylov solvers (Jacobi: 1/(diag(PQ)+shift))."""
+
+    def __init__(self, P, Q, shift=0.0, device=None, diag=None):
+        torch = _torch()
+        _lib.require_cuda()
+        self._L = _lib.lib()
+        self.device = torch.device(device or "cuda")
+        P = P.tocsr()
+        Q = Q.tocsr()
+        if P.shape[1] != Q.shape[0] or P.shape[0] != Q.shape[1]:
+            raise ValueError("P and Q shapes do not form a square product")
+        self.n, self.m = P.shape
+        self.tdtype = torch.complex128
+        self.shift = complex(shift)
+
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)
+        self._keep = [up(P.indptr, np.int32), up(P.indices, np.int32), up(P.data, np.complex128),
+                      up(Q.indptr, np.int32), up(Q.indices, np.int32), up(Q.data, np.complex128)]
+        if diag is None:
+            diag = np.asarray(P.multiply(Q.T).sum(axis=1)).ravel()
+        self.dinv = up(1.0 / (np.asarray(diag, dtype=np.complex128) + self.shift), np.complex128)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.fdfd_csr_product_create(C.byref(self._h), _lib.C128, self.n, self.m,
+                                                       *[t.data_ptr() for t in self._keep],
+                                                       self.shift.real, self.shift.imag))
+
+    def _stream(self):
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.fdfd_linop_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def apply(self, x, out=None):
+        torch = _torch()
+        x = x.to(device=self.device, dtype=self.tdtype).contiguous().reshape(-1)
+        if x.numel() != self.n:
+            raise ValueError("x has the wrong number of elements")
+        if out is None:
+            out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.fdfd_linop_apply(self._h, x.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def solve(self, b, x0=None, *, method="bicgstab", rtol=1e-12, maxit=20000, jacobi=True, raise_on_noconv=True,
+              **opts):
+        torch = _torch()
+        o = _lib.default_opts(method={"bicgstab": _lib.KRYLOV_BICGSTAB, "fgmres": _lib.KRYLOV_FGMRES}[method],
+                              rtol=float(rtol), maxit=int(maxit), **opts)
+        b = b.to(device=self.device, dtype=self.tdtype).contiguous().reshape(-1)
+        x = torch.zeros_like(b) if x0 is None else x0.to(device=self.device, dtype=self.tdtype).reshape(-1).clone()
+        info = (C.c_double * 8)()
+        with torch.cuda.device(self.device):
+            st = self._L.fdfd_linop_solve(self._h, C.byref(o), self.dinv.data_ptr() if jacobi else None,
+                                          b.data_ptr(), x.data_ptr(), info, self._stream())
+        d = dict(iterations=int(info[0]), relres=float(info[1]), applies=int(info[2]), seconds=float(info[4]),
+                 converged=(st == _lib.FDFD_OK))
+        if st == _lib.FDFD_ERR_NOCONV and not raise_on_noconv:
+            return x, d
+        _lib.check(st, d)
+        return x, d
+
+
 class SlabComm:
     """NCCL communicator for y-slab sharding; the 128-byte unique id travels through
     ``torch.distributed`` (any backend) from rank 0."""

@@ -165,6 +165,24 @@ int fdfd_blas_multi_dot(fdfd_blas_t*, int dtype, int64_t n, int k, const void* V
 int fdfd_blas_multi_axpy(fdfd_blas_t*, int dtype, int64_t n, int k, const void* V, int64_t ldv,
                          void* w, const double* h_host, double sign, double* nrm2_host, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K2b  full-vector mode-solver operator  Omega = P Q  kept as two device CSR matrices
+ *      — replaces the explicit product P_reduced @ Q_reduced and eigs' SuperLU solve
+ *        (Mode_Solver_2D/Mode_Solver_2D.py:771-780).
+ *   y = P (Q x) + shift * x ;  P: n x m, Q: m x n, int32 CSR arrays and complex data on the DEVICE
+ *   (caller-owned, must outlive the handle).  fdfd_linop_solve solves (P Q + shift I) x = b with the
+ *   K3 Krylov solvers; dinv (device, n complex, may be NULL) = 1/diag for Jacobi preconditioning.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct fdfd_linop fdfd_linop_t;
+int fdfd_csr_product_create(fdfd_linop_t** out, int dtype, int n, int m,
+                            const int32_t* P_indptr, const int32_t* P_indices, const void* P_data,
+                            const int32_t* Q_indptr, const int32_t* Q_indices, const void* Q_data,
+                            double shift_re, double shift_im);
+void fdfd_linop_destroy(fdfd_linop_t*);
+int fdfd_linop_apply(fdfd_linop_t*, const void* x, void* y, void* stream);
+int fdfd_linop_solve(fdfd_linop_t*, const fdfd_krylov_opts* opts, const void* dinv, const void* b,
+                     void* x, double* info, void* stream);
+
 /* z = M^-1 v: one application of the preconditioner `opts->precond` selects (device pointers).
  * Exposed so the preconditioner can be validated on its own (tests/test_mg_gpu.py). */
 int fdfd_precond_apply(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts, const void* v, void* z,

@@ -115,12 +115,59 @@ def band_fixture():
     np.savez_compressed(os.path.join(HERE, "band_golden.npz"), **out)
 
 
+def mode_cases():
+    """Problem definitions shared by the fixture generator and the tests (name -> builder(cls))."""
+    def ridge(cls):          # BASELINE config 2: example_ridge_dielectric_waveguide.py
+        s = cls(50e9, 24e-3, 16e-3, 240, 160, 5)
+        s.add_rectangle((3.0, 4.0, 5.0), 1, (0, 240), (60, 80))
+        s.add_rectangle(6.0, 1, (100, 140), (80, 100))
+        s.add_UPML(pml_width=30, n=3, sigma_max=1, direction="x")
+        return s
+
+    def strip(cls):          # small lossy microstrip-like case: PEC strip + ground, lossy substrate
+        s = cls(30e9, 12e-3, 8e-3, 60, 40, 3)
+        s.add_rectangle(4 + 1j, 1, (2e-3, 10e-3), (2e-3, 3e-3))
+        s.add_pec((5e-3, 7e-3), (3e-3, 3.2e-3))
+        s.add_pec((0, 60), (9, 10))
+        return s
+
+    def shapes(cls):         # circle + triangle + impedance sheet + PMC wall + y PML
+        s = cls(40e9, 10e-3, 10e-3, 50, 50, 4)
+        s.add_circle(5.0, 1.0, (5e-3, 5e-3), 2e-3, 0.8e-3)
+        s.add_triangle((2.0, 2.5, 3.0), 1.2, (1e-3, 1e-3), (4e-3, 1.5e-3), (2e-3, 3.5e-3))
+        s.add_impedance_surface(50 + 20j, 40, orientation="x")
+        s.add_pmc((0, 2), (0, 50), components=("yy", "zz"))
+        s.add_pml(pml_width=8, sigma_max=2, direction="y")
+        return s
+    return dict(ridge=ridge, strip=strip, shapes=shapes)
+
+
+def mode_fixture():
+    mod = ref_loader.load("Mode_Solver_2D")
+    out = {}
+    for name, build in mode_cases().items():
+        s = build(mod.ModeSolver2D)
+        s.solve()
+        out[f"{name}_eigenvalues"] = s.eigenvalues
+        out[f"{name}_neff"] = s.neff
+        out[f"{name}_sigma"] = np.array(s._resolve_eigs_guess(None))
+        for fld in ("Ex", "Ey", "Ez", "Hx", "Hy", "Hz"):
+            a = getattr(s, fld)
+            out[f"{name}_{fld}_norm"] = np.array([np.linalg.norm(a[:, :, m]) for m in range(s.num_modes)])
+            out[f"{name}_{fld}_dec"] = a[::7, ::5, :].copy()
+    np.savez_compressed(os.path.join(HERE, "mode_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--mode-only" in sys.argv:
+        mode_fixture()
+        sys.exit(0)
     if "--band-only" in sys.argv:
         band_fixture()
         sys.exit(0)
     yee_fixture()
     band_fixture()
+    mode_fixture()
     scatter_small()
     scatter_cfg1()
     for f in sorted(os.listdir(HERE)):
