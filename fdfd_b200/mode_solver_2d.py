@@ -523,7 +523,10 @@ class ModeSolver2D:
         hx, hy = Hxy[:self.n_hx, :], Hxy[self.n_hx:, :]
         ez = np.asarray(f["ezi"] @ (d_hy_ez @ hy - d_hx_ez @ hx), dtype=complex)
         hz = np.asarray(f["mzi"] @ (d_ey_hz @ ey - d_ex_hz @ ex), dtype=complex)
-        unfl = lambda a, shape: np.asarray(a, dtype=complex).reshape((*shape, a.shape[1]), order="F")  # noqa: E731
+        # NB: copies — in the reference `Ex`/`Ey` are *views* of `eigenvectors` (Mode_Solver_2D.py:797-798,
+        # 807-808), so its most-real rotation (:711-725) hits them twice and leaves Ex, Ey and the
+        # eigenvectors with a run-dependent phase; here all six fields share one consistent phase.
+        unfl = lambda a, shape: np.array(a, dtype=complex).reshape((*shape, a.shape[1]), order="F")  # noqa: E731
         self.Ex, self.Ey, self.Ez = unfl(ex, self.shape_ex), unfl(ey, self.shape_ey), unfl(ez, self.shape_ez)
         self.Hx, self.Hy, self.Hz = unfl(hx, self.shape_hx), unfl(hy, self.shape_hy), unfl(hz, self.shape_hz)
         for fld, m in zip((self.Ex, self.Ey, self.Ez, self.Hx, self.Hy, self.Hz), f["masks"]):

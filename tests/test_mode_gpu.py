@@ -37,9 +37,17 @@ def test_mode_solver_vs_golden(golden, case):
         ref_n = g[f"{case}_{fld}_norm"]
         assert np.allclose(nrm, ref_n, rtol=1e-6, atol=1e-9 * ref_n.max())
         dec, ref = a[::7, ::5, :], g[f"{case}_{fld}_dec"]
-        for m in range(s.num_modes):      # the most-real phase leaves a sign free
-            d = min(np.linalg.norm(dec[:, :, m] - ref[:, :, m]), np.linalg.norm(dec[:, :, m] + ref[:, :, m]))
-            assert d <= 1e-6 * max(np.linalg.norm(ref[:, :, m]), 1e-9 * ref_n.max())
+        for m in range(s.num_modes):
+            scale = max(np.linalg.norm(ref[:, :, m]), 1e-9 * ref_n.max())
+            if fld in ("Ex", "Ey"):
+                # the reference rotates Ex/Ey twice (they alias `eigenvectors`), which leaves them with a
+                # run-dependent phase: compare up to a free phase
+                ph = np.vdot(ref[:, :, m], dec[:, :, m])
+                ph = ph / abs(ph) if abs(ph) > 0 else 1.0
+                d = np.linalg.norm(dec[:, :, m] - ph * ref[:, :, m])
+            else:                          # the most-real phase leaves a sign free
+                d = min(np.linalg.norm(dec[:, :, m] - ref[:, :, m]), np.linalg.norm(dec[:, :, m] + ref[:, :, m]))
+            assert d <= 1e-6 * scale, (fld, m, d / scale)
     assert np.all(s.solver_info["residuals"] < 1e-8)
 
 
