@@ -488,8 +488,7 @@ class ModeSolver2D:
             raise ValueError(f"Not enough unconstrained electric DOFs ({n_free}) to solve {self.num_modes} modes.")
         # Omega = P_e Q_e on the free electric DOFs, kept factored on the device
         Om = CsrProductOperator(f["P_e"], f["Q_e"], shift=0.0, device=self.device)
-        diag = 1.0 / Om.dinv.cpu().numpy()
-        Oms = CsrProductOperator(f["P_e"], f["Q_e"], shift=-complex(sigma), device=self.device, diag=diag)
+        Oms = CsrProductOperator(f["P_e"], f["Q_e"], shift=-complex(sigma), device=self.device, diag=Om.diag)
         stats = dict(inner_solves=0, inner_iterations=0)
 
         def shifted(r):

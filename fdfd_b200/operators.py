@@ -193,7 +193,10 @@ class CsrProductOperator:
                       up(Q.indptr, np.int32), up(Q.indices, np.int32), up(Q.data, np.complex128)]
         if diag is None:
             diag = np.asarray(P.multiply(Q.T).sum(axis=1)).ravel()
-        self.dinv = up(1.0 / (np.asarray(diag, dtype=np.complex128) + self.shift), np.complex128)
+        self.diag = np.asarray(diag, dtype=np.complex128)
+        d = self.diag + self.shift
+        d = np.where(np.abs(d) > 0, d, 1.0)          # empty rows (fully constrained neighbours): identity
+        self.dinv = up(1.0 / d, np.complex128)
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._L.fdfd_csr_product_create(C.byref(self._h), _lib.C128, self.n, self.m,
