@@ -76,6 +76,8 @@ _PROTOTYPES = {
                                        C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "fdfd_csr_product_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]),
+    "fdfd_csr_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_double, C.c_double]),
     "fdfd_linop_destroy": (None, [C.c_void_p]),
     "fdfd_linop_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdfd_linop_solve": (C.c_int, [C.c_void_p, C.POINTER(KrylovOpts), C.c_void_p, C.c_void_p, C.c_void_p,

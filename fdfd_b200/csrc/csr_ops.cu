@@ -58,11 +58,49 @@ struct CsrProductOp : LinOp {
     }
 };
 
+// y = A x + shift * x for a square device CSR matrix (3-D pencil matrices A, B; K7 residual bases)
+struct CsrOp : LinOp {
+    CsrDev A;
+    double shift_re = 0.0, shift_im = 0.0;
+    int64_t n_local() const override { return A.nrows; }
+    template <typename C>
+    int run(const C* x, C* y, const C* b, cudaStream_t st) {
+        using R = typename real_of<C>::type;
+        const bool sh = shift_re != 0.0 || shift_im != 0.0;
+        csr_spmv_kernel<C><<<ceil_div(A.nrows, 256), 256, 0, st>>>(A.nrows, A.indptr, A.indices, (const C*)A.data, x, y,
+                                                                   mk<C>((R)shift_re, (R)shift_im), sh ? x : nullptr, b);
+        FDFD_CUDA(cudaGetLastError());
+        return FDFD_OK;
+    }
+    int apply(const void* x, void* y, cudaStream_t st) override {
+        if (dtype == FDFD_C128) return run<double2>((const double2*)x, (double2*)y, nullptr, st);
+        return run<float2>((const float2*)x, (float2*)y, nullptr, st);
+    }
+    int residual(const void* x, void* r, const void* b, cudaStream_t st) override {
+        if (dtype == FDFD_C128) return run<double2>((const double2*)x, (double2*)r, (const double2*)b, st);
+        return run<float2>((const float2*)x, (float2*)r, (const float2*)b, st);
+    }
+};
+
 }  // namespace fdfd
 
 using namespace fdfd;
 
 struct fdfd_linop { LinOp* op; };
+
+extern "C" int fdfd_csr_create(fdfd_linop_t** out, int dtype, int n, const int32_t* indptr,
+                               const int32_t* indices, const void* data, double shift_re, double shift_im) {
+    FDFD_CHECK_ARG(out && indptr && indices && data, "null pointer");
+    FDFD_CHECK_ARG(dtype == FDFD_C128 || dtype == FDFD_C64, "dtype must be FDFD_C128 or FDFD_C64");
+    FDFD_CHECK_ARG(n >= 1, "bad shape");
+    if (fdfd_device_count() <= 0) { set_error("no CUDA device visible: fdfd_b200 has no CPU path"); return FDFD_ERR_CUDA; }
+    CsrOp* op = new CsrOp();
+    op->dtype = dtype;
+    op->A.nrows = n; op->A.ncols = n; op->A.indptr = indptr; op->A.indices = indices; op->A.data = data;
+    op->shift_re = shift_re; op->shift_im = shift_im;
+    *out = new fdfd_linop{op};
+    return FDFD_OK;
+}
 
 extern "C" int fdfd_csr_product_create(fdfd_linop_t** out, int dtype, int n, int m,
                                        const int32_t* P_indptr, const int32_t* P_indices, const void* P_data,

@@ -247,6 +247,61 @@ class CsrProductOperator:
         return x, d
 
 
+class CsrOperator:
+    """y = A x (+ shift x) for one square scipy CSR matrix uploaded to the device."""
+
+    def __init__(self, A, shift=0.0, device=None):
+        torch = _torch()
+        _lib.require_cuda()
+        self._L = _lib.lib()
+        self.device = torch.device(device or "cuda")
+        A = A.tocsr()
+        if A.shape[0] != A.shape[1]:
+            raise ValueError("square matrix expected")
+        self.n = A.shape[0]
+        self.tdtype = torch.complex128
+
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(self.device)
+        self._keep = [up(A.indptr, np.int32), up(A.indices, np.int32), up(A.data, np.complex128)]
+        self._h = C.c_void_p()
+        sh = complex(shift)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.fdfd_csr_create(C.byref(self._h), _lib.C128, self.n, *[t.data_ptr() for t in self._keep],
+                                               sh.real, sh.imag))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.fdfd_linop_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def apply(self, x, out=None):
+        torch = _torch()
+        x = x.to(device=self.device, dtype=self.tdtype).contiguous().reshape(-1)
+        if x.numel() != self.n:
+            raise ValueError("x has the wrong number of elements")
+        if out is None:
+            out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.fdfd_linop_apply(self._h, x.data_ptr(), out.data_ptr(),
+                                                torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
+    def apply_rows(self, V):
+        """A applied to every row of V (m, n) -> (m, n): the SpMM of the refined extraction."""
+        torch = _torch()
+        out = torch.empty_like(V)
+        for i in range(V.shape[0]):
+            self.apply(V[i], out=out[i])
+        return out
+
+
 class SlabComm:
     """NCCL communicator for y-slab sharding; the 128-byte unique id travels through
     ``torch.distributed`` (any backend) from rank 0."""

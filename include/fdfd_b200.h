@@ -178,6 +178,10 @@ int fdfd_csr_product_create(fdfd_linop_t** out, int dtype, int n, int m,
                             const int32_t* P_indptr, const int32_t* P_indices, const void* P_data,
                             const int32_t* Q_indptr, const int32_t* Q_indices, const void* Q_data,
                             double shift_re, double shift_im);
+/* y = A x + shift * x for one square device CSR matrix (the 3-D pencil matrices A and B of
+ * Periodic_Solver_3D.py:478-533 and the SpMV / SpMM of refined_shift_invert_arnoldi.py:74-75,96-97) */
+int fdfd_csr_create(fdfd_linop_t** out, int dtype, int n, const int32_t* indptr, const int32_t* indices,
+                    const void* data, double shift_re, double shift_im);
 void fdfd_linop_destroy(fdfd_linop_t*);
 int fdfd_linop_apply(fdfd_linop_t*, const void* x, void* y, void* stream);
 int fdfd_linop_solve(fdfd_linop_t*, const fdfd_krylov_opts* opts, const void* dinv, const void* b,

@@ -158,7 +158,58 @@ def mode_fixture():
     np.savez_compressed(os.path.join(HERE, "mode_golden.npz"), **out)
 
 
+def periodic3d_cases():
+    def tiny(cls):
+        s = cls(Nx=8, Ny=7, Nz=6, x_range=4e-3, y_range=3.5e-3, z_range=3e-3, freq=25e9, num_modes=2,
+                sigma_guess=0, tol=1e-10, ncv=14)
+        s.add_pec((1e-3, 3e-3), (1e-3, 1.5e-3), (0, 1.5e-3))
+        s.add_block((6, 5, 4), 1, (1e-3, 3e-3), (0, 1e-3), (0, 6), subpixels=4)
+        s.add_UPML(['+y'], width=2, max_loss=3, n=3)
+        return s, dict(method="refined", max_restarts=6)
+
+    def sweep21(cls):        # first point of Periodic_3D_Dispersion.py (20x18x16, 21 GHz)
+        f = 21e9
+        k0 = 2 * np.pi * f / 3e8
+        s = cls(Nx=20, Ny=18, Nz=16, x_range=6e-3, y_range=6e-3, z_range=8e-3, freq=f, num_modes=2,
+                sigma_guess=1j * k0 * (0.12 * 21 - 2.7), tol=1e-2, ncv=30)
+        s.add_pec(slice(0, 3), slice(10, 11), slice(0, 16))
+        s.add_pec(slice(5, 8), slice(10, 11), slice(0, 16))
+        s.add_block(6, 1, slice(3, 17), slice(11, 17), slice(0, 16), subpixels=8)
+        s.add_pec(slice(0, 20), slice(17, 18), slice(0, 16))
+        s.add_UPML(['+y'], width=8, max_loss=10, n=3)
+        return s, dict(method="refined", max_restarts=8)
+
+    def small_eigs(cls):
+        s = cls(Nx=10, Ny=8, Nz=6, x_range=5e-3, y_range=4e-3, z_range=3e-3, freq=30e9, num_modes=3,
+                sigma_guess=-300j, tol=0, ncv=24)
+        s.add_block(4.0, 1, (1e-3, 4e-3), (0, 2e-3), (0, 6), subpixels=4)
+        s.add_pmc((0, 10), (7, 8), (0, 6))
+        s.add_UPML(['-x', '+x'], width=2, max_loss=2, n=3)
+        return s, dict(method="eigs")
+    return dict(tiny=tiny, sweep21=sweep21, small_eigs=small_eigs)
+
+
+def periodic3d_fixture():
+    mod = ref_loader.load("Periodic_Solver_3D")
+    out = {}
+    for name, build in periodic3d_cases().items():
+        s, kw = build(mod.PeriodicModeSolver3D)
+        s.solve(**kw)
+        out[f"{name}_eigenvalues"] = s.eigenvalues
+        out[f"{name}_gammas"] = s.gammas
+        if s.refined_residuals is not None:
+            out[f"{name}_residuals"] = s.refined_residuals
+            out[f"{name}_restarts"] = np.int64(s.refined_restarts)
+        for fld in ("Ex", "Hy"):
+            out[f"{name}_{fld}_norm"] = np.array([np.linalg.norm(s.fields[fld][m]) for m in range(s.num_modes)])
+            out[f"{name}_{fld}_dec"] = s.fields[fld][:, ::3, ::3, ::2].copy()
+    np.savez_compressed(os.path.join(HERE, "periodic3d_golden.npz"), **out)
+
+
 if __name__ == "__main__":
+    if "--p3d-only" in sys.argv:
+        periodic3d_fixture()
+        sys.exit(0)
     if "--mode-only" in sys.argv:
         mode_fixture()
         sys.exit(0)
@@ -168,6 +219,7 @@ if __name__ == "__main__":
     yee_fixture()
     band_fixture()
     mode_fixture()
+    periodic3d_fixture()
     scatter_small()
     scatter_cfg1()
     for f in sorted(os.listdir(HERE)):

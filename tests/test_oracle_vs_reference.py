@@ -141,3 +141,51 @@ def test_mode_host_logic_and_oracle(case):
     f = mine._factors()
     Om = (f["P_e"] @ f["Q_e"])
     assert abs(Om - o["Omega"]).max() <= 1e-12 * abs(o["Omega"]).max()
+
+
+def _p3d_cases():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.periodic3d_cases()
+
+
+@pytest.mark.parametrize("case", ["tiny", "small_eigs", "sweep21"])
+def test_periodic3d_host_logic_and_oracle(case):
+    """Drop-in 3-D class: cell tensors, Yee-location materials, the sixteen operators and the pencil
+    (A, B) are bit-identical to the reference's; the oracle's refined Arnoldi reproduces the
+    reference eigenvalues (tiny case)."""
+    import fdfd_b200
+    from oracle import periodic3d_oracle as po
+    build = _p3d_cases()[case]
+    ref, kw = build(ref_loader.load("Periodic_Solver_3D").PeriodicModeSolver3D)
+    mine, _ = build(fdfd_b200.PeriodicModeSolver3D)
+    for n in ("Erxx", "Eryy", "Erzz", "Mrxx", "Mryy", "Mrzz"):
+        assert np.array_equal(getattr(ref, f"cell_{n}_3D"), getattr(mine, f"cell_{n}_3D")), n
+        assert np.array_equal(getattr(ref, f"{n}_3D"), getattr(mine, f"{n}_3D")), n
+    assert np.array_equal(ref.material_no_average_mask, mine.material_no_average_mask)
+    ops = ["DEX_EZ_TO_EX", "DEY_EZ_TO_EY", "DEX_EY_TO_HZ", "DEY_EX_TO_HZ", "DHX_HY_TO_EZ", "DHY_HX_TO_EZ",
+           "DHX_HZ_TO_HX", "DHY_HZ_TO_HY", "DEZ_EX", "DEZ_EY", "DHZ_HX", "DHZ_HY", "AZ_EX", "AZ_EY", "AZ_HX", "AZ_HY"]
+    D = po.operators(ref.Nx, ref.Ny, ref.Nz, ref.dx, ref.dy, ref.dz)
+    for name in ops:
+        r = getattr(ref, name)
+        for other in (getattr(mine, name), D[name]):
+            assert r.shape == other.shape and r.format == other.format, name
+            assert r.indptr.tobytes() == other.indptr.tobytes() and r.indices.tobytes() == other.indices.tobytes(), name
+            assert r.data.tobytes() == other.data.tobytes(), name
+    Ar, Br = ref._build_eigen_matrices()
+    Am, Bm = mine._build_eigen_matrices()
+    assert (Ar != Am).nnz == 0 and (Br != Bm).nnz == 0
+    if case != "tiny":
+        return
+    ref.solve(**kw)
+    cell = {k: getattr(ref, f"cell_{k[0].upper()}{k[1:]}_3D") for k in ("erxx", "eryy", "erzz", "mrxx", "mryy", "mrzz")}
+    mats = po.materials_on_fields(cell, ref.material_no_average_mask)
+    A, B = po.pencil(mats, D, ref.omega)
+    assert (A != Ar).nnz == 0 and (B != Br).nnz == 0
+    vals, vecs, res, rs = po.refined_shift_invert_arnoldi(A, B, ref.sigma_guess, ref.num_modes, ref.tol, ncv=ref.ncv,
+                                                          max_restarts=kw["max_restarts"], seed=0)
+    assert np.max(np.abs(vals - ref.eigenvalues)) <= 1e-9 * np.abs(ref.eigenvalues).max()
+    assert rs == ref.refined_restarts and np.allclose(res, ref.refined_residuals, rtol=1e-6)

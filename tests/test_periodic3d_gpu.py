@@ -1,0 +1,57 @@
+"""GPU parity of the 3-D periodic mode solver (device CSR pencil, K7 refined shift-invert Arnoldi /
+K6 Krylov-Schur, dense-LU shifted solve) against golden results of the unmodified reference.
+Bar: eigenvalues / gammas within 1e-8 relative."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases():
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.periodic3d_cases()
+
+
+@pytest.mark.parametrize("case", ["tiny", "small_eigs", "sweep21"])
+def test_periodic3d_vs_golden(golden, case):
+    import fdfd_b200
+    g = golden("periodic3d_golden.npz")
+    s, kw = _cases()[case](fdfd_b200.PeriodicModeSolver3D)
+    s.solve(**kw)
+    ev = g[f"{case}_eigenvalues"]
+    # the refined variant returns the +- pair in |theta - sigma| order; match as sets when nearly tied
+    got = np.array(sorted(s.eigenvalues, key=lambda z: (round(z.real, 6), round(z.imag, 6))))
+    ref = np.array(sorted(ev, key=lambda z: (round(z.real, 6), round(z.imag, 6))))
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-8
+    assert np.allclose(np.sort_complex(s.gammas), np.sort_complex(g[f"{case}_gammas"]), rtol=1e-8, atol=0)
+    if f"{case}_residuals" in g:
+        assert s.refined_restarts == int(g[f"{case}_restarts"])
+        assert np.allclose(np.sort(s.refined_residuals), np.sort(g[f"{case}_residuals"]), rtol=1e-3, atol=1e-13)
+    assert s.fields["Ex"].shape == (s.num_modes, *s.shape_ex) and s.fields["Hy"].shape == (s.num_modes, *s.shape_hy)
+    if np.array_equal(np.round(s.eigenvalues, 6), np.round(ev, 6)):
+        for fld in ("Ex", "Hy"):
+            dec, rdec = s.fields[fld][:, ::3, ::3, ::2], g[f"{case}_{fld}_dec"]
+            for m in range(s.num_modes):          # eigenvectors are defined up to a phase
+                ph = np.vdot(rdec[m], dec[m])
+                ph = ph / abs(ph)
+                assert np.linalg.norm(dec[m] - ph * rdec[m]) <= 1e-5 * np.linalg.norm(rdec[m])
+
+
+def test_periodic3d_refuses_oversized_dense_solve(tmp_path):
+    import fdfd_b200
+    s = fdfd_b200.PeriodicModeSolver3D(6, 6, 4, 3e-3, 3e-3, 2e-3, 30e9, 1, sigma_guess=-200j, tol=1e-8, ncv=10)
+    s.DENSE_LIMIT = 100
+    with pytest.raises(NotImplementedError):
+        s.solve()
+    s.DENSE_LIMIT = 45000
+    s.solve()
+    p = s.save_results(str(tmp_path / "r.npz"), include_eigenvectors=True)
+    t = fdfd_b200.PeriodicModeSolver3D.load_results(p)
+    assert np.array_equal(t.eigenvalues, s.eigenvalues) and np.array_equal(t.fields["Ex"], s.fields["Ex"])
+    with pytest.raises(ValueError):
+        s.solve(method="nope")
