@@ -180,12 +180,19 @@ def periodic3d_cases():
         return s, dict(method="refined", max_restarts=8)
 
     def small_eigs(cls):
-        s = cls(Nx=10, Ny=8, Nz=6, x_range=5e-3, y_range=4e-3, z_range=3e-3, freq=30e9, num_modes=3,
-                sigma_guess=-300j, tol=0, ncv=24)
-        s.add_block(4.0, 1, (1e-3, 4e-3), (0, 2e-3), (0, 6), subpixels=4)
-        s.add_pmc((0, 10), (7, 8), (0, 6))
-        s.add_UPML(['-x', '+x'], width=2, max_loss=2, n=3)
-        return s, dict(method="eigs")
+        # NB: the reference's method="eigs" (ARPACK) is not reproducible on this pencil (singular B, highly
+        # non-normal: it returns start-vector dependent pseudo-eigenvalues near sigma),
+        # so the golden values come from its "refined" method; the GPU "eigs" path (Krylov-Schur) is
+        # tested against them.
+        f = 21e9
+        k0 = 2 * np.pi * f / 3e8
+        s = cls(Nx=10, Ny=9, Nz=8, x_range=6e-3, y_range=6e-3, z_range=8e-3, freq=f, num_modes=2,
+                sigma_guess=1j * k0 * (0.12 * 21 - 2.7), tol=1e-10, ncv=30)
+        s.add_block(6, 1, slice(2, 8), slice(5, 8), slice(0, 8), subpixels=8)
+        s.add_pmc(slice(0, 10), slice(0, 1), slice(0, 8))
+        s.add_pec(slice(0, 10), slice(8, 9), slice(0, 8))
+        s.add_UPML(['+y', '-x'], width=3, max_loss=10, n=3)
+        return s, dict(method="refined", max_restarts=8)
     return dict(tiny=tiny, sweep21=sweep21, small_eigs=small_eigs)
 
 
