@@ -79,28 +79,9 @@ extern "C" int fdfd_helm2d_create(fdfd_helm2d_t** out, int dtype, int pol, int N
     op.comm = comm ? comm->c : nullptr;
     op.variant = 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (sharded) {
-        const size_t rb = (size_t)Nx * op.elem();
-        cudaError_t e;
-        if ((e = cudaMalloc(&op.halo_south, rb)) != cudaSuccess || (e = cudaMalloc(&op.halo_north, rb)) != cudaSuccess ||
-            (e = cudaMalloc(&op.cb_ghost_buf, rb)) != cudaSuccess) {
-            fdfd_helm2d_destroy(h);
-            return cuda_fail(e, "cudaMalloc(halo)", __FILE__, __LINE__);
-        }
-        cudaMemsetAsync(op.halo_south, 0, rb, st);
-        cudaMemsetAsync(op.halo_north, 0, rb, st);
-        // static coefficient ghost: TE needs cb row j0-1 (from the south rank's last row),
-        // TM needs cb row j0+Ny (from the north rank's first row)
-        const int P = op.comm->nranks, r = op.comm->rank;
-        const bool per = bcy == FDFD_BC_BLOCH;
-        const int south = r > 0 ? r - 1 : (per ? P - 1 : -1);
-        const int north = r < P - 1 ? r + 1 : (per ? 0 : -1);
-        int s;
-        if (pol == FDFD_POL_TE)
-            s = comm_sendrecv(op.comm, (const char*)cb + (size_t)(Ny_local - 1) * rb, north, op.cb_ghost_buf, south, rb, st);
-        else
-            s = comm_sendrecv(op.comm, cb, south, op.cb_ghost_buf, north, rb, st);
-        if (s != FDFD_OK) { fdfd_helm2d_destroy(h); return s; }
+    {
+        int st_ = helm2d_setup_sharding(op, st);
+        if (st_ != FDFD_OK) { fdfd_helm2d_destroy(h); return st_; }
     }
     *out = h;
     return FDFD_OK;

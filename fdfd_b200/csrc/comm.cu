@@ -14,6 +14,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -36,13 +37,14 @@ void load_api() {
     SYM(CommInitRank, "ncclCommInitRank");
     SYM(CommDestroy, "ncclCommDestroy");
     SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
     SYM(Send, "ncclSend");
     SYM(Recv, "ncclRecv");
     SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd");
     SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
-    g_ok = g_api.GetUniqueId && g_api.CommInitRank && g_api.CommDestroy && g_api.AllReduce &&
+    g_ok = g_api.GetUniqueId && g_api.CommInitRank && g_api.CommDestroy && g_api.AllReduce && g_api.AllGather &&
            g_api.Send && g_api.Recv && g_api.GroupStart && g_api.GroupEnd;
 }
 
@@ -92,6 +94,15 @@ void comm_destroy(Comm* c) {
 int comm_allreduce_sum(Comm* c, double* buf, int count, cudaStream_t stream) {
     if (!c || c->nranks == 1) return FDFD_OK;
     FDFD_NCCL(g_api.AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)c->nccl, stream));
+    return FDFD_OK;
+}
+
+int comm_allgather(Comm* c, const void* send, void* recv, size_t bytes, cudaStream_t stream) {
+    if (!c || c->nranks == 1) {
+        if (send != recv) FDFD_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, stream));
+        return FDFD_OK;
+    }
+    FDFD_NCCL(g_api.AllGather(send, recv, bytes, ncclChar, (ncclComm_t)c->nccl, stream));
     return FDFD_OK;
 }
 

@@ -24,6 +24,8 @@ int comm_allreduce_sum(Comm* c, double* buf, int count, cudaStream_t stream);
 // (cyclic when `periodic`).  x is the local slab.
 int comm_halo_rows(Comm* c, const void* x, void* halo_south, void* halo_north, int Nx, int Ny,
                    size_t elem, bool periodic, cudaStream_t stream);
+// recv (nranks * bytes) <- concatenation of every rank's `send` (bytes each), rank order
+int comm_allgather(Comm* c, const void* send, void* recv, size_t bytes, cudaStream_t stream);
 // Generic neighbour exchange of arbitrary rows (used once for static coefficient ghosts).
 int comm_sendrecv(Comm* c, const void* send, int dst, void* recv, int src, size_t bytes,
                   cudaStream_t stream);

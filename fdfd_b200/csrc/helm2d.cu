@@ -273,6 +273,33 @@ template HelmArgs<float2> helm2d_args<float2>(const Helm2D&, const float2*, floa
 template int helm2d_launch_args<double2>(const Helm2D&, int, HelmArgs<double2>&, cudaStream_t);
 template int helm2d_launch_args<float2>(const Helm2D&, int, HelmArgs<float2>&, cudaStream_t);
 
+// Ghost-row buffers of a y-slab operator and the one-off exchange of the static coefficient ghost:
+// TE needs cb row j0-1 (the south rank's last row), TM needs cb row j0+Ny (the north rank's first).
+int helm2d_setup_sharding(Helm2D& op, cudaStream_t st) {
+    op.halo_south = op.halo_north = op.cb_ghost_buf = nullptr;
+    if (op.Ny == op.Ny_global) return FDFD_OK;
+    FDFD_CHECK_ARG(op.comm && op.comm->nranks > 1, "sharded operator needs a communicator");
+    const size_t rb = (size_t)op.Nx * op.elem();
+    FDFD_CUDA(cudaMalloc(&op.halo_south, rb));
+    FDFD_CUDA(cudaMalloc(&op.halo_north, rb));
+    FDFD_CUDA(cudaMalloc(&op.cb_ghost_buf, rb));
+    FDFD_CUDA(cudaMemsetAsync(op.halo_south, 0, rb, st));
+    FDFD_CUDA(cudaMemsetAsync(op.halo_north, 0, rb, st));
+    FDFD_CUDA(cudaMemsetAsync(op.cb_ghost_buf, 0, rb, st));
+    const int P = op.comm->nranks, r = op.comm->rank;
+    const bool per = op.bcy == FDFD_BC_BLOCH;
+    const int south = r > 0 ? r - 1 : (per ? P - 1 : -1);
+    const int north = r < P - 1 ? r + 1 : (per ? 0 : -1);
+    if (op.pol == FDFD_POL_TE)
+        return comm_sendrecv(op.comm, (const char*)op.cb + (size_t)(op.Ny - 1) * rb, north, op.cb_ghost_buf, south, rb, st);
+    return comm_sendrecv(op.comm, op.cb, south, op.cb_ghost_buf, north, rb, st);
+}
+
+void helm2d_release_sharding(Helm2D& op) {
+    cudaFree(op.halo_south); cudaFree(op.halo_north); cudaFree(op.cb_ghost_buf);
+    op.halo_south = op.halo_north = op.cb_ghost_buf = nullptr;
+}
+
 int helm2d_halo_exchange(Helm2D& op, const void* x, cudaStream_t stream) {
     if (op.Ny == op.Ny_global) return FDFD_OK;
     return comm_halo_rows(op.comm, x, op.halo_south, op.halo_north, op.Nx, op.Ny, op.elem(),

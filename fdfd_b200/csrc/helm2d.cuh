@@ -75,6 +75,8 @@ int helm2d_launch(const Helm2D& op, int mode, const C* x, C* y, const C* b,
                   const C* ca, const C* cb, const C* cd, double shift_re, double shift_im,
                   double omega, cudaStream_t stream);
 int helm2d_halo_exchange(Helm2D& op, const void* x, cudaStream_t stream);
+int helm2d_setup_sharding(Helm2D& op, cudaStream_t stream);
+void helm2d_release_sharding(Helm2D& op);
 
 // y = A x including halo exchange when sharded (dispatches on dtype).
 int helm2d_apply(Helm2D& op, int mode, const void* x, void* y, const void* b, double omega,

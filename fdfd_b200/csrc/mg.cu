@@ -40,9 +40,16 @@ constexpr int kMaxChunks = 32;
 template <typename C>
 struct PointCoefs { C kw, ke, ks, kn, dg; };
 
+// y-slab sharding: `open_s` / `open_n` say that local row 0 / Ny-1 has a neighbour row on another
+// rank; the face coefficient across that boundary is `cb_ghost` (TE: south rank's last cb row,
+// TM: north rank's first cb row — the same buffer K2 uses).
+template <typename C>
+struct SlabEdge { bool open_s, open_n; const C* cb_ghost; };
+
 template <typename C, bool TM>
 __device__ __forceinline__ PointCoefs<C> point_coefs(const C* ca, const C* cb, const C* cd, int Nx, int Ny,
-        typename real_of<C>::type sx, typename real_of<C>::type sy, C shift, int i, int j) {
+        typename real_of<C>::type sx, typename real_of<C>::type sy, C shift, int i, int j,
+        SlabEdge<C> edge = SlabEdge<C>{false, false, nullptr}) {
     PointCoefs<C> p;
     const int64_t n = (int64_t)j * Nx + i;
     C fw, fe, fs, fn;          // face coefficients incl. wall faces
@@ -50,13 +57,15 @@ __device__ __forceinline__ PointCoefs<C> point_coefs(const C* ca, const C* cb, c
     if (TM) {
         fw = ca[n]; has_w = i > 0;
         has_e = i < Nx - 1; fe = has_e ? ca[n + 1] : czero<C>();
-        fs = cb[n]; has_s = j > 0;
-        has_n = j < Ny - 1; fn = has_n ? cb[n + Nx] : czero<C>();
+        fs = cb[n]; has_s = j > 0 || edge.open_s;
+        has_n = j < Ny - 1 || edge.open_n;
+        fn = j < Ny - 1 ? cb[n + Nx] : (edge.open_n ? edge.cb_ghost[i] : czero<C>());
     } else {
         has_w = i > 0; fw = has_w ? ca[n - 1] : czero<C>();
         fe = ca[n]; has_e = i < Nx - 1;
-        has_s = j > 0; fs = has_s ? cb[n - Nx] : czero<C>();
-        fn = cb[n]; has_n = j < Ny - 1;
+        has_s = j > 0 || edge.open_s;
+        fs = j > 0 ? cb[n - Nx] : (edge.open_s ? edge.cb_ghost[i] : czero<C>());
+        fn = cb[n]; has_n = j < Ny - 1 || edge.open_n;
     }
     p.kw = has_w ? cscale(sx, fw) : czero<C>();
     p.ke = has_e ? cscale(sx, fe) : czero<C>();
@@ -75,31 +84,36 @@ struct LineSet {
     int lo = 0, hi = 0;   // strip widths (number of lines at the low / high end)
     int nl = 0;           // lo + hi
     int len = 0;          // unknowns per line
-    int m = 0, P = 0;     // chunk length, chunks per line
+    int m = 0, P = 0;     // chunk length, chunks per line ON THIS RANK
+    int nranks = 1;       // ranks a line is spread over (y-lines of a sharded grid), else 1
+    int Ptot = 0, k0 = 0; // chunks per line over all ranks, global index of this rank's first chunk
     C *fl = nullptr, *fc = nullptr, *fip = nullptr, *sv = nullptr, *sw = nullptr;  // [len][nl]
-    C *rinv = nullptr;    // [nl][2P*2P] column-major
+    C *rinv = nullptr;    // [nl][2Ptot*2Ptot] row-major
     C *g = nullptr;       // [len][nl] right-hand side / solution workspace
-    C *ifg = nullptr, *ifu = nullptr;  // [nl][2P]
+    C *ifg = nullptr;     // [nl][2P]   interface values of the local chunks
+    C *ifg_all = nullptr; // [nranks][nl][2P] gathered
+    C *ifu = nullptr;     // [nl][2Ptot] interface solution (replicated)
+    C *tips = nullptr, *tips_all = nullptr;  // spike tips [nl][P][4] / [nranks][nl][P][4]
     void release() {
         cudaFree(fl); cudaFree(fc); cudaFree(fip); cudaFree(sv); cudaFree(sw); cudaFree(rinv);
-        cudaFree(g); cudaFree(ifg); cudaFree(ifu);
-        fl = fc = fip = sv = sw = rinv = g = ifg = ifu = nullptr;
+        cudaFree(g); cudaFree(ifg); cudaFree(ifu); cudaFree(ifg_all); cudaFree(tips); cudaFree(tips_all);
+        fl = fc = fip = sv = sw = rinv = g = ifg = ifu = ifg_all = tips = tips_all = nullptr;
     }
 };
 
 template <typename C>
 struct LineView {
-    int dir, lo, hi, nl, len, m, P, Nx, Ny;
-    C *fl, *fc, *fip, *sv, *sw, *rinv, *g, *ifg, *ifu;
+    int dir, lo, hi, nl, len, m, P, Nx, Ny, nranks, Ptot, k0;
+    C *fl, *fc, *fip, *sv, *sw, *rinv, *g, *ifg, *ifg_all, *ifu, *tips, *tips_all;
 };
 
 template <typename C>
 LineView<C> view(const LineSet<C>& s, int Nx, int Ny) {
     LineView<C> v;
     v.dir = s.dir; v.lo = s.lo; v.hi = s.hi; v.nl = s.nl; v.len = s.len; v.m = s.m; v.P = s.P;
-    v.Nx = Nx; v.Ny = Ny;
+    v.Nx = Nx; v.Ny = Ny; v.nranks = s.nranks; v.Ptot = s.Ptot; v.k0 = s.k0;
     v.fl = s.fl; v.fc = s.fc; v.fip = s.fip; v.sv = s.sv; v.sw = s.sw; v.rinv = s.rinv;
-    v.g = s.g; v.ifg = s.ifg; v.ifu = s.ifu;
+    v.g = s.g; v.ifg = s.ifg; v.ifg_all = s.ifg_all; v.ifu = s.ifu; v.tips = s.tips; v.tips_all = s.tips_all;
     return v;
 }
 
@@ -113,13 +127,13 @@ __device__ __forceinline__ void line_point(const LineView<C>& v, int l, int t, i
 // tridiagonal entries of every line: fl <- sub, fip <- diag, fc <- super
 template <typename C, bool TM>
 __global__ void line_extract_kernel(LineView<C> v, const C* ca, const C* cb, const C* cd,
-        typename real_of<C>::type sx, typename real_of<C>::type sy, C shift) {
+        typename real_of<C>::type sx, typename real_of<C>::type sy, C shift, SlabEdge<C> edge) {
     const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (idx >= (int64_t)v.nl * v.len) return;
     const int l = (int)(idx % v.nl), t = (int)(idx / v.nl);
     int i, j;
     line_point(v, l, t, i, j);
-    PointCoefs<C> p = point_coefs<C, TM>(ca, cb, cd, v.Nx, v.Ny, sx, sy, shift, i, j);
+    PointCoefs<C> p = point_coefs<C, TM>(ca, cb, cd, v.Nx, v.Ny, sx, sy, shift, i, j, edge);
     v.fl[idx] = v.dir == 0 ? p.ks : p.kw;
     v.fc[idx] = v.dir == 0 ? p.kn : p.ke;
     v.fip[idx] = p.dg;
@@ -165,6 +179,10 @@ __global__ void line_factor_kernel(LineView<C> v) {
         v.sv[t * nl + l] = ev;
         v.sw[t * nl + l] = ew;
     }
+    // spike tips of this chunk, the only entries of the interface system
+    C* tip = v.tips + ((int64_t)l * v.P + k) * 4;
+    tip[0] = v.sv[t0 * nl + l]; tip[1] = v.sv[(t1 - 1) * nl + l];
+    tip[2] = v.sw[t0 * nl + l]; tip[3] = v.sw[(t1 - 1) * nl + l];
 }
 
 // interface system R (2P x 2P, unknowns f_0, z_0, f_1, z_1, ...) and its inverse by Gauss-Jordan
@@ -174,20 +192,19 @@ __global__ void line_reduced_inverse_kernel(LineView<C> v) {
     extern __shared__ unsigned char smem_raw[];
     C* R = reinterpret_cast<C*>(smem_raw);
     const int l = blockIdx.x;
-    const int n = 2 * v.P;
-    const int64_t nl = v.nl;
+    const int n = 2 * v.Ptot;
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) R[e] = (e / n == e % n) ? mk<C>(1, 0) : czero<C>();
     __syncthreads();
-    for (int k = threadIdx.x; k < v.P; k += blockDim.x) {
-        const int t0 = k * v.m, t1 = min(v.len, t0 + v.m);
-        if (t0 >= t1) continue;
-        if (k > 0) {       // coupling to z_{k-1}
-            R[(2 * k) * n + 2 * (k - 1) + 1] = v.sv[t0 * nl + l];
-            R[(2 * k + 1) * n + 2 * (k - 1) + 1] = v.sv[(t1 - 1) * nl + l];
+    for (int kg = threadIdx.x; kg < v.Ptot; kg += blockDim.x) {
+        const int r = kg / v.P, k = kg % v.P;
+        const C* tip = v.tips_all + (((int64_t)r * v.nl + l) * v.P + k) * 4;
+        if (kg > 0) {                 // coupling to z_{kg-1}
+            R[(2 * kg) * n + 2 * (kg - 1) + 1] = tip[0];
+            R[(2 * kg + 1) * n + 2 * (kg - 1) + 1] = tip[1];
         }
-        if (k < v.P - 1 && (k + 1) * v.m < v.len) {   // coupling to f_{k+1}
-            R[(2 * k) * n + 2 * (k + 1)] = v.sw[t0 * nl + l];
-            R[(2 * k + 1) * n + 2 * (k + 1)] = v.sw[(t1 - 1) * nl + l];
+        if (kg < v.Ptot - 1) {        // coupling to f_{kg+1}
+            R[(2 * kg) * n + 2 * (kg + 1)] = tip[2];
+            R[(2 * kg + 1) * n + 2 * (kg + 1)] = tip[3];
         }
     }
     __syncthreads();
@@ -269,7 +286,7 @@ __global__ void __launch_bounds__(64) line_local_solve_kernel(LineView<C> v) {
             }
         }
     }
-    if (v.P > 1) {
+    if (v.Ptot > 1) {
         v.ifg[(int64_t)l * 2 * v.P + 2 * k] = e;
         v.ifg[(int64_t)l * 2 * v.P + 2 * k + 1] = e_last;
     }
@@ -280,14 +297,14 @@ template <typename C>
 __global__ void __launch_bounds__(256) line_reduced_kernel(LineView<C> v) {
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int n = 2 * v.P;
+    const int n = 2 * v.Ptot, nloc = 2 * v.P;
     if (warp >= (int64_t)v.nl * n) return;
     const int l = (int)(warp / n), row = (int)(warp % n);
     const C* Ri = v.rinv + ((int64_t)l * n + row) * n;
-    const C* gi = v.ifg + (int64_t)l * n;
     double ax = 0.0, ay = 0.0;
     for (int q = lane; q < n; q += 32) {
-        const C r = Ri[q], g = gi[q];
+        // gathered interface values are rank-major: [rank][line][2P]
+        const C r = Ri[q], g = v.ifg_all[((int64_t)(q / nloc) * v.nl + l) * nloc + (q % nloc)];
         ax += (double)r.x * g.x - (double)r.y * g.y;
         ay += (double)r.x * g.y + (double)r.y * g.x;
     }
@@ -306,11 +323,11 @@ __global__ void line_correct_kernel(LineView<C> v, C* x, typename real_of<C>::ty
     if (idx >= (int64_t)v.nl * v.len) return;
     const int l = (int)(idx % v.nl), t = (int)(idx / v.nl);
     C e = v.g[idx];
-    if (v.P > 1) {
-        const int k = t / v.m;
-        const C* u = v.ifu + (int64_t)l * 2 * v.P;
-        if (k > 0) e = csub(e, cmul(v.sv[idx], u[2 * (k - 1) + 1]));
-        if (k < v.P - 1 && (k + 1) * v.m < v.len) e = csub(e, cmul(v.sw[idx], u[2 * (k + 1)]));
+    if (v.Ptot > 1) {
+        const int kg = v.k0 + t / v.m;
+        const C* u = v.ifu + (int64_t)l * 2 * v.Ptot;
+        if (kg > 0) e = csub(e, cmul(v.sv[idx], u[2 * (kg - 1) + 1]));
+        if (kg < v.Ptot - 1) e = csub(e, cmul(v.sw[idx], u[2 * (kg + 1)]));
     }
     if (v.dir == 0) {
         int i, j;
@@ -379,7 +396,7 @@ __global__ void __launch_bounds__(256) strip_rows_scatter_kernel(LineView<C> v, 
 // grid transfer and coarse coefficients
 template <typename C, bool TM>
 __global__ void coarsen_coefs_kernel(int Nxc, int Nyc, const C* ca, const C* cb, const C* cd,
-        C* cac, C* cbc, C* cdc, typename real_of<C>::type wall_mult) {
+        C* cac, C* cbc, C* cdc, typename real_of<C>::type wall_mult, bool wall_lo_y, bool wall_hi_y) {
     using R = typename real_of<C>::type;
     const int I = blockIdx.x * blockDim.x + threadIdx.x, J = blockIdx.y * blockDim.y + threadIdx.y;
     if (I >= Nxc || J >= Nyc) return;
@@ -388,8 +405,9 @@ __global__ void coarsen_coefs_kernel(int Nxc, int Nyc, const C* ca, const C* cb,
     const int64_t f00 = (int64_t)(2 * J) * Nx + 2 * I;
     C a = cscale((R)0.5, cadd(ca[f00 + ix], ca[f00 + Nx + ix]));
     C b = cscale((R)0.5, cadd(cb[f00 + (int64_t)ix * Nx], cb[f00 + (int64_t)ix * Nx + 1]));
-    if (TM) { if (I == 0) a = cscale(wall_mult, a); if (J == 0) b = cscale(wall_mult, b); }
-    else { if (I == Nxc - 1) a = cscale(wall_mult, a); if (J == Nyc - 1) b = cscale(wall_mult, b); }
+    // (y-slab sharding: only the rank that owns the global wall row scales its cb)
+    if (TM) { if (I == 0) a = cscale(wall_mult, a); if (J == 0 && wall_lo_y) b = cscale(wall_mult, b); }
+    else { if (I == Nxc - 1) a = cscale(wall_mult, a); if (J == Nyc - 1 && wall_hi_y) b = cscale(wall_mult, b); }
     const int64_t c = (int64_t)J * Nxc + I;
     cac[c] = a; cbc[c] = b;
     if (cd) cdc[c] = cscale((R)0.25, cadd(cadd(cd[f00], cd[f00 + 1]), cadd(cd[f00 + Nx], cd[f00 + Nx + 1])));
@@ -405,26 +423,31 @@ __global__ void restrict_kernel(int Nxc, int Nyc, const C* rf, C* rc) {
     rc[(int64_t)J * Nxc + I] = cscale((R)0.25, cadd(cadd(rf[f], rf[f + 1]), cadd(rf[f + Nx], rf[f + Nx + 1])));
 }
 
-// x_f += P e_c ; bilinear, clamped on the flux-free side, linear to zero at the wall
+// x_f += P e_c ; bilinear, clamped on the flux-free side, linear to zero at the wall.
+// ec_south / ec_north: coarse ghost rows J = -1 / J = Nyc owned by the neighbouring ranks (null at a
+// global boundary, where the wall / clamp rule applies).
 template <typename C, bool TM>
-__global__ void prolong_add_kernel(int Nxc, int Nyc, const C* ec, C* xf, typename real_of<C>::type wq) {
+__global__ void prolong_add_kernel(int Nxc, int Nyc, const C* ec, C* xf, typename real_of<C>::type wq,
+                                   const C* ec_south, const C* ec_north) {
     using R = typename real_of<C>::type;
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
     const int Nx = 2 * Nxc, Ny = 2 * Nyc;
     if (i >= Nx || j >= Ny) return;
-    // 1-D weights: value = w0 * e[I0] + w1 * e[I1]
-    auto axis = [&](int f, int Nc, int& I0, int& I1, R& w0, R& w1) {
+    // 1-D weights: value = w0 * e[I0] + w1 * e[I1]; `ghost` = I1 lies on a neighbouring rank
+    auto axis = [&](int f, int Nc, bool ghost_lo, bool ghost_hi, int& I0, int& I1, R& w0, R& w1) {
         const int I = f >> 1;
         I0 = I; w0 = (R)0.75; w1 = (R)0.25;
         I1 = (f & 1) ? I + 1 : I - 1;
-        if (I1 < 0) { if (TM) { w0 = wq; w1 = 0; } I1 = 0; if (!TM) { I1 = I; } }
-        else if (I1 >= Nc) { if (!TM) { w0 = wq; w1 = 0; } I1 = Nc - 1; if (TM) { I1 = I; } }
+        if (I1 < 0 && !ghost_lo) { if (TM) { w0 = wq; w1 = 0; } I1 = 0; if (!TM) { I1 = I; } }
+        else if (I1 >= Nc && !ghost_hi) { if (!TM) { w0 = wq; w1 = 0; } I1 = Nc - 1; if (TM) { I1 = I; } }
     };
     int I0, I1, J0, J1; R wx0, wx1, wy0, wy1;
-    axis(i, Nxc, I0, I1, wx0, wx1);
-    axis(j, Nyc, J0, J1, wy0, wy1);
-    C v = cscale(wy0, cadd(cscale(wx0, ec[(int64_t)J0 * Nxc + I0]), cscale(wx1, ec[(int64_t)J0 * Nxc + I1])));
-    v = cadd(v, cscale(wy1, cadd(cscale(wx0, ec[(int64_t)J1 * Nxc + I0]), cscale(wx1, ec[(int64_t)J1 * Nxc + I1]))));
+    axis(i, Nxc, false, false, I0, I1, wx0, wx1);
+    axis(j, Nyc, ec_south != nullptr, ec_north != nullptr, J0, J1, wy0, wy1);
+    const C* row0 = ec + (int64_t)J0 * Nxc;
+    const C* row1 = J1 < 0 ? ec_south : (J1 >= Nyc ? ec_north : ec + (int64_t)J1 * Nxc);
+    C v = cscale(wy0, cadd(cscale(wx0, row0[I0]), cscale(wx1, row0[I1])));
+    v = cadd(v, cscale(wy1, cadd(cscale(wx0, row1[I0]), cscale(wx1, row1[I1]))));
     const int64_t n = (int64_t)j * Nx + i;
     xf[n] = cadd(xf[n], v);
 }
@@ -440,6 +463,10 @@ struct Level {
     bool own_xb = true;
     double delta = 1.0;
     LineSet<C> ylines, xlines;
+    bool first = true, last = true;   // this rank owns the global low-y / high-y wall
+    SlabEdge<C> edge() const {
+        return SlabEdge<C>{!first, !last, (const C*)op.cb_ghost_buf};
+    }
 };
 
 template <typename C>
@@ -485,6 +512,7 @@ struct MGPrecond : Precond {
             if (v.own_coefs) { cudaFree(v.ca); cudaFree(v.cb); cudaFree(v.cd); }
             if (l > 0) cudaFree(v.b);
             cudaFree(v.x0); cudaFree(v.r0); cudaFree(v.t0);
+            helm2d_release_sharding(v.op);
             v.ylines.release(); v.xlines.release();
         }
     }
@@ -495,29 +523,51 @@ struct MGPrecond : Precond {
     int setup_lines(Level<C>& lv, LineSet<C>& s, int dir, int lo, int hi, cudaStream_t st) {
         using R = typename real_of<C>::type;
         const int Nx = lv.op.Nx, Ny = lv.op.Ny;
+        Comm* comm = lv.op.comm;
+        const bool sharded = comm && comm->nranks > 1;
         const int across = dir == 0 ? Nx : Ny;
-        if (lo + hi > across) { lo = across; hi = 0; }
+        if (lo + hi > across) {
+            FDFD_CHECK_ARG(!(sharded && dir == 1), "absorbing-layer rows exceed the rows of one slab");
+            lo = across; hi = 0;
+        }
+        FDFD_CHECK_ARG(!(sharded && dir == 1 && (lo >= Ny || hi >= Ny)), "absorbing-layer rows exceed the rows of one slab");
         s.dir = dir; s.lo = lo; s.hi = hi; s.nl = lo + hi;
         s.len = dir == 0 ? Ny : Nx;
+        // y-lines of a sharded grid run through every rank: each rank owns P chunks of its own rows
+        s.nranks = (dir == 0 && sharded) ? comm->nranks : 1;
         if (s.nl == 0) return FDFD_OK;
-        int P = s.len >= 512 ? kMaxChunks : (s.len >= 128 ? 8 : 1);
+        const int len_global = s.len * s.nranks;
+        int Pglob = len_global >= 512 ? kMaxChunks : (len_global >= 128 ? 8 : 1);
+        int P = Pglob / s.nranks;
+        if (P < 1) P = 1;
+        FDFD_CHECK_ARG(P * s.nranks <= kMaxChunks, "too many ranks for the partitioned line solver");
         s.m = (s.len + P - 1) / P;
         s.P = (s.len + s.m - 1) / s.m;
+        s.Ptot = s.P * s.nranks;
+        s.k0 = (s.nranks > 1 ? comm->rank : 0) * s.P;
         const size_t e = (size_t)s.len * s.nl * sizeof(C);
         FDFD_CUDA(cudaMalloc(&s.fl, e)); FDFD_CUDA(cudaMalloc(&s.fc, e)); FDFD_CUDA(cudaMalloc(&s.fip, e));
         FDFD_CUDA(cudaMalloc(&s.sv, e)); FDFD_CUDA(cudaMalloc(&s.sw, e)); FDFD_CUDA(cudaMalloc(&s.g, e));
         FDFD_CUDA(cudaMemsetAsync(s.sv, 0, e, st)); FDFD_CUDA(cudaMemsetAsync(s.sw, 0, e, st));
-        const size_t ni = (size_t)s.nl * 2 * s.P;
-        FDFD_CUDA(cudaMalloc(&s.ifg, ni * sizeof(C))); FDFD_CUDA(cudaMalloc(&s.ifu, ni * sizeof(C)));
-        FDFD_CUDA(cudaMalloc(&s.rinv, ni * 2 * s.P * sizeof(C)));
+        const size_t nloc = (size_t)s.nl * 2 * s.P, ntot = (size_t)s.nl * 2 * s.Ptot;
+        FDFD_CUDA(cudaMalloc(&s.ifg, nloc * sizeof(C)));
+        FDFD_CUDA(cudaMalloc(&s.ifg_all, ntot * sizeof(C)));
+        FDFD_CUDA(cudaMalloc(&s.ifu, ntot * sizeof(C)));
+        FDFD_CUDA(cudaMalloc(&s.rinv, ntot * 2 * s.Ptot * sizeof(C)));
+        FDFD_CUDA(cudaMalloc(&s.tips, (size_t)s.nl * s.P * 4 * sizeof(C)));
+        FDFD_CUDA(cudaMalloc(&s.tips_all, (size_t)s.nl * s.Ptot * 4 * sizeof(C)));
         LineView<C> v = view(s, Nx, Ny);
         const int64_t tot = (int64_t)s.nl * s.len;
         const int blocks = (int)((tot + 255) / 256);
-        if (TM()) line_extract_kernel<C, true><<<blocks, 256, 0, st>>>(v, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift());
-        else line_extract_kernel<C, false><<<blocks, 256, 0, st>>>(v, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift());
+        if (TM()) line_extract_kernel<C, true><<<blocks, 256, 0, st>>>(v, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), lv.edge());
+        else line_extract_kernel<C, false><<<blocks, 256, 0, st>>>(v, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), lv.edge());
         line_factor_kernel<C><<<(s.nl * s.P + 127) / 128, 128, 0, st>>>(v);
-        if (s.P > 1) {
-            const size_t smem = (size_t)4 * s.P * s.P * sizeof(C);
+        FDFD_CUDA(cudaGetLastError());
+        // every rank needs the spike tips of all chunks to build (and invert) the interface system
+        FDFD_TRY(comm_allgather(s.nranks > 1 ? comm : nullptr, s.tips, s.tips_all,
+                                (size_t)s.nl * s.P * 4 * sizeof(C), st));
+        if (s.Ptot > 1) {
+            const size_t smem = (size_t)4 * s.Ptot * s.Ptot * sizeof(C);
             FDFD_CUDA(cudaFuncSetAttribute(line_reduced_inverse_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             line_reduced_inverse_kernel<C><<<s.nl, 128, smem, st>>>(v);
         }
@@ -529,9 +579,13 @@ struct MGPrecond : Precond {
         using R = typename real_of<C>::type;
         LineView<C> v = view(s, lv.op.Nx, lv.op.Ny);
         line_local_solve_kernel<C><<<(s.nl * s.P + 63) / 64, 64, 0, st>>>(v);
-        if (s.P > 1) line_reduced_kernel<C><<<(int)(((int64_t)s.nl * 2 * s.P * 32 + 255) / 256), 256, 0, st>>>(v);
+        if (s.Ptot > 1) {
+            FDFD_TRY(comm_allgather(s.nranks > 1 ? lv.op.comm : nullptr, s.ifg, s.ifg_all,
+                                    (size_t)s.nl * 2 * s.P * sizeof(C), st));
+            line_reduced_kernel<C><<<(int)(((int64_t)s.nl * 2 * s.Ptot * 32 + 255) / 256), 256, 0, st>>>(v);
+        }
         const int64_t tot = (int64_t)s.nl * s.len;
-        if (s.P > 1 || s.dir == 0)
+        if (s.Ptot > 1 || s.dir == 0)
             line_correct_kernel<C><<<(int)((tot + 255) / 256), 256, 0, st>>>(v, x, (R)omega);
         if (s.dir == 1) {
             dim3 grid((lv.op.Nx + 31) / 32, (s.nl + 31) / 32);
@@ -545,6 +599,7 @@ struct MGPrecond : Precond {
     int smooth(int l, cudaStream_t st) {
         using R = typename real_of<C>::type;
         Level<C>& lv = L[l];
+        FDFD_TRY(helm2d_halo_exchange(lv.op, lv.x, st));
         HelmArgs<C> a = helm2d_args<C>(lv.op, lv.x, lv.t, lv.b, lv.ca, lv.cb, lv.cd, shift_re, shift_im, o.mg_omega);
         a.strip_lo = lv.ylines.lo; a.strip_hi = lv.ylines.hi; a.line_rhs = lv.ylines.g; a.row0 = 0;
         FDFD_TRY(helm2d_launch_args<C>(lv.op, APPLY_SMOOTH, a, st));
@@ -583,6 +638,7 @@ struct MGPrecond : Precond {
             return FDFD_OK;
         }
         for (int s = 0; s < o.mg_pre; ++s) FDFD_TRY(smooth(l, st));
+        FDFD_TRY(helm2d_halo_exchange(lv.op, lv.x, st));
         FDFD_TRY(helm2d_launch<C>(lv.op, APPLY_RESID, lv.x, lv.r, lv.b, lv.ca, lv.cb, lv.cd, shift_re, shift_im, 0.0, st));
         Level<C>& lc = L[l + 1];
         dim3 bt(32, 8);
@@ -594,8 +650,12 @@ struct MGPrecond : Precond {
         const double dc = (lv.delta + 0.5) / 2.0;
         const R wq = (R)(lv.delta / (2.0 * dc));
         dim3 gf((lv.op.Nx + 31) / 32, (lv.op.Ny + 7) / 8);
-        if (TM()) prolong_add_kernel<C, true><<<gf, bt, 0, st>>>(lc.op.Nx, lc.op.Ny, lc.x, lv.x, wq);
-        else prolong_add_kernel<C, false><<<gf, bt, 0, st>>>(lc.op.Nx, lc.op.Ny, lc.x, lv.x, wq);
+        // bilinear interpolation reads one coarse row beyond the slab on each open side
+        FDFD_TRY(helm2d_halo_exchange(lc.op, lc.x, st));
+        const C* gs = lc.first ? nullptr : (const C*)lc.op.halo_south;
+        const C* gn = lc.last ? nullptr : (const C*)lc.op.halo_north;
+        if (TM()) prolong_add_kernel<C, true><<<gf, bt, 0, st>>>(lc.op.Nx, lc.op.Ny, lc.x, lv.x, wq, gs, gn);
+        else prolong_add_kernel<C, false><<<gf, bt, 0, st>>>(lc.op.Nx, lc.op.Ny, lc.x, lv.x, wq, gs, gn);
         FDFD_CUDA(cudaGetLastError());
         for (int s = 0; s < o.mg_post; ++s) FDFD_TRY(smooth(l, st));
         return FDFD_OK;
@@ -648,15 +708,23 @@ struct MGPrecond : Precond {
         using R = typename real_of<C>::type;
         o = opts;
         shift_re = opts.mg_shift_re; shift_im = opts.mg_shift_im;
-        FDFD_CHECK_ARG(A.Ny == A.Ny_global, "multigrid preconditioner: sharded operators not supported yet");
+        const bool sharded = A.Ny != A.Ny_global;
+        if (sharded) {
+            FDFD_CHECK_ARG(A.comm && A.comm->nranks > 1, "sharded operator needs a communicator");
+            FDFD_CHECK_ARG((int64_t)A.Ny * A.comm->nranks == A.Ny_global && A.j0 == A.comm->rank * A.Ny,
+                           "sharded multigrid needs equal y-slabs in rank order");
+            o.mg_graph = 0;      // NCCL calls inside the cycle: no graph capture
+        }
         FDFD_CHECK_ARG(A.bcx == FDFD_BC_DIRICHLET && A.bcy == FDFD_BC_DIRICHLET, "multigrid preconditioner needs Dirichlet walls");
         FDFD_CHECK_ARG(A.cd != nullptr, "multigrid preconditioner needs the diagonal term");
         const int min_n = opts.mg_min_n > 2 ? opts.mg_min_n : 2;
         int lx_lo = opts.line_x_lo, lx_hi = opts.line_x_hi, ly_lo = opts.line_y_lo, ly_hi = opts.line_y_hi;
         Level<C> f;
-        f.op = A; f.op.halo_south = f.op.halo_north = f.op.cb_ghost_buf = nullptr; f.op.h_x = f.op.h_y = nullptr;
+        f.op = A; f.op.h_x = f.op.h_y = nullptr;
         f.ca = (C*)A.ca; f.cb = (C*)A.cb; f.cd = (C*)A.cd; f.own_coefs = false; f.delta = 1.0;
         f.op.shift_re = shift_re; f.op.shift_im = shift_im;
+        f.first = A.j0 == 0; f.last = A.j0 + A.Ny == A.Ny_global;
+        FDFD_TRY(helm2d_setup_sharding(f.op, st));      // the hierarchy owns its ghost buffers on every level
         const double kh_max = opts.mg_kh_max > 0 ? opts.mg_kh_max : 1e30;
         L.push_back(f);
         while (true) {
@@ -667,14 +735,17 @@ struct MGPrecond : Precond {
             cur.x0 = cur.x; cur.r0 = cur.r; cur.t0 = cur.t;
             if (L.size() > 1) FDFD_CUDA(cudaMalloc(&cur.b, bytes));
             FDFD_TRY(setup_lines(cur, cur.ylines, 0, lx_lo, lx_hi, st));
-            FDFD_TRY(setup_lines(cur, cur.xlines, 1, ly_lo, ly_hi, st));
+            FDFD_TRY(setup_lines(cur, cur.xlines, 1, cur.first ? ly_lo : 0, cur.last ? ly_hi : 0, st));
             const bool max_levels = opts.mg_levels > 0 && (int)L.size() >= opts.mg_levels;
+            const int Nyg = cur.op.Ny_global;
             const double s_next = std::min(cur.op.sx, cur.op.sy) / 4.0;
             const double kh_next = s_next > 0 ? 1.0 / std::sqrt(std::fabs(s_next)) : 1e30;
-            if (max_levels || (Nx & 1) || (Ny & 1) || Nx / 2 < min_n || Ny / 2 < min_n || kh_next > kh_max) break;
+            if (max_levels || (Nx & 1) || (Ny & 1) || (cur.op.j0 & 1) || Nx / 2 < min_n || Nyg / 2 < min_n ||
+                kh_next > kh_max) break;
             Level<C> c;
             c.op = cur.op;
-            c.op.Nx = Nx / 2; c.op.Ny = Ny / 2; c.op.Ny_global = Ny / 2; c.op.j0 = 0;
+            c.op.Nx = Nx / 2; c.op.Ny = Ny / 2; c.op.Ny_global = Nyg / 2; c.op.j0 = cur.op.j0 / 2;
+            c.first = cur.first; c.last = cur.last;
             c.op.sx = cur.op.sx / 4; c.op.sy = cur.op.sy / 4;
             c.delta = (cur.delta + 0.5) / 2.0;
             const size_t cb = (size_t)c.op.Nx * c.op.Ny * sizeof(C);
@@ -682,10 +753,11 @@ struct MGPrecond : Precond {
             c.own_coefs = true;
             const R mult = (R)(cur.delta / c.delta);
             dim3 bt(32, 8), g((c.op.Nx + 31) / 32, (c.op.Ny + 7) / 8);
-            if (TM()) coarsen_coefs_kernel<C, true><<<g, bt, 0, st>>>(c.op.Nx, c.op.Ny, cur.ca, cur.cb, cur.cd, c.ca, c.cb, c.cd, mult);
-            else coarsen_coefs_kernel<C, false><<<g, bt, 0, st>>>(c.op.Nx, c.op.Ny, cur.ca, cur.cb, cur.cd, c.ca, c.cb, c.cd, mult);
+            if (TM()) coarsen_coefs_kernel<C, true><<<g, bt, 0, st>>>(c.op.Nx, c.op.Ny, cur.ca, cur.cb, cur.cd, c.ca, c.cb, c.cd, mult, cur.first, cur.last);
+            else coarsen_coefs_kernel<C, false><<<g, bt, 0, st>>>(c.op.Nx, c.op.Ny, cur.ca, cur.cb, cur.cd, c.ca, c.cb, c.cd, mult, cur.first, cur.last);
             FDFD_CUDA(cudaGetLastError());
             c.op.ca = c.ca; c.op.cb = c.cb; c.op.cd = c.cd;
+            FDFD_TRY(helm2d_setup_sharding(c.op, st));
             lx_lo = (lx_lo + 1) / 2; lx_hi = (lx_hi + 1) / 2; ly_lo = (ly_lo + 1) / 2; ly_hi = (ly_hi + 1) / 2;
             L.push_back(c);
         }

@@ -61,6 +61,40 @@ def main():
             failures.append(f"solve {method}: err {err}, relres {info['relres']}")
         part.close()
         full.close()
+    # sharded multigrid preconditioner == single-domain multigrid (same algorithm; the line solver only
+    # partitions its chunks differently), then a full MG-preconditioned scattering solve
+    sys.path.insert(0, ROOT)
+    from oracle import scattering_oracle as so
+    for pol in ("TE", "TM"):
+        N, pw = 256, 12
+        p = so.cylinder_problem(N, eps_r=4.0, pml_width=pw, mask=pw + 8)
+        ca, cb, cd, sx, sy = so.stencil_coefficients(p, pol)
+        v = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+        j0, j1 = fdfd_b200.slab_rows(N, world, rank)
+        lines = dict(line_x_lo=pw, line_x_hi=pw, line_y_lo=pw, line_y_hi=pw, mg_coarse_its=6, mg_shift_im=0.5, mg_omega=0.8)
+        full = fdfd_b200.HelmholtzOperator2D(pol, N, N, ca, cb, cd, sx, sy, device=dev)
+        zf = full.precond_apply(torch.from_numpy(v).to(dev), precond="mg", **lines).reshape(N, N)
+        part = fdfd_b200.HelmholtzOperator2D(pol, N, N, ca[j0:j1], cb[j0:j1], cd[j0:j1], sx, sy, device=dev,
+                                             rows=(j0, j1), comm=comm)
+        zp = part.precond_apply(torch.from_numpy(np.ascontiguousarray(v[j0:j1])).to(dev), precond="mg", **lines)
+        err = (torch.linalg.vector_norm(zp.reshape(-1) - zf[j0:j1].reshape(-1)) / torch.linalg.vector_norm(zf[j0:j1])).item()
+        if not err <= 1e-7:
+            failures.append(f"mg precond {pol}: sharded vs full rel diff {err}")
+        # solve
+        A = so.build_A(p, pol)
+        b = so.rhs(A, p).reshape(N, N)
+        xf, inf_f = full.solve(torch.from_numpy(b).to(dev).reshape(-1), method="fgmres", precond="mg", rtol=1e-9,
+                               maxit=400, line_x_lo=pw, line_x_hi=pw, line_y_lo=pw, line_y_hi=pw)
+        xp, inf_p = part.solve(torch.from_numpy(np.ascontiguousarray(b[j0:j1])).to(dev).reshape(-1), method="fgmres",
+                               precond="mg", rtol=1e-9, maxit=400, line_x_lo=pw, line_x_hi=pw, line_y_lo=pw, line_y_hi=pw)
+        ref = xf.reshape(N, N)[j0:j1].reshape(-1)
+        err = (torch.linalg.vector_norm(xp - ref) / torch.linalg.vector_norm(ref)).item()
+        if err > 1e-6 or inf_p["relres"] > 1e-9 or abs(inf_p["iterations"] - inf_f["iterations"]) > 3:
+            failures.append(f"mg solve {pol}: err {err}, its {inf_p['iterations']} vs {inf_f['iterations']}, relres {inf_p['relres']}")
+        if rank == 0:
+            print(f"sharded MG {pol}: precond ok, solve its {inf_p['iterations']} (single {inf_f['iterations']})", flush=True)
+        part.close()
+        full.close()
     flag = torch.tensor([len(failures)], device=dev)
     dist.all_reduce(flag)
     if failures:
