@@ -48,3 +48,46 @@ def slab_coefficients(Nx, Ny, j0, j1, pol="TE", eps_r=-1e6, f0=10e9, pml=40, sig
         ma, mb, dg = er * (Sx / Sy), er * (Sy / Sx), mr * (Sx * Sy)      # ERyy, ERxx, MRzz
     s = 1.0 / (k0 * dx) ** 2
     return (1.0 / ma).to(dtype).contiguous(), (1.0 / mb).to(dtype).contiguous(), dg.to(dtype).contiguous(), s, s
+
+
+def slab_problem(Nx, Ny, j0, j1, pol="TE", angle_deg=45.0, mask=80, device="cuda", **kw):
+    """Slab coefficients plus the plane-wave source and TF/SF mask rows of the same synthetic problem
+    (Scattering_Solver_2D.py:89-121, :156-173), all built on the device for rows [j0, j1)."""
+    import torch
+
+    ca, cb, cd, sx, sy = slab_coefficients(Nx, Ny, j0, j1, pol=pol, device=device, **kw)
+    f0 = kw.get("f0", 10e9)
+    lam = C0 / f0
+    d = lam / 50.0
+    k0 = 2 * math.pi * f0 / C0
+    x = (torch.arange(Nx, device=device, dtype=torch.float64) + 0.5) * d - Nx * d / 2
+    y = (torch.arange(j0, j1, device=device, dtype=torch.float64) + 0.5) * d - Ny * d / 2
+    kx, ky = k0 * math.cos(math.radians(angle_deg)), k0 * math.sin(math.radians(angle_deg))
+    ph = -(kx * x[None, :] + ky * y[:, None])
+    src = torch.complex(torch.cos(ph), torch.sin(ph))
+    jj = torch.arange(j0, j1, device=device)[:, None]
+    ii = torch.arange(Nx, device=device)[None, :]
+    inside = (ii >= mask) & (ii < Nx - mask) & (jj >= mask) & (jj < Ny - mask)
+    q = torch.where(inside, 0.0, 1.0).to(torch.complex128) if 2 * mask < min(Nx, Ny) else torch.ones_like(src)
+    return ca, cb, cd, sx, sy, src, q
+
+
+def sharded_scattering_solve(Nx, Ny, pol="TE", comm=None, rank=0, world=1, device="cuda", pml=40, mask=80,
+                             solver=None, **kw):
+    """Solve the synthetic scattering problem on `world` y-slabs (one per rank).  Returns
+    (x_local (rows, Nx) device tensor, info dict)."""
+    from .operators import HelmholtzOperator2D, slab_rows
+
+    j0, j1 = slab_rows(Ny, world, rank)
+    ca, cb, cd, sx, sy, src, q = slab_problem(Nx, Ny, j0, j1, pol=pol, mask=mask, device=device, pml=pml, **kw)
+    A = HelmholtzOperator2D(pol, Nx, Ny, ca, cb, cd, sx, sy, device=device,
+                            rows=(j0, j1) if world > 1 else None, comm=comm)
+    s = src.reshape(-1)
+    qf = q.reshape(-1)
+    b = qf * A.apply(s) - A.apply(qf * s)           # (Q A - A Q) src with two sharded stencil applies
+    opts = dict(method="fgmres", precond="mg", rtol=1e-8, maxit=20000, restart=40 if pol.upper() == "TE" else 30,
+                line_x_lo=pml, line_x_hi=pml, line_y_lo=pml, line_y_hi=pml)
+    opts.update(solver or {})
+    x, info = A.solve(b, raise_on_noconv=False, **opts)
+    A.close()
+    return x.reshape(j1 - j0, Nx), info

@@ -89,7 +89,7 @@ def main():
                                precond="mg", rtol=1e-9, maxit=400, line_x_lo=pw, line_x_hi=pw, line_y_lo=pw, line_y_hi=pw)
         ref = xf.reshape(N, N)[j0:j1].reshape(-1)
         err = (torch.linalg.vector_norm(xp - ref) / torch.linalg.vector_norm(ref)).item()
-        if err > 1e-6 or inf_p["relres"] > 1e-9 or abs(inf_p["iterations"] - inf_f["iterations"]) > 3:
+        if err > 1e-6 or inf_p["relres"] > 1e-9 or abs(inf_p["iterations"] - inf_f["iterations"]) > 0.25 * inf_f["iterations"]:
             failures.append(f"mg solve {pol}: err {err}, its {inf_p['iterations']} vs {inf_f['iterations']}, relres {inf_p['relres']}")
         if rank == 0:
             print(f"sharded MG {pol}: precond ok, solve its {inf_p['iterations']} (single {inf_f['iterations']})", flush=True)
