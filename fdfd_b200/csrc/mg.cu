@@ -476,6 +476,8 @@ struct MGPrecond : Precond {
     double shift_re = 1.0, shift_im = 0.5;
     int coarse_its = 8;
     BicgWorkspace coarse_ws;
+    int nlev = 0;       // levels of the cycle = L[0 .. nlev)
+    int rep = -1;       // index in L of the replicated (unsharded) copy of the coarsest level, or -1
     // CUDA-graph replay of the cycle, one executable graph per (input, output) pointer pair
     cudaStream_t gstream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -618,7 +620,25 @@ struct MGPrecond : Precond {
     int cycle(int l, cudaStream_t st) {
         using R = typename real_of<C>::type;
         Level<C>& lv = L[l];
-        const int last = (int)L.size() - 1;
+        const int last = nlev - 1;
+        if (l == last && rep >= 0 && o.mg_coarse_mode == 1) {
+            // Sharded grid: the coarsest problem is latency bound (its kernels do not fill one GPU),
+            // so every rank gathers the coarse right-hand side and solves the WHOLE coarse problem
+            // redundantly with no communication inside, instead of ~90 latency-bound NCCL calls of a
+            // distributed BiCGSTAB; each rank keeps its own rows of the result.
+            Level<C>& R = L[rep];
+            const size_t loc = (size_t)lv.op.n_local() * sizeof(C);
+            FDFD_TRY(comm_allgather(lv.op.comm, lv.b, R.b, loc, st));
+            FDFD_CUDA(cudaMemsetAsync(R.r, 0, (size_t)R.op.n_local() * sizeof(C), st));
+            fdfd_krylov_opts io = o;
+            io.maxit = coarse_its;
+            SolveInfo ii;
+            coarse_pre.mg = this; coarse_pre.level = rep;
+            HelmOp cop(R.op);
+            FDFD_TRY(bicgstab_solve(cop, &coarse_pre, io, R.b, R.r, ii, st, &coarse_ws, true));
+            FDFD_CUDA(cudaMemcpyAsync(lv.x, R.r + (int64_t)lv.op.j0 * lv.op.Nx, loc, cudaMemcpyDeviceToDevice, st));
+            return FDFD_OK;
+        }
         if (l == last) {
             if (o.mg_coarse_mode == 1) {
                 // coarse_its sync-free BiCGSTAB iterations on the shifted coarse operator; the
@@ -762,8 +782,36 @@ struct MGPrecond : Precond {
             lx_lo = (lx_lo + 1) / 2; lx_hi = (lx_hi + 1) / 2; ly_lo = (ly_lo + 1) / 2; ly_hi = (ly_hi + 1) / 2;
             L.push_back(c);
         }
+        nlev = (int)L.size();
+        if (sharded && o.mg_coarse_mode == 1) {
+            // replicated copy of the coarsest level: gather its coefficient slabs (equal slabs in rank
+            // order -> the gathered arrays are the global arrays) and set it up as a single-rank level
+            const Level<C> c = L.back();
+            Level<C> R;
+            R.op = c.op;
+            R.op.Ny = c.op.Ny_global; R.op.j0 = 0; R.op.comm = nullptr;
+            R.op.halo_south = R.op.halo_north = R.op.cb_ghost_buf = nullptr;
+            R.first = R.last = true; R.delta = c.delta;
+            const size_t loc = (size_t)c.op.n_local() * sizeof(C), full = (size_t)R.op.n_local() * sizeof(C);
+            FDFD_CUDA(cudaMalloc(&R.ca, full)); FDFD_CUDA(cudaMalloc(&R.cb, full)); FDFD_CUDA(cudaMalloc(&R.cd, full));
+            R.own_coefs = true;
+            FDFD_TRY(comm_allgather(c.op.comm, c.ca, R.ca, loc, st));
+            FDFD_TRY(comm_allgather(c.op.comm, c.cb, R.cb, loc, st));
+            FDFD_TRY(comm_allgather(c.op.comm, c.cd, R.cd, loc, st));
+            R.op.ca = R.ca; R.op.cb = R.cb; R.op.cd = R.cd;
+            FDFD_CUDA(cudaMalloc(&R.x, full)); FDFD_CUDA(cudaMalloc(&R.r, full)); FDFD_CUDA(cudaMalloc(&R.t, full));
+            FDFD_CUDA(cudaMalloc(&R.b, full));
+            R.x0 = R.x; R.r0 = R.r; R.t0 = R.t;
+            // strip widths of this level (halved once per coarsening, as in the loop above)
+            int wx_lo = opts.line_x_lo, wx_hi = opts.line_x_hi, wy_lo = opts.line_y_lo, wy_hi = opts.line_y_hi;
+            for (int q = 1; q < nlev; ++q) { wx_lo = (wx_lo + 1) / 2; wx_hi = (wx_hi + 1) / 2; wy_lo = (wy_lo + 1) / 2; wy_hi = (wy_hi + 1) / 2; }
+            L.push_back(R);
+            rep = (int)L.size() - 1;
+            FDFD_TRY(setup_lines(L[rep], L[rep].ylines, 0, wx_lo, wx_hi, st));
+            FDFD_TRY(setup_lines(L[rep], L[rep].xlines, 1, wy_lo, wy_hi, st));
+        }
         {
-            const Level<C>& c = L.back();
+            const Level<C>& c = L[nlev - 1];
             const double kh = 1.0 / std::sqrt(std::fabs(std::min(c.op.sx, c.op.sy)));
             if (opts.mg_coarse_its > 0) coarse_its = opts.mg_coarse_its;
             else {
@@ -773,11 +821,11 @@ struct MGPrecond : Precond {
             }
             if (o.verbose)
                 fprintf(stderr, "[fdfd] multigrid: %d levels, coarsest %d x %d (k*h = %.3f), coarse mode %d its %d\n",
-                        (int)L.size(), c.op.Nx, c.op.Ny, kh, o.mg_coarse_mode, coarse_its);
+                        nlev, c.op.Nx, c.op.Ny_global, kh, o.mg_coarse_mode, coarse_its);
         }
         if (o.mg_coarse_mode == 1) {
             // the inner solver must not allocate inside the (captured) cycle
-            const Level<C>& c = L.back();
+            const Level<C>& c = L.back();      // the replicated level when present (the larger one)
             FDFD_TRY(coarse_ws.ensure((size_t)c.op.n_local() * sizeof(C), true));
         }
         if (o.mg_graph) {
