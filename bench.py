@@ -253,6 +253,21 @@ def run_ours(args):
                      "kernel": "helm2d_march_kernel<double2, TE, APPLY_AX>",
                      "algorithmic_bytes_per_launch": bytes_rank},
     }
+    if world > 1 and not args.no_solve:
+        # strong scaling of the time-to-solution: the SAME 4096^2 TE problem split into `world` y-slabs
+        # (inputs generated on the device per slab; sharded multigrid-preconditioned FGMRES)
+        N = args.solve_size
+        barrier()
+        t0 = time.perf_counter()
+        xs, info = synthetic.sharded_scattering_solve(N, N, pol="TE", comm=comm, rank=rank, world=world, device=dev)
+        torch.cuda.synchronize(dev)
+        tt = torch.tensor([time.perf_counter() - t0, info["seconds"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        line["solve"] = {"grid": f"{N}x{N}", "pol": "TE", "scaling": "strong", "n_gpus": world,
+                         "time_to_solution_s": round(float(tt[0]), 3), "device_solve_s": round(float(tt[1]), 3),
+                         "iterations": info["iterations"], "relres": info["relres"], "converged": info["converged"],
+                         "inputs": "synthetic, generated on the device per y-slab"}
+        del xs
     if world == 1 and rank == 0:
         if not args.no_solve:
             line["solve"] = time_to_solution(args)
