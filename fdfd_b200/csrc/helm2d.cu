@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.Nx) return;
     const int Nx = a.Nx, Ny = a.Ny;
-    const int jb = blockIdx.y * a.rows_per_cta;
-    const int je = min(jb + a.rows_per_cta, Ny);
+    const int jb = a.row_begin + blockIdx.y * a.rows_per_cta;
+    const int je = min(jb + a.rows_per_cta, a.row_end);
     if (jb >= je) return;
 
     // x-direction neighbour bookkeeping (column constants)
@@ -195,6 +195,7 @@ HelmArgs<C> helm2d_args(const Helm2D& op, const C* x, C* y, const C* b, const C*
     a.shift = mk<C>((R)shift_re, (R)shift_im);
     a.omega = (R)omega;
     a.strip_lo = a.strip_hi = 0; a.line_rhs = nullptr; a.row0 = 0;
+    a.row_begin = 0; a.row_end = op.Ny;
     // ghost rows
     const bool first = op.j0 == 0, last = op.j0 + op.Ny == op.Ny_global;
     const bool sharded = op.Ny != op.Ny_global;
@@ -233,7 +234,8 @@ int helm2d_launch_args(const Helm2D& op, int mode, HelmArgs<C>& a, cudaStream_t 
     int bx = v.bx;
     while (bx > 32 && bx / 2 >= op.Nx) bx /= 2;
     a.rows_per_cta = v.ry;
-    dim3 grid(ceil_div(op.Nx, bx), ceil_div(op.Ny, v.ry));
+    if (a.row_end <= a.row_begin) return FDFD_OK;
+    dim3 grid(ceil_div(op.Nx, bx), ceil_div(a.row_end - a.row_begin, v.ry));
     FDFD_CHECK_ARG(grid.y <= 65535, "too many row tiles for one launch");
 #define LAUNCH(TMv, MODEv) helm2d_march_kernel<C, TMv, MODEv><<<grid, bx, 0, stream>>>(a)
 #define LAUNCH_MODE(MODEv) do { if (TM) LAUNCH(true, MODEv); else LAUNCH(false, MODEv); } while (0)
@@ -277,6 +279,7 @@ template int helm2d_launch_args<float2>(const Helm2D&, int, HelmArgs<float2>&, c
 // TE needs cb row j0-1 (the south rank's last row), TM needs cb row j0+Ny (the north rank's first).
 int helm2d_setup_sharding(Helm2D& op, cudaStream_t st) {
     op.halo_south = op.halo_north = op.cb_ghost_buf = nullptr;
+    op.comm_stream = nullptr; op.ev_x = op.ev_h = nullptr;
     if (op.Ny == op.Ny_global) return FDFD_OK;
     FDFD_CHECK_ARG(op.comm && op.comm->nranks > 1, "sharded operator needs a communicator");
     const size_t rb = (size_t)op.Nx * op.elem();
@@ -286,6 +289,9 @@ int helm2d_setup_sharding(Helm2D& op, cudaStream_t st) {
     FDFD_CUDA(cudaMemsetAsync(op.halo_south, 0, rb, st));
     FDFD_CUDA(cudaMemsetAsync(op.halo_north, 0, rb, st));
     FDFD_CUDA(cudaMemsetAsync(op.cb_ghost_buf, 0, rb, st));
+    FDFD_CUDA(cudaStreamCreateWithFlags(&op.comm_stream, cudaStreamNonBlocking));
+    FDFD_CUDA(cudaEventCreateWithFlags(&op.ev_x, cudaEventDisableTiming));
+    FDFD_CUDA(cudaEventCreateWithFlags(&op.ev_h, cudaEventDisableTiming));
     const int P = op.comm->nranks, r = op.comm->rank;
     const bool per = op.bcy == FDFD_BC_BLOCH;
     const int south = r > 0 ? r - 1 : (per ? P - 1 : -1);
@@ -297,7 +303,11 @@ int helm2d_setup_sharding(Helm2D& op, cudaStream_t st) {
 
 void helm2d_release_sharding(Helm2D& op) {
     cudaFree(op.halo_south); cudaFree(op.halo_north); cudaFree(op.cb_ghost_buf);
+    if (op.comm_stream) cudaStreamDestroy(op.comm_stream);
+    if (op.ev_x) cudaEventDestroy(op.ev_x);
+    if (op.ev_h) cudaEventDestroy(op.ev_h);
     op.halo_south = op.halo_north = op.cb_ghost_buf = nullptr;
+    op.comm_stream = nullptr; op.ev_x = op.ev_h = nullptr;
 }
 
 int helm2d_halo_exchange(Helm2D& op, const void* x, cudaStream_t stream) {
@@ -306,16 +316,36 @@ int helm2d_halo_exchange(Helm2D& op, const void* x, cudaStream_t stream) {
                           op.bcy == FDFD_BC_BLOCH, stream);
 }
 
+template <typename C>
+static int helm2d_apply_t(Helm2D& op, int mode, const C* x, C* y, const C* b, double omega, cudaStream_t stream) {
+    HelmArgs<C> a = helm2d_args<C>(op, x, y, b, (const C*)op.ca, (const C*)op.cb, (const C*)op.cd,
+                                   op.shift_re, op.shift_im, omega);
+    const bool sharded = op.Ny != op.Ny_global;
+    const int edge = 8;                       // rows per boundary launch (one tile of the default shape)
+    if (!sharded || !op.comm_stream || op.Ny < 4 * edge) {
+        FDFD_TRY(helm2d_halo_exchange(op, x, stream));
+        return helm2d_launch_args<C>(op, mode, a, stream);
+    }
+    // y-slab: exchange the two ghost rows on a side stream while the interior rows (which do not
+    // read them) are computed; the two boundary tiles are launched once the ghosts have arrived
+    FDFD_CUDA(cudaEventRecord(op.ev_x, stream));
+    FDFD_CUDA(cudaStreamWaitEvent(op.comm_stream, op.ev_x, 0));
+    FDFD_TRY(helm2d_halo_exchange(op, x, op.comm_stream));
+    FDFD_CUDA(cudaEventRecord(op.ev_h, op.comm_stream));
+    a.row_begin = edge; a.row_end = op.Ny - edge;
+    FDFD_TRY(helm2d_launch_args<C>(op, mode, a, stream));
+    FDFD_CUDA(cudaStreamWaitEvent(stream, op.ev_h, 0));
+    a.row_begin = 0; a.row_end = edge;
+    FDFD_TRY(helm2d_launch_args<C>(op, mode, a, stream));
+    a.row_begin = op.Ny - edge; a.row_end = op.Ny;
+    return helm2d_launch_args<C>(op, mode, a, stream);
+}
+
 int helm2d_apply(Helm2D& op, int mode, const void* x, void* y, const void* b, double omega,
                  cudaStream_t stream) {
-    FDFD_TRY(helm2d_halo_exchange(op, x, stream));
     if (op.dtype == FDFD_C128)
-        return helm2d_launch<double2>(op, mode, (const double2*)x, (double2*)y, (const double2*)b,
-                                      (const double2*)op.ca, (const double2*)op.cb,
-                                      (const double2*)op.cd, op.shift_re, op.shift_im, omega, stream);
-    return helm2d_launch<float2>(op, mode, (const float2*)x, (float2*)y, (const float2*)b,
-                                 (const float2*)op.ca, (const float2*)op.cb, (const float2*)op.cd,
-                                 op.shift_re, op.shift_im, omega, stream);
+        return helm2d_apply_t<double2>(op, mode, (const double2*)x, (double2*)y, (const double2*)b, omega, stream);
+    return helm2d_apply_t<float2>(op, mode, (const float2*)x, (float2*)y, (const float2*)b, omega, stream);
 }
 
 }  // namespace fdfd

@@ -42,6 +42,7 @@ struct HelmArgs {
     int strip_lo, strip_hi;
     C* line_rhs;         // workspace [row][line], line = strip column index, row stride = strip_lo + strip_hi
     int row0;            // global row of local row 0 (sharded lines)
+    int row_begin, row_end;  // rows this launch covers (halo overlap splits a pass into 3 launches)
 };
 
 struct Helm2D {
@@ -56,6 +57,9 @@ struct Helm2D {
     int variant;
     // ghost rows for sharded operation (device, Nx elements each)
     void *halo_south, *halo_north, *cb_ghost_buf;
+    // halo exchange overlapped with the interior rows: side stream + fork/join events
+    cudaStream_t comm_stream;
+    cudaEvent_t ev_x, ev_h;
     // scratch for *_host entry points
     void *h_x, *h_y;
     int64_t n_local() const { return (int64_t)Nx * Ny; }

@@ -791,6 +791,7 @@ struct MGPrecond : Precond {
             R.op = c.op;
             R.op.Ny = c.op.Ny_global; R.op.j0 = 0; R.op.comm = nullptr;
             R.op.halo_south = R.op.halo_north = R.op.cb_ghost_buf = nullptr;
+            R.op.comm_stream = nullptr; R.op.ev_x = R.op.ev_h = nullptr;
             R.first = R.last = true; R.delta = c.delta;
             const size_t loc = (size_t)c.op.n_local() * sizeof(C), full = (size_t)R.op.n_local() * sizeof(C);
             FDFD_CUDA(cudaMalloc(&R.ca, full)); FDFD_CUDA(cudaMalloc(&R.cb, full)); FDFD_CUDA(cudaMalloc(&R.cd, full));
