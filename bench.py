@@ -24,6 +24,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 NX = 4096
 ROWS_PER_RANK = 4096

@@ -17,6 +17,8 @@
 // once per tile (+1 halo row); the x-neighbours and the second ca value come from L1 (the
 // row was just loaded by the adjacent lanes).  All global accesses are 16-byte, unit-stride
 // across the warp.
+#include <cstdlib>
+
 #include "helm2d.cuh"
 #include "comm.cuh"
 
@@ -322,7 +324,11 @@ static int helm2d_apply_t(Helm2D& op, int mode, const C* x, C* y, const C* b, do
                                    op.shift_re, op.shift_im, omega);
     const bool sharded = op.Ny != op.Ny_global;
     const int edge = 8;                       // rows per boundary launch (one tile of the default shape)
-    if (!sharded || !op.comm_stream || op.Ny < 4 * edge) {
+    // Measured on 2 x B200 (4096^2 per rank): the fork/join below costs ~28 us per apply against
+    // ~10 us for the serial NCCL exchange it hides, so it only pays for slabs whose exchange is slow
+    // relative to the launch overhead; it stays off unless FDFD_OVERLAP_HALO=1.
+    static const bool overlap = getenv("FDFD_OVERLAP_HALO") && atoi(getenv("FDFD_OVERLAP_HALO")) != 0;
+    if (!sharded || !overlap || !op.comm_stream || op.Ny < 4 * edge) {
         FDFD_TRY(helm2d_halo_exchange(op, x, stream));
         return helm2d_launch_args<C>(op, mode, a, stream);
     }
