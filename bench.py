@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
     os.environ["NCCL_DEBUG"] = "WARN"
 
+_OUT = sys.stdout
 NX = 4096
 ROWS_PER_RANK = 4096
 POL = "TE"
@@ -95,7 +96,7 @@ def run_reference(args):
                                  "oracle port (same scipy calls) is timed"},
         "e2e": {"value": round(r["value"], 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -282,7 +283,7 @@ def run_ours(args):
                           f"({r['build_s']:.1f} s) + 10 x CSR SpMV `A @ x` ({r['seconds_per_step'] * 1e3:.1f} ms each)",
                 "host_cores": r["host_threads_available"]}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if comm is not None:
         A.close()
         comm.close()
@@ -320,6 +321,15 @@ def time_to_solution(args):
                          "2048^2 takes 259 s on 8 cores"}
 
 
+def _quiet_stdout():
+    """stdout must carry exactly ONE JSON line: route fd 1 to stderr for the whole run (NCCL / torch
+    print banners such as "NCCL version ..." there) and return a writer bound to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -330,6 +340,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--solve-size", type=int, default=4096)
     args = ap.parse_args()
+    global _OUT
+    _OUT = _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
