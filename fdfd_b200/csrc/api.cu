@@ -1,6 +1,8 @@
 // extern "C" surface of libfdfd_b200.so (see include/fdfd_b200.h).
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
+#include <vector>
 
 #include "comm.cuh"
 #include "helm2d.cuh"
@@ -27,7 +29,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 using namespace fdfd;
 
-struct fdfd_helm2d { Helm2D op; };
+namespace { struct HostPipe; }
+struct fdfd_helm2d { Helm2D op; HostPipe* pipe = nullptr; };
 struct fdfd_comm { Comm* c; };
 
 extern "C" const char* fdfd_last_error(void) { return g_err; }
@@ -87,10 +90,12 @@ extern "C" int fdfd_helm2d_create(fdfd_helm2d_t** out, int dtype, int pol, int N
     return FDFD_OK;
 }
 
+static void destroy_pipe(HostPipe* p);
 extern "C" void fdfd_helm2d_destroy(fdfd_helm2d_t* h) {
     if (!h) return;
     cudaFree(h->op.halo_south); cudaFree(h->op.halo_north); cudaFree(h->op.cb_ghost_buf);
     cudaFree(h->op.h_x); cudaFree(h->op.h_y);
+    destroy_pipe(h->pipe);
     delete h;
 }
 
@@ -107,17 +112,91 @@ static int ensure_host_scratch(Helm2D& op) {
     return FDFD_OK;
 }
 
+// Host-buffer apply, pipelined: the grid is cut into row chunks; chunk k+1 is uploaded while chunk k
+// is computed and chunk k-1 is downloaded (full-duplex PCIe), each on its own non-blocking stream.
+// The stencil of chunk k reads one row of chunk k+1, so its launch waits for that upload.
+namespace {
+struct HostPipe {
+    cudaStream_t up = nullptr, cmp = nullptr, down = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_cmp;
+    int ensure(size_t nchunks) {
+        if (!up) {
+            FDFD_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+            FDFD_CUDA(cudaStreamCreateWithFlags(&cmp, cudaStreamNonBlocking));
+            FDFD_CUDA(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+        }
+        while (ev_up.size() < nchunks) {
+            cudaEvent_t a, b;
+            FDFD_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            FDFD_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            ev_up.push_back(a); ev_cmp.push_back(b);
+        }
+        return FDFD_OK;
+    }
+    ~HostPipe() {
+        for (auto e : ev_up) cudaEventDestroy(e);
+        for (auto e : ev_cmp) cudaEventDestroy(e);
+        if (up) cudaStreamDestroy(up);
+        if (cmp) cudaStreamDestroy(cmp);
+        if (down) cudaStreamDestroy(down);
+    }
+};
+
+template <typename C>
+int apply_host_pipelined(Helm2D& op, HostPipe& pipe, const C* xh, C* yh) {
+    const int Nx = op.Nx, Ny = op.Ny;
+    int rows = (int)(((size_t)24 << 20) / ((size_t)Nx * sizeof(C)));      // ~24 MB per chunk
+    rows = rows < 8 ? 8 : (rows / 8) * 8;                                 // multiple of the tile height
+    const int nch = (Ny + rows - 1) / rows;
+    FDFD_TRY(pipe.ensure((size_t)nch));
+    C* xd = (C*)op.h_x;
+    C* yd = (C*)op.h_y;
+    for (int k = 0; k < nch; ++k) {
+        const int r0 = k * rows, r1 = std::min(Ny, r0 + rows);
+        FDFD_CUDA(cudaMemcpyAsync(xd + (size_t)r0 * Nx, xh + (size_t)r0 * Nx, (size_t)(r1 - r0) * Nx * sizeof(C),
+                                  cudaMemcpyHostToDevice, pipe.up));
+        FDFD_CUDA(cudaEventRecord(pipe.ev_up[k], pipe.up));
+    }
+    HelmArgs<C> a = helm2d_args<C>(op, xd, yd, nullptr, (const C*)op.ca, (const C*)op.cb, (const C*)op.cd,
+                                   op.shift_re, op.shift_im, 0.0);
+    for (int k = 0; k < nch; ++k) {
+        const int r0 = k * rows, r1 = std::min(Ny, r0 + rows);
+        // rows of this chunk read x rows r0-1 .. r1: need uploads up to chunk k+1 (and, for a Bloch
+        // wrap in y, the first and last chunk)
+        FDFD_CUDA(cudaStreamWaitEvent(pipe.cmp, pipe.ev_up[std::min(k + 1, nch - 1)], 0));
+        if (op.bcy == FDFD_BC_BLOCH && (k == 0 || k == nch - 1))
+            FDFD_CUDA(cudaStreamWaitEvent(pipe.cmp, pipe.ev_up[nch - 1], 0));
+        a.row_begin = r0; a.row_end = r1;
+        FDFD_TRY(helm2d_launch_args<C>(op, APPLY_AX, a, pipe.cmp));
+        FDFD_CUDA(cudaEventRecord(pipe.ev_cmp[k], pipe.cmp));
+        FDFD_CUDA(cudaStreamWaitEvent(pipe.down, pipe.ev_cmp[k], 0));
+        FDFD_CUDA(cudaMemcpyAsync(yh + (size_t)r0 * Nx, yd + (size_t)r0 * Nx, (size_t)(r1 - r0) * Nx * sizeof(C),
+                                  cudaMemcpyDeviceToHost, pipe.down));
+    }
+    FDFD_CUDA(cudaStreamSynchronize(pipe.down));
+    return FDFD_OK;
+}
+}  // namespace
+
 extern "C" int fdfd_helm2d_apply_host(fdfd_helm2d_t* h, const void* x_host, void* y_host) {
     FDFD_CHECK_ARG(h && x_host && y_host, "null pointer");
     Helm2D& op = h->op;
     FDFD_TRY(ensure_host_scratch(op));
     const size_t bytes = (size_t)op.n_local() * op.elem();
+    if (op.Ny == op.Ny_global && op.Ny >= 64) {
+        if (!h->pipe) h->pipe = new HostPipe();
+        if (op.dtype == FDFD_C128) return apply_host_pipelined<double2>(op, *h->pipe, (const double2*)x_host, (double2*)y_host);
+        return apply_host_pipelined<float2>(op, *h->pipe, (const float2*)x_host, (float2*)y_host);
+    }
+    // sharded slab (ghost rows come from the neighbours) or tiny grid: plain upload / apply / download
     FDFD_CUDA(cudaMemcpyAsync(op.h_x, x_host, bytes, cudaMemcpyHostToDevice, 0));
     FDFD_TRY(helm2d_apply(op, APPLY_AX, op.h_x, op.h_y, nullptr, 0.0, 0));
     FDFD_CUDA(cudaMemcpyAsync(y_host, op.h_y, bytes, cudaMemcpyDeviceToHost, 0));
     FDFD_CUDA(cudaStreamSynchronize(0));
     return FDFD_OK;
 }
+
+static void destroy_pipe(HostPipe* p) { delete p; }
 
 extern "C" int64_t fdfd_helm2d_bytes_per_apply(const fdfd_helm2d_t* h) {
     if (!h) return 0;

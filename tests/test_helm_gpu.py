@@ -107,6 +107,16 @@ def test_apply_linearity_full_size():
     lhs = A.apply(x1 + alpha * x2)
     rhs = A.apply(x1) + alpha * A.apply(x2)
     assert (torch.linalg.vector_norm(lhs - rhs) / torch.linalg.vector_norm(rhs)).item() <= 1e-14
+    # host-buffer entry point at full size: pipelined in row chunks (upload / compute / download
+    # overlap) -- must equal the device-resident apply bit for bit, for pinned and pageable buffers
+    ref_dev = A.apply(x1).cpu()
+    xh = torch.empty(N * N, dtype=torch.complex128, pin_memory=True)
+    yh = torch.empty(N * N, dtype=torch.complex128, pin_memory=True)
+    xh.copy_(x1.reshape(-1))
+    A.apply_host(xh.numpy(), out=yh.numpy())
+    assert torch.equal(yh, ref_dev.reshape(-1))
+    ypage = A.apply_host(x1.reshape(-1).cpu().numpy())
+    assert np.array_equal(ypage, ref_dev.reshape(-1).numpy())
     # first and last 4 rows against the numpy oracle evaluated on a 5-row band (the band's
     # artificial wall row is excluded; the true walls at j=0 / j=N-1 are exercised)
     full = A.apply(x1).reshape(N, N)
