@@ -37,7 +37,10 @@ class FDFD2DScatteringSolver:
     #: default solver settings; override per instance (``sim.solver_options.update(...)``)
     DEFAULT_SOLVER = dict(method="fgmres", precond="mg", rtol=1e-8, maxit=5000)
 
-    def __init__(self, frequency, x_range, y_range, Nx, Ny, *, dtype="complex128", device=None):
+    def __init__(self, frequency, x_range, y_range, Nx, Ny, *, dtype="complex128", device=None, comm=None):
+        """`comm` (a :class:`fdfd_b200.SlabComm`, one process per GPU) shards the solve into y-slabs:
+        every rank defines the same problem, solves its rows and `solve_total_field_*` returns the
+        full (Ny, Nx) field gathered on every rank."""
         self.frequency = float(frequency)
         self.omega = 2 * np.pi * self.frequency
         self.k0 = self.omega / self.c0
@@ -58,6 +61,12 @@ class FDFD2DScatteringSolver:
         self._pml = dict(x=0, y=0)
         self.dtype = dtype
         self.device = device
+        self.comm = comm
+        if comm is not None and comm.world_size > 1:
+            from .operators import slab_rows
+            self._rows = slab_rows(self.Ny, comm.world_size, comm.rank)
+        else:
+            self._rows = None
         self.solver_options = dict(self.DEFAULT_SOLVER)
         self.solver_info = {}
 
@@ -155,8 +164,12 @@ class FDFD2DScatteringSolver:
         pol = pol.upper()
         if rebuild or pol not in self._ops:
             ca, cb, cd, sx, sy = self.stencil_coefficients(pol)
-            self._ops[pol] = HelmholtzOperator2D(pol, self.Nx, self.Ny, ca, cb, cd, sx, sy,
-                                                 dtype=self.dtype, device=self.device)
+            if self._rows is not None:
+                j0, j1 = self._rows
+                ca, cb, cd = ca[j0:j1], cb[j0:j1], cd[j0:j1]
+            self._ops[pol] = HelmholtzOperator2D(pol, self.Nx, self.Ny, ca, cb, cd, sx, sy, dtype=self.dtype,
+                                                 device=self.device, rows=self._rows,
+                                                 comm=self.comm if self._rows is not None else None)
         return self._ops[pol]
 
     def _build_A_TE(self):
@@ -169,10 +182,14 @@ class FDFD2DScatteringSolver:
         """b = (Q A - A Q) src  (Scattering_Solver_2D.py:198 / :213) with two stencil applies."""
         import torch
 
-        q = torch.from_numpy(np.ascontiguousarray(self.Q.diagonal())).to(A.device).to(A.tdtype)
         if (self.Q - sp.diags(self.Q.diagonal())).nnz:
             raise NotImplementedError("only diagonal mask operators Q are supported on the GPU path")
-        s = torch.from_numpy(np.ascontiguousarray(self.source)).to(A.device).to(A.tdtype)
+        qd, sd = self.Q.diagonal(), self.source
+        if self._rows is not None:
+            lo, hi = self._rows[0] * self.Nx, self._rows[1] * self.Nx
+            qd, sd = qd[lo:hi], sd[lo:hi]
+        q = torch.from_numpy(np.ascontiguousarray(qd)).to(A.device).to(A.tdtype)
+        s = torch.from_numpy(np.ascontiguousarray(sd)).to(A.device).to(A.tdtype)
         return q * A.apply(s) - A.apply(q * s)
 
     def _solve(self, pol, reuse_factorisation=True):
@@ -189,7 +206,23 @@ class FDFD2DScatteringSolver:
             opts.setdefault("line_y_hi", self._pml["y"])
         x, info = A.solve(b, **opts)
         self.solver_info[pol] = info
+        if self._rows is not None:
+            import torch
+            import torch.distributed as dist
+            parts = [torch.empty((r1 - r0) * self.Nx, dtype=x.dtype, device=x.device)
+                     for r0, r1 in (self._slab(r) for r in range(self.comm.world_size))]
+            if dist.get_backend() == "nccl":
+                dist.all_gather(parts, x.contiguous())
+            else:
+                cpu = [p.cpu() for p in parts]
+                dist.all_gather(cpu, x.cpu().contiguous())
+                parts = cpu
+            x = torch.cat([p.to(x.device) for p in parts])
         return x.reshape(self.Ny, self.Nx).cpu().numpy().astype(np.complex128, copy=False)
+
+    def _slab(self, rank):
+        from .operators import slab_rows
+        return slab_rows(self.Ny, self.comm.world_size, rank)
 
     def solve_total_field_TE(self, reuse_factorisation: bool = True):
         self.Ez = self._solve("TE", reuse_factorisation)

@@ -95,6 +95,21 @@ def main():
             print(f"sharded MG {pol}: precond ok, solve its {inf_p['iterations']} (single {inf_f['iterations']})", flush=True)
         part.close()
         full.close()
+    # drop-in class, sharded: every rank gets the full field, equal to the single-GPU result
+    N = 256
+    f0 = 10e9
+    lam = 299792458 / f0
+    fields = []
+    for c in (None, comm):
+        sim = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N, device=dev, comm=c)
+        sim.add_object(4.0, 1.0, (sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
+        sim.add_UPML(pml_width=16, sigma_max=10)
+        sim.add_mask(30)
+        sim.add_source("plane_wave", angle_deg=45.0)
+        fields.append(sim.solve_total_field_TM())
+    err = np.linalg.norm(fields[1] - fields[0]) / np.linalg.norm(fields[0])
+    if fields[1].shape != (N, N) or err > 1e-6:
+        failures.append(f"sharded FDFD2DScatteringSolver: rel diff {err}")
     flag = torch.tensor([len(failures)], device=dev)
     dist.all_reduce(flag)
     if failures:
