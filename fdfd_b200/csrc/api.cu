@@ -227,6 +227,7 @@ extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
     o->mg_coarse_its = 0;          /* 0 = automatic from k*h of the coarsest level */
     o->mg_coarse_mode = 1;
     o->mg_graph = 1;
+    o->mg_coarse_replicate = -1;
     o->lgmres_k = 0;
     o->restart = 30;
     o->mg_kh_max = 1.3;

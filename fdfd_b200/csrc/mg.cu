@@ -783,7 +783,12 @@ struct MGPrecond : Precond {
             L.push_back(c);
         }
         nlev = (int)L.size();
-        if (sharded && o.mg_coarse_mode == 1) {
+        // Replicate the coarsest level only while it is small enough to be latency bound on one GPU
+        // (<= 2^20 points, measured: 1024^2 coarse grid of an 8192^2 problem); larger coarse grids are
+        // bandwidth bound and keep the distributed BiCGSTAB (16384^2: 2048^2 coarse grid).
+        const int64_t coarse_pts = (int64_t)L.back().op.Nx * L.back().op.Ny_global;
+        const bool replicate = opts.mg_coarse_replicate > 0 || (opts.mg_coarse_replicate < 0 && coarse_pts <= ((int64_t)1 << 20));
+        if (sharded && o.mg_coarse_mode == 1 && replicate) {
             // replicated copy of the coarsest level: gather its coefficient slabs (equal slabs in rank
             // order -> the gathered arrays are the global arrays) and set it up as a single-rank level
             const Level<C> c = L.back();

@@ -137,6 +137,8 @@ typedef struct {
     int mg_coarse_mode; /* coarsest level: 0 = mg_coarse_its smoothing sweeps, 1 = mg_coarse_its
                          * iterations of BiCGSTAB preconditioned by one smoothing sweep              */
     int lgmres_k;     /* FGMRES: number of previous-cycle corrections that augment each restart cycle */
+    int mg_coarse_replicate; /* sharded grids: 1 = every rank solves the whole coarsest level, 0 = distributed,
+                              * -1 = automatic (replicate while the coarse grid has <= 2^20 points)        */
     int mg_graph;     /* 1 = replay the multigrid cycle as a captured CUDA graph (default)            */
     double mg_kh_max; /* stop coarsening once k*h = 1/sqrt(min(sx,sy)) of the next level exceeds this */
 } fdfd_krylov_opts;
