@@ -64,6 +64,7 @@ _PROTOTYPES = {
     "fdfd_helm2d_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdfd_helm2d_apply_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdfd_helm2d_bytes_per_apply": (C.c_int64, [C.c_void_p]),
+    "fdfd_helm2d_invalidate": (C.c_int, [C.c_void_p]),
     "fdfd_helm2d_set_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "fdfd_krylov_default_opts": (None, [C.POINTER(KrylovOpts)]),
     "fdfd_krylov_solve": (C.c_int, [C.c_void_p, C.POINTER(KrylovOpts), C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]),

@@ -30,7 +30,15 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 using namespace fdfd;
 
 namespace { struct HostPipe; }
-struct fdfd_helm2d { Helm2D op; HostPipe* pipe = nullptr; };
+struct fdfd_helm2d {
+    Helm2D op;
+    HostPipe* pipe = nullptr;
+    // preconditioner kept between solves with the same operator (the analogue of the reference's
+    // cached factorisation `_LU_TE/_LU_TM`, Scattering_Solver_2D.py:192-194): hierarchy, line-solver
+    // factors and the captured graph are built once
+    Precond* cached_M = nullptr;
+    fdfd_krylov_opts cached_opts;
+};
 struct fdfd_comm { Comm* c; };
 
 extern "C" const char* fdfd_last_error(void) { return g_err; }
@@ -96,6 +104,7 @@ extern "C" void fdfd_helm2d_destroy(fdfd_helm2d_t* h) {
     cudaFree(h->op.halo_south); cudaFree(h->op.halo_north); cudaFree(h->op.cb_ghost_buf);
     cudaFree(h->op.h_x); cudaFree(h->op.h_y);
     destroy_pipe(h->pipe);
+    delete h->cached_M;
     delete h;
 }
 
@@ -238,6 +247,22 @@ extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
     o->reorth = 0;
 }
 
+static bool same_precond(const fdfd_krylov_opts& a, const fdfd_krylov_opts& b) {
+    return a.precond == b.precond && a.mg_levels == b.mg_levels && a.mg_pre == b.mg_pre && a.mg_post == b.mg_post &&
+           a.mg_shift_re == b.mg_shift_re && a.mg_shift_im == b.mg_shift_im && a.mg_omega == b.mg_omega &&
+           a.mg_cycle == b.mg_cycle && a.mg_coarse_its == b.mg_coarse_its && a.line_x_lo == b.line_x_lo &&
+           a.line_x_hi == b.line_x_hi && a.line_y_lo == b.line_y_lo && a.line_y_hi == b.line_y_hi &&
+           a.mg_wfrom == b.mg_wfrom && a.mg_min_n == b.mg_min_n && a.mg_coarse_mode == b.mg_coarse_mode &&
+           a.mg_coarse_replicate == b.mg_coarse_replicate && a.mg_graph == b.mg_graph && a.mg_kh_max == b.mg_kh_max;
+}
+
+extern "C" int fdfd_helm2d_invalidate(fdfd_helm2d_t* h) {
+    FDFD_CHECK_ARG(h, "null operator");
+    delete h->cached_M;
+    h->cached_M = nullptr;
+    return FDFD_OK;
+}
+
 extern "C" int fdfd_krylov_solve(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts, const void* b,
                                  void* x, double* info_out, void* stream) {
     FDFD_CHECK_ARG(h && opts && b && x, "null pointer");
@@ -246,10 +271,20 @@ extern "C" int fdfd_krylov_solve(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts,
     cudaStream_t st = (cudaStream_t)stream;
     Precond* M = nullptr;
     int s = FDFD_OK;
-    if (opts->precond == FDFD_PRECOND_JACOBI) s = make_jacobi_precond(A, &M, st);
-    else if (opts->precond == FDFD_PRECOND_MG) s = make_mg_precond(A, *opts, &M, st);
-    else if (opts->precond != FDFD_PRECOND_NONE) { set_error("unknown preconditioner %d", opts->precond); s = FDFD_ERR_ARG; }
-    if (s != FDFD_OK) return s;
+    if (opts->precond == FDFD_PRECOND_NONE) {
+        M = nullptr;
+    } else if (h->cached_M && same_precond(h->cached_opts, *opts)) {
+        M = h->cached_M;
+    } else {
+        delete h->cached_M;
+        h->cached_M = nullptr;
+        if (opts->precond == FDFD_PRECOND_JACOBI) s = make_jacobi_precond(A, &M, st);
+        else if (opts->precond == FDFD_PRECOND_MG) s = make_mg_precond(A, *opts, &M, st);
+        else { set_error("unknown preconditioner %d", opts->precond); s = FDFD_ERR_ARG; }
+        if (s != FDFD_OK) return s;
+        h->cached_M = M;
+        h->cached_opts = *opts;
+    }
     SolveInfo info;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -264,7 +299,6 @@ extern "C" int fdfd_krylov_solve(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts,
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     info.seconds = ms * 1e-3;
-    delete M;
     if (info_out) {
         info_out[0] = info.iterations; info_out[1] = info.relres; info_out[2] = (double)info.op_applies;
         info_out[3] = (double)info.precond_applies; info_out[4] = info.seconds; info_out[5] = info.breakdowns;

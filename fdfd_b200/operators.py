@@ -82,6 +82,10 @@ class HelmholtzOperator2D:
     def bytes_per_apply(self):
         return int(self._L.fdfd_helm2d_bytes_per_apply(self._h))
 
+    def invalidate(self):
+        """Drop the cached preconditioner (after changing the coefficient tensors in place)."""
+        _lib.check(self._L.fdfd_helm2d_invalidate(self._h))
+
     def set_variant(self, v):
         _lib.check(self._L.fdfd_helm2d_set_variant(self._h, int(v)))
 

@@ -194,6 +194,8 @@ class FDFD2DScatteringSolver:
 
     def _solve(self, pol, reuse_factorisation=True):
         A = self.operator(pol)
+        if not reuse_factorisation:
+            A.invalidate()          # reference: reuse_factorisation=False -> no cached LU (:194, :209)
         b = self._rhs(A)
         opts = dict(self.solver_options)
         # TE (Ez) with strongly negative eps needs a longer recurrence than TM (measured at 4096^2:

@@ -144,6 +144,11 @@ typedef struct {
 } fdfd_krylov_opts;
 
 void fdfd_krylov_default_opts(fdfd_krylov_opts*);
+/* The preconditioner built by a solve (multigrid hierarchy, line factors, captured graph) is kept in
+ * the operator handle and reused by later solves with the same preconditioner options — the
+ * counterpart of the reference's cached factorisation.  Call fdfd_helm2d_invalidate after changing
+ * the coefficient arrays in place. */
+int fdfd_helm2d_invalidate(fdfd_helm2d_t*);
 int fdfd_krylov_solve(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts,
                       const void* b, void* x, double* info, void* stream);
 /* HOST-buffer solve (full operator): uploads b and x0, solves, downloads x. */

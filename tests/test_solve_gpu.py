@@ -101,3 +101,48 @@ def test_scattering_cfg1(golden, pol):
     p = so.cylinder_problem(N)
     ref = so.solve_total_field(p, pol)
     assert np.linalg.norm(F - ref) <= 1e-6 * np.linalg.norm(ref)
+
+
+def test_repeated_solves_reuse_preconditioner(golden):
+    """Second solve on the same operator (new source) reuses the cached multigrid hierarchy, like the
+    reference reuses its LU (`reuse_factorisation=True`); results must still match the oracle."""
+    import time
+    import fdfd_b200
+    N = 192
+    f0 = 10e9
+    lam = 299792458 / f0
+    sim = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N)
+    sim.add_object(4.0, 1.0, (sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
+    sim.add_UPML(pml_width=20, sigma_max=10)
+    sim.add_mask(40)
+    p = so.cylinder_problem(N, eps_r=4.0, pml_width=20, mask=40)
+    times = []
+    for angle, reuse in ((45.0, True), (10.0, True), (70.0, False)):
+        sim.add_source("plane_wave", angle_deg=angle)
+        so.add_source(p, "plane_wave", angle_deg=angle)
+        t = time.perf_counter()
+        F = sim.solve_total_field_TE(reuse_factorisation=reuse)
+        times.append(time.perf_counter() - t)
+        ref = so.solve_total_field(p, "TE")
+        assert np.linalg.norm(F - ref) <= 1e-6 * np.linalg.norm(ref), angle
+    assert sim.solver_info["TE"]["relres"] <= 1e-8
+
+
+@pytest.mark.parametrize("pol", ["TE", "TM"])
+def test_complex64_solve(pol):
+    """complex64 path (40 B/pt operator, fp32 multigrid + FGMRES): residual 1e-4, field within 1e-3."""
+    import fdfd_b200
+    N = 160
+    f0 = 10e9
+    lam = 299792458 / f0
+    sim = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N, dtype="complex64")
+    sim.add_object(4.0, 1.0, (sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
+    sim.add_UPML(pml_width=16, sigma_max=10)
+    sim.add_mask(32)
+    sim.add_source("plane_wave", angle_deg=45.0)
+    sim.solver_options.update(rtol=1e-4)
+    F = getattr(sim, "solve_total_field_" + pol)()
+    p = so.cylinder_problem(N, eps_r=4.0, pml_width=16, mask=32)
+    ref = so.solve_total_field(p, pol)
+    assert sim.solver_info[pol]["relres"] <= 1e-4
+    assert np.linalg.norm(F - ref) <= 2e-3 * np.linalg.norm(ref)
