@@ -237,6 +237,7 @@ extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
     o->mg_coarse_mode = 1;
     o->mg_graph = 1;
     o->mg_coarse_replicate = -1;
+    o->mg_single = 0;
     o->lgmres_k = 0;
     o->restart = 30;
     o->mg_kh_max = 1.3;
@@ -253,7 +254,7 @@ static bool same_precond(const fdfd_krylov_opts& a, const fdfd_krylov_opts& b) {
            a.mg_cycle == b.mg_cycle && a.mg_coarse_its == b.mg_coarse_its && a.line_x_lo == b.line_x_lo &&
            a.line_x_hi == b.line_x_hi && a.line_y_lo == b.line_y_lo && a.line_y_hi == b.line_y_hi &&
            a.mg_wfrom == b.mg_wfrom && a.mg_min_n == b.mg_min_n && a.mg_coarse_mode == b.mg_coarse_mode &&
-           a.mg_coarse_replicate == b.mg_coarse_replicate && a.mg_graph == b.mg_graph && a.mg_kh_max == b.mg_kh_max;
+           a.mg_coarse_replicate == b.mg_coarse_replicate && a.mg_single == b.mg_single && a.mg_graph == b.mg_graph && a.mg_kh_max == b.mg_kh_max;
 }
 
 extern "C" int fdfd_helm2d_invalidate(fdfd_helm2d_t* h) {

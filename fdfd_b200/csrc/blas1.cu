@@ -328,6 +328,24 @@ int pointwise_mul(int64_t n, C* out, const C* x, const C* d, cudaStream_t stream
     return FDFD_OK;
 }
 
+template <typename Cin, typename Cout>
+__global__ void __launch_bounds__(kThreads) convert_kernel(int64_t n, const Cin* __restrict__ in, Cout* __restrict__ out) {
+    using R = typename real_of<Cout>::type;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const Cin v = in[i];
+        out[i] = mk<Cout>((R)v.x, (R)v.y);
+    }
+}
+template <typename Cin, typename Cout>
+int convert(int64_t n, const Cin* in, Cout* out, cudaStream_t stream) {
+    convert_kernel<Cin, Cout><<<stream_grid(n), kThreads, 0, stream>>>(n, in, out);
+    FDFD_CUDA(cudaGetLastError());
+    return FDFD_OK;
+}
+template int convert<double2, float2>(int64_t, const double2*, float2*, cudaStream_t);
+template int convert<float2, double2>(int64_t, const float2*, double2*, cudaStream_t);
+
 int allreduce_slots(Comm* comm, Scalars& sc, int s0, int count, cudaStream_t stream) {
     if (!comm || comm->nranks == 1) return FDFD_OK;
     return comm_allreduce_sum(comm, (double*)(sc.slot + s0), 2 * count, stream);

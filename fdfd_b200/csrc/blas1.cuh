@@ -54,6 +54,10 @@ int scale_inv_sqrt(int64_t n, C* out, const C* x, int nrm2_slot, Scalars& sc, cu
 template <typename C>
 int pointwise_mul(int64_t n, C* out, const C* x, const C* d, cudaStream_t stream);
 
+// out = (Cout) in, elementwise precision conversion (mixed-precision preconditioning)
+template <typename Cin, typename Cout>
+int convert(int64_t n, const Cin* in, Cout* out, cudaStream_t stream);
+
 // sum slots [s0, s0+count) across ranks (no-op without communicator)
 int allreduce_slots(Comm* comm, Scalars& sc, int s0, int count, cudaStream_t stream);
 

@@ -845,10 +845,54 @@ struct MGPrecond : Precond {
     }
 };
 
+// Mixed precision: the cycle runs in complex64 (half the bytes of every smoothing / transfer pass)
+// inside a complex128 flexible Krylov method, which tolerates the inexact preconditioner.
+struct MixedMGPrecond : Precond {
+    Helm2D A32;
+    float2 *ca = nullptr, *cb = nullptr, *cd = nullptr, *v32 = nullptr, *z32 = nullptr;
+    MGPrecond<float2>* mg = nullptr;
+    int64_t n = 0;
+    ~MixedMGPrecond() override {
+        delete mg;
+        cudaFree(ca); cudaFree(cb); cudaFree(cd); cudaFree(v32); cudaFree(z32);
+    }
+    int build(Helm2D& A, const fdfd_krylov_opts& opts, cudaStream_t st) {
+        n = A.n_local();
+        const size_t bytes = (size_t)n * sizeof(float2);
+        FDFD_CUDA(cudaMalloc(&ca, bytes)); FDFD_CUDA(cudaMalloc(&cb, bytes)); FDFD_CUDA(cudaMalloc(&cd, bytes));
+        FDFD_CUDA(cudaMalloc(&v32, bytes)); FDFD_CUDA(cudaMalloc(&z32, bytes));
+        FDFD_TRY((convert<double2, float2>(n, (const double2*)A.ca, ca, st)));
+        FDFD_TRY((convert<double2, float2>(n, (const double2*)A.cb, cb, st)));
+        FDFD_TRY((convert<double2, float2>(n, (const double2*)A.cd, cd, st)));
+        A32 = A;
+        A32.dtype = FDFD_C64;
+        A32.ca = ca; A32.cb = cb; A32.cd = cd;
+        A32.halo_south = A32.halo_north = A32.cb_ghost_buf = nullptr;
+        A32.comm_stream = nullptr; A32.ev_x = A32.ev_h = nullptr;
+        A32.h_x = A32.h_y = nullptr;
+        mg = new MGPrecond<float2>();
+        return mg->build(A32, opts, st);
+    }
+    int apply(const void* v, void* z, cudaStream_t st) override {
+        ++applies;
+        FDFD_TRY((convert<double2, float2>(n, (const double2*)v, v32, st)));
+        FDFD_TRY(mg->apply(v32, z32, st));
+        return convert<float2, double2>(n, z32, (double2*)z, st);
+    }
+};
+
 }  // namespace
 
 int make_mg_precond(Helm2D& A, const fdfd_krylov_opts& opts, Precond** out, cudaStream_t stream) {
     int s;
+    if (A.dtype == FDFD_C128 && opts.mg_single) {
+        FDFD_CHECK_ARG(A.cd != nullptr, "multigrid preconditioner needs the diagonal term");
+        auto* M = new MixedMGPrecond();
+        s = M->build(A, opts, stream);
+        if (s != FDFD_OK) { delete M; return s; }
+        *out = M;
+        return FDFD_OK;
+    }
     if (A.dtype == FDFD_C128) {
         auto* M = new MGPrecond<double2>();
         s = M->build(A, opts, stream);

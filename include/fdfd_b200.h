@@ -139,6 +139,7 @@ typedef struct {
     int lgmres_k;     /* FGMRES: number of previous-cycle corrections that augment each restart cycle */
     int mg_coarse_replicate; /* sharded grids: 1 = every rank solves the whole coarsest level, 0 = distributed,
                               * -1 = automatic (replicate while the coarse grid has <= 2^20 points)        */
+    int mg_single;    /* 1 = run the multigrid cycle in complex64 inside a complex128 solve (mixed precision) */
     int mg_graph;     /* 1 = replay the multigrid cycle as a captured CUDA graph (default)            */
     double mg_kh_max; /* stop coarsening once k*h = 1/sqrt(min(sx,sy)) of the next level exceeds this */
 } fdfd_krylov_opts;

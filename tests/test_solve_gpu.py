@@ -146,3 +146,31 @@ def test_complex64_solve(pol):
     ref = so.solve_total_field(p, pol)
     assert sim.solver_info[pol]["relres"] <= 1e-4
     assert np.linalg.norm(F - ref) <= 2e-3 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("pol", ["TE", "TM"])
+def test_mixed_precision_preconditioner(pol):
+    """complex64 multigrid cycle inside the complex128 FGMRES: same 1e-8 residual / 1e-6 field bars."""
+    import fdfd_b200
+    N = 192
+    f0 = 10e9
+    lam = 299792458 / f0
+    sim = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N)
+    sim.add_object(-1e6, 1.0, (sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
+    sim.add_UPML(pml_width=20, sigma_max=10)
+    sim.add_mask(40)
+    sim.add_source("plane_wave", angle_deg=45.0)
+    sim.solver_options.update(mg_single=1)
+    F = getattr(sim, "solve_total_field_" + pol)()
+    its_mixed = sim.solver_info[pol]["iterations"]
+    p = so.cylinder_problem(N, eps_r=-1e6, pml_width=20, mask=40)
+    ref = so.solve_total_field(p, pol)
+    assert sim.solver_info[pol]["relres"] <= 1e-8
+    assert np.linalg.norm(F - ref) <= 1e-6 * np.linalg.norm(ref)
+    sim2 = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N)
+    sim2.add_object(-1e6, 1.0, (sim2.X ** 2 + sim2.Y ** 2) <= (0.5 * lam) ** 2)
+    sim2.add_UPML(pml_width=20, sigma_max=10)
+    sim2.add_mask(40)
+    sim2.add_source("plane_wave", angle_deg=45.0)
+    getattr(sim2, "solve_total_field_" + pol)()
+    assert its_mixed <= 1.3 * sim2.solver_info[pol]["iterations"] + 3
