@@ -8,8 +8,9 @@ fields, generalised pencil ``A x = gamma B x``.  Same constructor, ``add_block``
 GPU side: the pencil matrices live on the device as CSR (K2b), the refined shift-invert Arnoldi
 (``fdfd_b200.eigs.refined_shift_invert_arnoldi``) keeps its basis, Gram-Schmidt, SpMM and refined
 extraction on the device; ``method="eigs"`` uses the Krylov-Schur solver (K6).  The shifted solve
-is a dense LU on the device for pencils up to ``DENSE_LIMIT`` unknowns (see
-``eigs.DenseShiftedSolver`` for why) — larger cells are refused loudly, never sent to a CPU path.
+is a direct solver on the device: the z-periodic cell is a ring of planes, folded into a block
+tridiagonal matrix and factorised with dense block pivots (``eigs.PlaneBlockShiftedSolver``); cells
+below 4000 unknowns use one dense LU (``eigs.DenseShiftedSolver``).  Nothing is sent to a CPU path.
 Host side (numpy, as the reference): sub-pixel blocks, penalty PEC/PMC, per-layer UPML,
 cell -> Yee averaging, operator and pencil assembly (vectorised; arrays identical).
 """
@@ -24,7 +25,8 @@ _COMPS = ("xx", "yy", "zz")
 
 
 class PeriodicModeSolver3D:
-    DENSE_LIMIT = 45000
+    DENSE_LIMIT = 45000          # dense-LU shifted solve (small cells, or PLANE_BLOCK = False)
+    PLANE_BLOCK = True           # plane-block direct solver (eigs.PlaneBlockShiftedSolver) for cells >= 4000 unknowns
 
     def __init__(self, Nx, Ny, Nz, x_range, y_range, z_range, freq, num_modes, sigma_guess=None, tol=0, ncv=None,
                  *, device=None):
@@ -301,6 +303,11 @@ class PeriodicModeSolver3D:
                     format="csr")
         return A, B
 
+    def _unknown_planes(self):
+        """z-plane index of every unknown of [Ex; Ey; Hx; Hy] (flat index i + nx (j + ny k), k slowest)."""
+        return np.concatenate([np.arange(int(np.prod(sh))) // (sh[0] * sh[1])
+                               for sh in (self.shape_ex, self.shape_ey, self.shape_hx, self.shape_hy)])
+
     # ---- solve (Periodic_Solver_3D.py:535-604) -----------------------------------------------------------------
     def solve(self, method="refined", sigma_guess=None, tol=None, ncv=None, max_restarts=12, random_seed=0):
         import torch
@@ -313,14 +320,16 @@ class PeriodicModeSolver3D:
             raise ValueError("method must be 'eigs' or 'refined'.")
         A, B = self._build_eigen_matrices()
         dev = torch.device(self.device or "cuda")
+        planes = self._unknown_planes() if self.PLANE_BLOCK else None
         if method == "refined":
             (self.eigenvalues, self.eigenvectors, self.refined_residuals,
              self.refined_restarts) = _eigs.refined_shift_invert_arnoldi(
                 A, B, sigma=sigma_guess, num_modes=self.num_modes, tol=tol, ncv=ncv, max_restarts=max_restarts,
-                random_seed=random_seed, device=dev, dense_limit=self.DENSE_LIMIT)
+                random_seed=random_seed, device=dev, dense_limit=self.DENSE_LIMIT, planes=planes, nplanes=self.Nz)
         else:
             Ad, Bd = CsrOperator(A, device=dev), CsrOperator(B, device=dev)
-            solve = _eigs.DenseShiftedSolver(A, B, sigma_guess, dev, limit=self.DENSE_LIMIT)
+            solve = _eigs.make_shifted_solver(A, B, sigma_guess, dev, dense_limit=self.DENSE_LIMIT, planes=planes,
+                                              nplanes=self.Nz)
             lam, X, res, _ = _eigs.eigs_shift_invert(Ad.apply, Bd.apply, solve, A.shape[0], self.num_modes, sigma_guess,
                                                       ncv=ncv, tol=max(float(tol or 0.0), 1e-12), device=dev)
             order = np.argsort(np.abs(lam - sigma_guess))

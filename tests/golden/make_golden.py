@@ -196,6 +196,31 @@ def periodic3d_cases():
     return dict(tiny=tiny, sweep21=sweep21, small_eigs=small_eigs)
 
 
+def periodic3d_cfg4(cls):
+    """BASELINE config 4: example_image_guide_leaky_wave_antenna.py:7-28 verbatim (30x30x32, n = 119 040)."""
+    s = cls(Nx=30, Ny=30, Nz=32, x_range=6e-3, y_range=6e-3, z_range=8e-3, freq=22e9, num_modes=2, sigma_guess=0,
+            tol=0.1, ncv=30)
+    s.add_pec((1.5e-3, 4.5e-3), (1.5e-3, 1.55e-3), (0, 1.5e-3))
+    s.add_block(6, 1, (1.5e-3, 4.5e-3), (0, 1.5e-3), (0, 32), subpixels=8)
+    s.add_UPML(['+y'], width=10, max_loss=5, n=3)
+    return s, dict(method="refined", max_restarts=8)
+
+
+def periodic3d_cfg4_fixture():
+    """~40 min of SuperLU on the host: kept in its own file so the other goldens regenerate fast."""
+    import time
+    mod = ref_loader.load("Periodic_Solver_3D")
+    s, kw = periodic3d_cfg4(mod.PeriodicModeSolver3D)
+    t0 = time.time()
+    s.solve(**kw)
+    out = dict(eigenvalues=s.eigenvalues, gammas=s.gammas, residuals=s.refined_residuals,
+               restarts=np.int64(s.refined_restarts), reference_seconds=np.float64(time.time() - t0))
+    for fld in ("Ex", "Hy"):
+        out[f"{fld}_norm"] = np.array([np.linalg.norm(s.fields[fld][m]) for m in range(s.num_modes)])
+        out[f"{fld}_dec"] = s.fields[fld][:, ::3, ::3, ::4].copy()
+    np.savez_compressed(os.path.join(HERE, "periodic3d_cfg4_golden.npz"), **out)
+
+
 def periodic3d_fixture():
     mod = ref_loader.load("Periodic_Solver_3D")
     out = {}
@@ -214,6 +239,9 @@ def periodic3d_fixture():
 
 
 if __name__ == "__main__":
+    if "--p3d-cfg4" in sys.argv:
+        periodic3d_cfg4_fixture()
+        sys.exit(0)
     if "--p3d-only" in sys.argv:
         periodic3d_fixture()
         sys.exit(0)

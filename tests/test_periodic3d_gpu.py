@@ -47,9 +47,61 @@ def test_periodic3d_vs_golden(golden, case):
                 assert np.linalg.norm(dec[m] - ph * rdec[m]) <= ftol * np.linalg.norm(rdec[m])
 
 
+@pytest.mark.parametrize("case,Nz", [("small_eigs", None), ("odd", 5), ("odd", 7)])
+def test_plane_block_solver_matches_dense_lu(case, Nz):
+    """The folded block-tridiagonal direct solver (even and odd plane counts) against the dense LU
+    of the same shifted pencil, and against the residual of the sparse matrix itself."""
+    import torch
+    import fdfd_b200
+    from fdfd_b200 import eigs
+    if case == "odd":
+        s = fdfd_b200.PeriodicModeSolver3D(6, 5, Nz, 3e-3, 2.5e-3, 2e-3, 30e9, 1, sigma_guess=-200j, tol=1e-8, ncv=10)
+        s.add_block(4, 1, (1e-3, 2e-3), (0, 1e-3), (0, Nz), subpixels=2)
+        s.add_pec((0, 3e-3), (2e-3, 2.5e-3), (0, Nz))
+    else:
+        s, _ = _cases()[case](fdfd_b200.PeriodicModeSolver3D)
+    A, B = s._build_eigen_matrices()
+    blk = eigs.PlaneBlockShiftedSolver(A.tocsr(), B.tocsr(), s.sigma_guess, s._unknown_planes(), s.Nz, "cuda")
+    lu = eigs.DenseShiftedSolver(A.tocsr(), B.tocsr(), s.sigma_guess, "cuda")
+    rng = np.random.default_rng(3)
+    b = rng.standard_normal(A.shape[0]) + 1j * rng.standard_normal(A.shape[0])
+    xb, xl = blk(torch.from_numpy(b).cuda()).cpu().numpy(), lu(torch.from_numpy(b).cuda()).cpu().numpy()
+    S = (A - s.sigma_guess * B).tocsr()
+    assert np.linalg.norm(S @ xb - b) <= 1e-12 * np.linalg.norm(b)
+    assert np.linalg.norm(xb - xl) <= 1e-9 * np.linalg.norm(xl)
+    with pytest.raises(ValueError):                # unknowns that couple across non-neighbouring planes
+        eigs.PlaneBlockShiftedSolver(A.tocsr(), B.tocsr(), s.sigma_guess, (s._unknown_planes() * 2) % s.Nz, s.Nz, "cuda")
+
+
+def test_periodic3d_cfg4_vs_reference():
+    """BASELINE config 4 (example_image_guide_leaky_wave_antenna.py, 30x30x32, n = 119 040): the
+    reference needs ~40 min of SuperLU; golden values from tests/golden/make_golden.py --p3d-cfg4."""
+    import fdfd_b200
+    path = os.path.join(os.path.dirname(__file__), "golden", "periodic3d_cfg4_golden.npz")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    s, kw = m.periodic3d_cfg4(fdfd_b200.PeriodicModeSolver3D)
+    s.solve(**kw)
+    if os.path.exists(path):
+        g = np.load(path)
+        ref_ev, ref_g, ref_res = g["eigenvalues"], g["gammas"], g["residuals"]
+    else:                                           # values recorded in SURVEY.md §8c (12 digits)
+        ref_ev = np.array([132.734212970 + 63.993572050j, -(132.734212970 + 63.993572050j)])
+        ref_g = np.array([0.288072356067 + 0.138884908881j, -(0.288072356067 + 0.138884908881j)])
+        ref_res = np.array([5.3e-11, 4.7e-11])
+    key = lambda z: (round(z.real, 5), round(z.imag, 5))  # noqa: E731
+    got, ref = np.array(sorted(s.eigenvalues, key=key)), np.array(sorted(ref_ev, key=key))
+    assert np.max(np.abs(got - ref) / np.abs(ref)) <= 1e-8
+    assert np.allclose(np.sort_complex(s.gammas), np.sort_complex(ref_g), rtol=1e-8, atol=0)
+    assert np.all(s.refined_residuals <= max(1e-9, 10 * ref_res.max()))
+    assert s.refined_restarts == 0
+
+
 def test_periodic3d_refuses_oversized_dense_solve(tmp_path):
     import fdfd_b200
     s = fdfd_b200.PeriodicModeSolver3D(6, 6, 4, 3e-3, 3e-3, 2e-3, 30e9, 1, sigma_guess=-200j, tol=1e-8, ncv=10)
+    s.PLANE_BLOCK = False
     s.DENSE_LIMIT = 100
     with pytest.raises(NotImplementedError):
         s.solve()
