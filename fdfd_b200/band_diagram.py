@@ -185,7 +185,7 @@ class BandDiagramSolver2D:
 
     # ---- solver core (Band_Diagram_Solver.py:256-336) ------------------------------------------------
     def compute_band_structure(self, beta_path, *, num_bands, polarisations: Iterable[str] = ("TE", "TM"),
-                               eig_sigma=0.0, tol=1e-11, inner="auto"):
+                               eig_sigma=0.0, tol=1e-11, inner="auto", batch=None):
         import torch
 
         polarisations = tuple(p.upper() for p in polarisations)
@@ -213,21 +213,17 @@ class BandDiagramSolver2D:
             dev, tdt = A0.device, A0.tdtype
             Mdev = torch.from_numpy(M).to(dev).to(tdt).reshape(-1)
             cdev = (-sigma) * Mdev.reshape(self.Ny, self.Nx)
-            pieces = self._dense_pieces(kind, A0.ca, A0.cb, cdev) if dense else None
+            if dense:
+                self._sweep_batched(kind, A0, cdev, Mdev, beta_path, num_bands, sigma, tol, delta, pol,
+                                    eigenvalues, frequencies, info, batch)
+                continue
             v0 = None
             for idx in range(ns):
                 ph = self._phases(beta_path[:, idx])
                 A = self._operator(kind, A0.ca, A0.cb, None, ph)
-                if dense:
-                    C0, Cx, Cxp, Cy, Cyp = pieces
-                    px, py = complex(ph[0]), complex(ph[1])
-                    S = C0 + px * Cx + px.conjugate() * Cxp + py * Cy + py.conjugate() * Cyp
-                    LU, piv = torch.linalg.lu_factor(S)
-                    solve = lambda r: torch.linalg.lu_solve(LU, piv, r.reshape(-1, 1)).reshape(-1)  # noqa: E731
-                else:
-                    As = self._operator(kind, A0.ca, A0.cb, cdev, ph)
-                    solve = lambda r: As.solve(r, method="bicgstab", precond="jacobi", rtol=1e-13,  # noqa: E731
-                                               maxit=20000)[0]
+                As = self._operator(kind, A0.ca, A0.cb, cdev, ph)
+                solve = lambda r: As.solve(r, method="bicgstab", precond="jacobi", rtol=1e-13,  # noqa: E731
+                                           maxit=20000)[0]
                 lam, X, res, rs = _eigs.eigs_shift_invert(A.apply, lambda v: Mdev * v.reshape(-1), solve, n,
                                                            num_bands, sigma, tol=tol, v0=v0, device=dev, dtype=tdt,
                                                            blas=blas, seed=idx)
@@ -240,6 +236,7 @@ class BandDiagramSolver2D:
                 info["eigensolves"] += 1
                 info["max_residual"] = max(info["max_residual"], float(np.max(res[np.abs(lam) > 1e-6 * delta], initial=0.0)))
                 A.close()
+                As.close()
         self.solver_info = info
         result = BandStructureResult(beta_path=beta_path, tick_positions=self._tick_positions_from_path(beta_path),
                                      tick_labels=getattr(self, "_tick_labels", []) or
@@ -247,6 +244,70 @@ class BandDiagramSolver2D:
                                      frequencies=frequencies, eigenvalues=eigenvalues)
         self._results = result
         return result
+
+    def _sweep_batched(self, kind, A0, cdev, Mdev, beta_path, num_bands, sigma, tol, delta, pol, eigenvalues,
+                       frequencies, info, batch):
+        """All path points of one polarisation in lock-step: the shifted operator
+        is an affine function of the two Bloch phases, so the dense pieces are assembled once, each
+        chunk of points forms its shifted matrices by broadcasting, inverts them as one batch and
+        runs `eigs.krylov_schur_batched` — one batched GEMV per Arnoldi step for the whole chunk."""
+        import torch
+        import time
+        n, ns = self.Nx * self.Ny, beta_path.shape[1]
+        dev, tdt = A0.device, A0.tdtype
+
+        def lap(key, t0):
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            info[key] = info.get(key, 0.0) + time.perf_counter() - t0
+            return time.perf_counter()
+
+        t = time.perf_counter()
+        C0, Cx, Cxp, Cy, Cyp = self._dense_pieces(kind, A0.ca, A0.cb, cdev)
+        t = lap("t_assemble", t)
+        if batch is None:                     # S, its inverse and one temporary per point
+            free = torch.cuda.mem_get_info(dev)[0] if dev.type == "cuda" else 8 << 30
+            batch = max(1, min(ns, int(0.6 * free // (3 * n * n * 16))))
+        ph = np.array([self._phases(beta_path[:, i]) for i in range(ns)])
+        for lo in range(0, ns, batch):
+            hi = min(ns, lo + batch)
+            px = torch.from_numpy(ph[lo:hi, 0]).to(dev).to(tdt).view(-1, 1, 1)
+            py = torch.from_numpy(ph[lo:hi, 1]).to(dev).to(tdt).view(-1, 1, 1)
+            S = C0.unsqueeze(0) + px * Cx
+            S += px.conj() * Cxp
+            S += py * Cy
+            S += py.conj() * Cyp
+            inv = torch.linalg.inv(S)
+            t = lap("t_invert", t)
+            state = {"inv": inv}
+
+            def set_active(idx, state=state, inv=inv):
+                state["inv"] = inv if idx is None else inv.index_select(0, idx)
+
+            def op(W, state=state):
+                return torch.bmm(state["inv"], (Mdev * W).unsqueeze(2)).squeeze(2)
+
+            mu, X, _, rs = _eigs.krylov_schur_batched(op, set_active, hi - lo, n, num_bands, tol=tol, device=dev,
+                                                       dtype=tdt, seed=lo)
+            t = lap("t_krylov", t)
+            lam = sigma + 1.0 / mu                                             # (P, k)
+            lam_d = torch.from_numpy(lam).to(dev).to(tdt)
+            MX = Mdev * X                                                     # (P, k, n)
+            AX = torch.bmm(X, S.transpose(1, 2)) + sigma * MX                 # A = S + sigma M
+            num = torch.linalg.vector_norm(AX - lam_d.unsqueeze(2) * MX, dim=2)
+            den = torch.linalg.vector_norm(AX, dim=2) + lam_d.abs() * torch.linalg.vector_norm(MX, dim=2)
+            res = (num / den.clamp_min(1e-300)).cpu().numpy()
+            for i in range(hi - lo):
+                order = np.argsort(np.real(lam[i]))
+                vals = lam[i][order][:num_bands]
+                eigenvalues[pol][:, lo + i] = vals
+                frequencies[pol][:, lo + i] = self._normalise_eigenvalues(vals)
+                info["max_residual"] = max(info["max_residual"],
+                                           float(np.max(res[i][np.abs(lam[i]) > 1e-6 * delta], initial=0.0)))
+            info["restarts"] += rs
+            info["eigensolves"] += hi - lo
+            del S, inv, state
+            t = lap("t_post", t)
 
     def _sort_eigenvalues(self, values, num_bands):
         return values[np.argsort(np.real(values))][:num_bands]

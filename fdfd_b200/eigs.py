@@ -147,6 +147,94 @@ def krylov_schur(op, n, k, *, ncv=None, tol=1e-10, max_restarts=100, v0=None, se
         restarts += 1
 
 
+def krylov_schur_batched(op, set_active, P, n, k, *, ncv=None, tol=1e-10, max_restarts=100, seed=0, device=None,
+                         dtype=None):
+    """`krylov_schur` for P independent operators of equal size advanced in lock-step (the Bloch
+    sweep of Band_Diagram_Solver.py:302-323: one small eigenproblem per path point).  Every Arnoldi
+    step is one batched operator application (`op(W)` on a (Pa, n) block, Pa = points still
+    iterating) plus batched Gram-Schmidt GEMMs, with no host synchronisation inside a cycle; the
+    (ncv+1) x ncv projected matrices of all points visit the host once per cycle for the Ritz
+    test and the Krylov-Schur restart.  `set_active(idx)` tells the operator which points remain
+    (device index tensor, or None for all).
+    Returns (mu (P, k), X (P, k, n) device, resid (P, k), restarts)."""
+    import torch
+
+    device = torch.device(device or "cuda")
+    dtype = dtype or torch.complex128
+    if ncv is None:
+        ncv = max(2 * k + 1, 20)
+    ncv = int(min(max(ncv, k + 2), n))
+    keep = min(ncv - 1, k + max(1, (ncv - k) // 2))
+    g = torch.Generator(device="cpu").manual_seed(int(seed))
+    v0 = (torch.rand((P, n, 2), generator=g, dtype=torch.float64) * 2 - 1)
+    v0 = torch.view_as_complex(v0).to(device=device, dtype=dtype)
+    V = torch.zeros((P, ncv + 1, n), dtype=dtype, device=device)
+    V[:, 0] = v0 / torch.linalg.vector_norm(v0, dim=1, keepdim=True)
+    H = torch.zeros((P, ncv + 1, ncv), dtype=dtype, device=device)
+    active = np.arange(P)
+    mu_out = np.zeros((P, k), dtype=np.complex128)
+    res_out = np.zeros((P, k))
+    X_out = torch.empty((P, k, n), dtype=dtype, device=device)
+    set_active(None)
+    p0, restarts = 0, 0
+    while True:
+        for j in range(p0, ncv):
+            w = op(V[:, j])
+            Vj = V[:, :j + 1]
+            h = torch.bmm(Vj, w.conj().unsqueeze(2)).conj()               # (Pa, j+1, 1) = V^H w
+            w = w - torch.bmm(Vj.transpose(1, 2), h).squeeze(2)
+            h2 = torch.bmm(Vj, w.conj().unsqueeze(2)).conj()
+            w = w - torch.bmm(Vj.transpose(1, 2), h2).squeeze(2)
+            beta = torch.linalg.vector_norm(w, dim=1)
+            H[:, :j + 1, j] = (h + h2).squeeze(2)
+            H[:, j + 1, j] = beta.to(dtype)
+            V[:, j + 1] = w / beta.clamp_min(1e-300).unsqueeze(1)
+        Hh = H.cpu().numpy()
+        Pa = len(active)
+        done = np.zeros(Pa, dtype=bool)
+        Sk = np.zeros((Pa, k, ncv), dtype=np.complex128)
+        Qk = np.zeros((Pa, keep, ncv), dtype=np.complex128)
+        Tn = np.zeros((Pa, ncv + 1, ncv), dtype=np.complex128)
+        for a in range(Pa):
+            Hm, b = Hh[a, :ncv, :ncv], Hh[a, ncv, :ncv]
+            mu, S = np.linalg.eig(Hm)
+            order = np.argsort(-np.abs(mu))
+            mu, S = mu[order], S[:, order]
+            S = S / np.linalg.norm(S, axis=0, keepdims=True)
+            res = np.abs(b @ S)
+            done[a] = np.all(res[:k] <= tol * np.abs(mu[:k]))
+            mu_out[active[a]], res_out[active[a]] = mu[:k], res[:k]
+            Sk[a] = S[:, :k].T
+            if not done[a] and restarts < max_restarts:
+                thr = np.sort(np.abs(mu))[::-1][keep - 1]
+                T, Q, _ = sla.schur(Hm, output="complex", sort=lambda x: abs(x) >= thr * (1 - 1e-12))
+                Qk[a] = Q[:, :keep].T
+                Tn[a, :keep, :keep] = T[:keep, :keep]
+                Tn[a, keep, :keep] = b @ Q[:, :keep]
+        if restarts >= max_restarts:
+            done[:] = True
+        fin = np.flatnonzero(done)
+        if fin.size:
+            X = torch.bmm(torch.from_numpy(Sk[fin]).to(device=device, dtype=dtype), V[torch.from_numpy(fin).to(device), :ncv])
+            X_out[torch.from_numpy(active[fin]).to(device)] = X / torch.linalg.vector_norm(X, dim=2, keepdim=True)
+        go = np.flatnonzero(~done)
+        if go.size == 0:
+            return mu_out, X_out, res_out, restarts
+        gd = torch.from_numpy(go).to(device)
+        Vg = V.index_select(0, gd)
+        Vn = torch.bmm(torch.from_numpy(Qk[go]).to(device=device, dtype=dtype), Vg[:, :ncv])
+        last = Vg[:, ncv].clone()
+        V = Vg
+        V[:, :keep] = Vn
+        V[:, keep] = last
+        V[:, keep + 1:] = 0
+        H = torch.from_numpy(Tn[go]).to(device=device, dtype=dtype)
+        active = active[go]
+        set_active(torch.from_numpy(active).to(device))
+        p0 = keep
+        restarts += 1
+
+
 def eigs_shift_invert(apply_A, apply_M, solve_shifted, n, k, sigma, *, ncv=None, tol=1e-10, max_restarts=100,
                       v0=None, seed=0, device=None, dtype=None, blas=None):
     """k eigenvalues of ``A x = lambda M x`` closest to ``sigma``.
