@@ -38,6 +38,7 @@ struct fdfd_helm2d {
     // factors and the captured graph are built once
     Precond* cached_M = nullptr;
     fdfd_krylov_opts cached_opts;
+    KrylovArena arena;      // Krylov basis memory, kept with the preconditioner
 };
 struct fdfd_comm { Comm* c; };
 
@@ -241,6 +242,7 @@ extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
     o->lgmres_k = 0;
     o->restart = 30;
     o->mg_kh_max = 1.3;
+    o->basis_single = 0;
     o->verbose = 0;
     o->line_x_lo = o->line_x_hi = o->line_y_lo = o->line_y_hi = 0;
     o->mg_wfrom = 3;
@@ -261,6 +263,7 @@ extern "C" int fdfd_helm2d_invalidate(fdfd_helm2d_t* h) {
     FDFD_CHECK_ARG(h, "null operator");
     delete h->cached_M;
     h->cached_M = nullptr;
+    h->arena.release();
     return FDFD_OK;
 }
 
@@ -292,7 +295,7 @@ extern "C" int fdfd_krylov_solve(fdfd_helm2d_t* h, const fdfd_krylov_opts* opts,
     cudaEventRecord(e0, st);
     HelmOp op(A);
     if (opts->method == FDFD_KRYLOV_BICGSTAB) s = bicgstab_solve(op, M, *opts, b, x, info, st);
-    else if (opts->method == FDFD_KRYLOV_FGMRES) s = fgmres_solve(op, M, *opts, b, x, info, st);
+    else if (opts->method == FDFD_KRYLOV_FGMRES) s = fgmres_solve(op, M, *opts, b, x, info, st, &h->arena);
     else { set_error("unknown Krylov method %d", opts->method); s = FDFD_ERR_ARG; }
     cudaEventRecord(e1, st);
     cudaEventSynchronize(e1);

@@ -4,6 +4,10 @@
 #include "blas1.cuh"
 #include "comm.cuh"
 
+#include <cstdlib>
+
+#include <cuda/ptx>
+
 namespace fdfd {
 
 int Scalars::alloc() {
@@ -87,7 +91,12 @@ __device__ __forceinline__ void reduce_finalize(double (&v)[K], double* partials
     }
 }
 
+// (measured on B200: F2F.F64.F32 converts 16 values per clock per SM, DFMA issues 59 per clock per SM;
+// an integer-instruction widening was tried and is slower than the hardware conversion)
 template <typename C> __device__ __forceinline__ double2 to_d(C a) { return make_double2((double)a.x, (double)a.y); }
+template <typename Cout, typename Cin> __device__ __forceinline__ Cout cvt(Cin a) {
+    return mk<Cout>((typename real_of<Cout>::type)a.x, (typename real_of<Cout>::type)a.y);
+}
 template <typename C> __device__ __forceinline__ C from_d(double2 a) {
     return mk<C>((typename real_of<C>::type)a.x, (typename real_of<C>::type)a.y);
 }
@@ -216,44 +225,274 @@ int dots(int64_t n, int ndots, const C* const* xs, const C* const* ys, int s0, S
 // ---------------------------------------------------------------------------------------------
 constexpr int kMB = 8;  // vectors per multi-vector pass
 
-template <typename C>
-__global__ void __launch_bounds__(kThreads) multi_dot_kernel(int64_t n, int k, const C* __restrict__ V,
+// Two consecutive elements per thread and loop trip: a complex64 pair is one 16-byte load, a
+// complex128 pair two of them.  With one 8-byte load per vector and trip the complex64 kernels
+// kept too few bytes in flight (measured 2.8-3.7 TB/s against 5.6-5.8 TB/s for complex128).
+template <typename C> struct Pair { C a, b; };
+__device__ __forceinline__ Pair<float2> ld_pair(const float2* p, int64_t i2) {
+    const float4 v = reinterpret_cast<const float4*>(p)[i2];
+    return Pair<float2>{make_float2(v.x, v.y), make_float2(v.z, v.w)};
+}
+__device__ __forceinline__ Pair<double2> ld_pair(const double2* p, int64_t i2) {
+    return Pair<double2>{p[2 * i2], p[2 * i2 + 1]};
+}
+__device__ __forceinline__ void st_pair(float2* p, int64_t i2, float2 a, float2 b) {
+    reinterpret_cast<float4*>(p)[i2] = make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st_pair(double2* p, int64_t i2, double2 a, double2 b) {
+    p[2 * i2] = a; p[2 * i2 + 1] = b;
+}
+static inline bool pair_ok(const void* V, int64_t ldv, const void* w) {
+    return ((uintptr_t)V % 16 == 0) && ((uintptr_t)w % 16 == 0) && (ldv % 2 == 0);
+}
+
+// four fused multiply-adds per complex element (the separate multiply / add form costs six FP64
+// instructions; these kernels sit close to the FP64 issue limit once the basis is complex64)
+__device__ __forceinline__ void dot_acc(double& re, double& im, double2 a, double2 b) {
+    re = fma(a.x, b.x, re); re = fma(a.y, b.y, re);
+    im = fma(a.x, b.y, im); im = fma(-a.y, b.x, im);
+}
+template <typename C> __device__ __forceinline__ C cfma4(C b, C c, C a) {
+    using R = typename real_of<C>::type;
+    R x = fma(b.x, c.x, a.x); x = fma(-b.y, c.y, x);
+    R y = fma(b.x, c.y, a.y); y = fma(b.y, c.x, y);
+    return mk<C>(x, y);
+}
+
+template <typename CV, typename C, int U>
+__global__ void __launch_bounds__(kThreads) multi_dot_kernel(int64_t n, int k, const CV* __restrict__ V,
         int64_t ldv, const C* __restrict__ w, double* out, double* partials, unsigned int* counter) {
     double acc[2 * kMB];
 #pragma unroll
     for (int q = 0; q < 2 * kMB; ++q) acc[q] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double2 b = to_d(w[i]);
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (U == 2) {
+        const int64_t n2 = n >> 1;
+        for (int64_t i = tid; i < n2; i += stride) {
+            const Pair<C> b = ld_pair(w, i);
+            const double2 b0 = to_d(b.a), b1 = to_d(b.b);
 #pragma unroll
-        for (int q = 0; q < kMB; ++q) {
-            if (q < k) {
-                const double2 a = to_d(V[(int64_t)q * ldv + i]);
-                acc[2 * q] += a.x * b.x + a.y * b.y;
-                acc[2 * q + 1] += a.x * b.y - a.y * b.x;
+            for (int q = 0; q < kMB; ++q) {
+                if (q < k) {
+                    const Pair<CV> a = ld_pair(V + (int64_t)q * ldv, i);
+                    dot_acc(acc[2 * q], acc[2 * q + 1], to_d(a.a), b0);
+                    dot_acc(acc[2 * q], acc[2 * q + 1], to_d(a.b), b1);
+                }
             }
+        }
+        if ((n & 1) && tid == 0) {
+            const double2 b = to_d(w[n - 1]);
+#pragma unroll
+            for (int q = 0; q < kMB; ++q)
+                if (q < k) dot_acc(acc[2 * q], acc[2 * q + 1], to_d(V[(int64_t)q * ldv + n - 1]), b);
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += stride) {
+            const double2 b = to_d(w[i]);
+#pragma unroll
+            for (int q = 0; q < kMB; ++q)
+                if (q < k) dot_acc(acc[2 * q], acc[2 * q + 1], to_d(V[(int64_t)q * ldv + i]), b);
         }
     }
     reduce_finalize<2 * kMB>(acc, partials, counter, out);
 }
 
-template <typename C>
-int multi_dot(int64_t n, int k, const C* V, int64_t ldv, const C* w, int s0, Scalars& sc,
+// ---- bulk-copy (TMA) staged variants -------------------------------------------------------------
+// The register kernels above keep (resident threads) x (loads per trip) bytes in flight; with the
+// 74-84 registers the eight accumulator pairs need, that is ~120 KB per SM for a complex128 basis
+// (5.6-5.9 TB/s) and half of it for a complex64 basis (3.5 TB/s — no gain from the smaller basis).
+// Here one persistent CTA per SM streams tiles of w and of up to eight basis vectors into shared
+// memory with cp.async.bulk (completion on an mbarrier, no registers tied up by loads in flight):
+// up to ~200 KB per SM are in flight whatever the element type, and the threads only do LDS + DFMA.
+namespace ptx = cuda::ptx;
+constexpr int kStreamThreads = 512;
+constexpr int kMaxStages = 16;
+constexpr size_t kStreamSmem = 200 * 1024;
+
+struct StreamPlan { int tile, stages, threads, grid; size_t smem; };
+template <typename CV, typename C>
+static StreamPlan stream_plan(int k) {
+    // tile (elements per vector per stage): about 36-72 KB per stage so that a stage lasts ~1 us per SM.
+    // A complex64 basis runs two CTAs per SM (256 threads, half the shared memory each) so that one CTA
+    // computes while the other sits in its per-tile barrier; the complex128 stages are too large for that.
+    const int ctas = sizeof(CV) == sizeof(float2) ? 2 : 1;
+    int tile = k >= 5 ? 512 : (k >= 2 ? 1024 : 2048);
+    const size_t stage = (size_t)tile * (sizeof(C) + (size_t)k * sizeof(CV));
+    int stages = (int)(kStreamSmem / ctas / stage);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 1) stages = 1;
+    return StreamPlan{tile, stages, kStreamThreads / ctas, kNumSMs * ctas, stage * stages};
+}
+
+template <typename CV, typename C>
+struct StreamPipe {
+    unsigned char* smem;
+    uint64_t* full;
+    int ntiles, my;           // full tiles of the vector; tiles of this CTA
+    int k, tile, stages;
+    uint32_t wbytes, vbytes, stage_bytes;
+    const CV* V; int64_t ldv; const C* w;
+    // consumer / producer cursors kept incrementally (no integer divisions on the per-tile path)
+    int cs, pi, ps;
+    uint32_t cpar;
+
+    __device__ __forceinline__ int64_t tile_elem0(int i) const { return ((int64_t)blockIdx.x + (int64_t)i * gridDim.x) * tile; }
+    __device__ __forceinline__ C* w_tile(int s) const { return (C*)(smem + (uint32_t)s * stage_bytes); }
+    __device__ __forceinline__ CV* v_tile(int s, int q) const {
+        return (CV*)(smem + (uint32_t)s * stage_bytes + wbytes + (uint32_t)q * vbytes);
+    }
+    __device__ __forceinline__ void issue_next() {            // one elected thread
+        const int64_t e0 = tile_elem0(pi);
+        ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, &full[ps], stage_bytes);
+        ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, w_tile(ps), w + e0, wbytes, &full[ps]);
+        for (int q = 0; q < k; ++q)
+            ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, v_tile(ps, q), V + (int64_t)q * ldv + e0, vbytes, &full[ps]);
+        ++pi;
+        if (++ps == stages) ps = 0;
+    }
+    __device__ __forceinline__ void init(unsigned char* sm, uint64_t* bars, int64_t n, int k_, int tile_, int stages_,
+                                         const CV* V_, int64_t ldv_, const C* w_) {
+        smem = sm; full = bars; k = k_; tile = tile_; stages = stages_; V = V_; ldv = ldv_; w = w_;
+        wbytes = (uint32_t)(tile * sizeof(C)); vbytes = (uint32_t)(tile * sizeof(CV));
+        stage_bytes = wbytes + (uint32_t)k * vbytes;
+        ntiles = (int)(n / tile);
+        my = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        cs = 0; cpar = 0; pi = 0; ps = 0;
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < stages; ++s) ptx::mbarrier_init(&full[s], 1);
+            ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+            ptx::fence_proxy_async(ptx::space_shared);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            while (pi < my && pi < stages) issue_next();
+    }
+    // wait for the next tile of this CTA; returns its stage
+    __device__ __forceinline__ int wait() const {
+        while (!ptx::mbarrier_try_wait_parity(&full[cs], cpar)) {}
+        return cs;
+    }
+    // every thread is done with the current stage: refill it with the next tile not yet requested
+    __device__ __forceinline__ void release() {
+        __syncthreads();
+        if (threadIdx.x == 0 && pi < my) issue_next();
+        if (++cs == stages) { cs = 0; cpar ^= 1u; }
+    }
+};
+
+template <typename CV, typename C>
+__global__ void __launch_bounds__(kStreamThreads, 1) stream_dot_kernel(int64_t n, int k, const CV* __restrict__ V,
+        int64_t ldv, const C* __restrict__ w, int tile, int stages, double* out, double* partials, unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char stream_smem[];
+    __shared__ uint64_t bars[kMaxStages];
+    StreamPipe<CV, C> p;
+    p.init(stream_smem, bars, n, k, tile, stages, V, ldv, w);
+    double acc[2 * kMB];
+#pragma unroll
+    for (int q = 0; q < 2 * kMB; ++q) acc[q] = 0.0;
+    for (int i = 0; i < p.my; ++i) {
+        const int s = p.wait();
+        const C* ws = p.w_tile(s);
+        const CV* vs = p.v_tile(s, 0);
+        for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+            const double2 b = to_d(ws[e]);
+#pragma unroll
+            for (int q = 0; q < kMB; ++q)
+                if (q < k) dot_acc(acc[2 * q], acc[2 * q + 1], to_d(vs[q * tile + e]), b);
+        }
+        p.release();
+    }
+    // ragged tail (< tile elements) straight from global memory, spread over the CTAs
+    for (int64_t e = (int64_t)p.ntiles * tile + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        const double2 b = to_d(w[e]);
+#pragma unroll
+        for (int q = 0; q < kMB; ++q)
+            if (q < k) dot_acc(acc[2 * q], acc[2 * q + 1], to_d(V[(int64_t)q * ldv + e]), b);
+    }
+    reduce_finalize<2 * kMB>(acc, partials, counter, out);
+}
+
+template <typename CV, typename C, bool NORM>
+__global__ void __launch_bounds__(kStreamThreads, 1) stream_axpy_kernel(int64_t n, int k, const CV* __restrict__ V,
+        int64_t ldv, C* __restrict__ w, const double2* coef, double sign, int tile, int stages, double* out,
+        double* partials, unsigned int* counter) {
+    extern __shared__ __align__(128) unsigned char stream_smem[];
+    __shared__ uint64_t bars[kMaxStages];
+    StreamPipe<CV, C> p;
+    p.init(stream_smem, bars, n, k, tile, stages, V, ldv, w);
+    C h[kMB];
+#pragma unroll
+    for (int q = 0; q < kMB; ++q) h[q] = q < k ? from_d<C>(cscale(sign, coef[q])) : czero<C>();
+    double acc[1] = {0.0};
+    for (int i = 0; i < p.my; ++i) {
+        const int s = p.wait();
+        const C* ws = p.w_tile(s);
+        const CV* vs = p.v_tile(s, 0);
+        C* wg = w + p.tile_elem0(i);
+        for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+            C r = ws[e];
+#pragma unroll
+            for (int q = 0; q < kMB; ++q)
+                if (q < k) r = cfma4(h[q], cvt<C>(vs[q * tile + e]), r);
+            wg[e] = r;
+            if (NORM) acc[0] += (double)r.x * (double)r.x + (double)r.y * (double)r.y;
+        }
+        p.release();
+    }
+    for (int64_t e = (int64_t)p.ntiles * tile + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n;
+         e += (int64_t)gridDim.x * blockDim.x) {
+        C r = w[e];
+#pragma unroll
+        for (int q = 0; q < kMB; ++q)
+            if (q < k) r = cfma4(h[q], cvt<C>(V[(int64_t)q * ldv + e]), r);
+        w[e] = r;
+        if (NORM) acc[0] += (double)r.x * (double)r.x + (double)r.y * (double)r.y;
+    }
+    if (NORM) reduce_finalize<1>(acc, partials, counter, out);
+}
+
+// vectors long enough to fill every SM with several stages go through the staged kernels
+static inline bool use_stream(int64_t n, const void* V, int64_t ldv, size_t esz_v, const void* w) {
+    static const bool off = getenv("FDFD_NO_STREAM_BLAS") != nullptr;
+    return !off && n >= ((int64_t)1 << 20) && ((uintptr_t)V % 16 == 0) && ((uintptr_t)w % 16 == 0) &&
+           ((ldv * (int64_t)esz_v) % 16 == 0);
+}
+template <typename K>
+static int stream_attr(K kernel) {
+    FDFD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmem));
+    return FDFD_OK;
+}
+
+template <typename CV, typename C>
+int multi_dot(int64_t n, int k, const CV* V, int64_t ldv, const C* w, int s0, Scalars& sc,
               cudaStream_t stream) {
-    const int grid = stream_grid(n);
+    const bool pairs = pair_ok(V, ldv, w);
+    const bool staged = use_stream(n, V, ldv, sizeof(CV), w);
+    if (staged) FDFD_TRY(stream_attr(stream_dot_kernel<CV, C>));
+    const int grid = stream_grid(pairs ? (n + 1) / 2 : n);
     for (int base = 0; base < k; base += kMB) {
         const int kk = (k - base) < kMB ? (k - base) : kMB;
         // the kernel writes 2*kMB doubles; keep them inside the slot array
         FDFD_CHECK_ARG(s0 + base + kMB <= Scalars::kSlots, "multi_dot: slot range");
-        multi_dot_kernel<C><<<grid, kThreads, 0, stream>>>(n, kk, V + (int64_t)base * ldv, ldv, w,
-                (double*)(sc.slot + s0 + base), sc.partials, sc.counter);
+        if (staged) {
+            const StreamPlan pl = stream_plan<CV, C>(kk);
+            stream_dot_kernel<CV, C><<<pl.grid, pl.threads, pl.smem, stream>>>(n, kk, V + (int64_t)base * ldv, ldv, w,
+                    pl.tile, pl.stages, (double*)(sc.slot + s0 + base), sc.partials, sc.counter);
+        } else if (pairs)
+            multi_dot_kernel<CV, C, 2><<<grid, kThreads, 0, stream>>>(n, kk, V + (int64_t)base * ldv, ldv, w,
+                    (double*)(sc.slot + s0 + base), sc.partials, sc.counter);
+        else
+            multi_dot_kernel<CV, C, 1><<<grid, kThreads, 0, stream>>>(n, kk, V + (int64_t)base * ldv, ldv, w,
+                    (double*)(sc.slot + s0 + base), sc.partials, sc.counter);
     }
     FDFD_CUDA(cudaGetLastError());
     return FDFD_OK;
 }
 
-template <typename C, bool NORM>
-__global__ void __launch_bounds__(kThreads) multi_axpy_kernel(int64_t n, int k, const C* __restrict__ V,
+template <typename CV, typename C, bool NORM, int U>
+__global__ void __launch_bounds__(kThreads) multi_axpy_kernel(int64_t n, int k, const CV* __restrict__ V,
         int64_t ldv, C* __restrict__ w, const double2* coef, double sign, double* out,
         double* partials, unsigned int* counter) {
     C h[kMB];
@@ -261,56 +500,114 @@ __global__ void __launch_bounds__(kThreads) multi_axpy_kernel(int64_t n, int k, 
     for (int q = 0; q < kMB; ++q) h[q] = q < k ? from_d<C>(cscale(sign, coef[q])) : czero<C>();
     double acc[1] = {0.0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-        C r = w[i];
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (U == 2) {
+        const int64_t n2 = n >> 1;
+        for (int64_t i = tid; i < n2; i += stride) {
+            Pair<C> r = ld_pair(w, i);
 #pragma unroll
-        for (int q = 0; q < kMB; ++q)
-            if (q < k) r = cfma(h[q], V[(int64_t)q * ldv + i], r);
-        w[i] = r;
-        if (NORM) acc[0] += (double)r.x * (double)r.x + (double)r.y * (double)r.y;
+            for (int q = 0; q < kMB; ++q) {
+                if (q < k) {
+                    const Pair<CV> a = ld_pair(V + (int64_t)q * ldv, i);
+                    r.a = cfma4(h[q], cvt<C>(a.a), r.a);
+                    r.b = cfma4(h[q], cvt<C>(a.b), r.b);
+                }
+            }
+            st_pair(w, i, r.a, r.b);
+            if (NORM) acc[0] += (double)r.a.x * (double)r.a.x + (double)r.a.y * (double)r.a.y +
+                                (double)r.b.x * (double)r.b.x + (double)r.b.y * (double)r.b.y;
+        }
+        if ((n & 1) && tid == 0) {
+            C r = w[n - 1];
+#pragma unroll
+            for (int q = 0; q < kMB; ++q)
+                if (q < k) r = cfma4(h[q], cvt<C>(V[(int64_t)q * ldv + n - 1]), r);
+            w[n - 1] = r;
+            if (NORM) acc[0] += (double)r.x * (double)r.x + (double)r.y * (double)r.y;
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += stride) {
+            C r = w[i];
+#pragma unroll
+            for (int q = 0; q < kMB; ++q)
+                if (q < k) r = cfma4(h[q], cvt<C>(V[(int64_t)q * ldv + i]), r);
+            w[i] = r;
+            if (NORM) acc[0] += (double)r.x * (double)r.x + (double)r.y * (double)r.y;
+        }
     }
     if (NORM) reduce_finalize<1>(acc, partials, counter, out);
 }
 
 __global__ void zero_im_kernel(double2* slot) { slot->y = 0.0; }
 
-template <typename C>
-int multi_axpy(int64_t n, int k, const C* V, int64_t ldv, C* w, int s0, double sign,
+template <typename CV, typename C>
+int multi_axpy(int64_t n, int k, const CV* V, int64_t ldv, C* w, int s0, double sign,
                int nrm_slot, Scalars& sc, cudaStream_t stream) {
-    const int grid = stream_grid(n);
     if (k == 0 && nrm_slot >= 0) {
         const C* xs[1] = {w}; const C* ys[1] = {w};
         return dots<C>(n, 1, xs, ys, nrm_slot, sc, stream);
     }
+    const bool pairs = pair_ok(V, ldv, w);
+    const bool staged = use_stream(n, V, ldv, sizeof(CV), w);
+    if (staged) {
+        FDFD_TRY(stream_attr(stream_axpy_kernel<CV, C, true>));
+        FDFD_TRY(stream_attr(stream_axpy_kernel<CV, C, false>));
+    }
+    const int grid = stream_grid(pairs ? (n + 1) / 2 : n);
     for (int base = 0; base < k; base += kMB) {
         const int kk = (k - base) < kMB ? (k - base) : kMB;
         const bool last = base + kMB >= k;
-        if (last && nrm_slot >= 0) {
-            multi_axpy_kernel<C, true><<<grid, kThreads, 0, stream>>>(n, kk, V + (int64_t)base * ldv,
-                    ldv, w, sc.slot + s0 + base, sign, (double*)(sc.slot + nrm_slot), sc.partials, sc.counter);
+        const CV* Vb = V + (int64_t)base * ldv;
+        const double2* cf = sc.slot + s0 + base;
+        if (staged) {
+            const StreamPlan pl = stream_plan<CV, C>(kk);
+            const bool nrm = last && nrm_slot >= 0;
+            double* o = nrm ? (double*)(sc.slot + nrm_slot) : nullptr;
+            if (nrm) {
+                stream_axpy_kernel<CV, C, true><<<pl.grid, pl.threads, pl.smem, stream>>>(n, kk, Vb, ldv, w, cf, sign,
+                        pl.tile, pl.stages, o, sc.partials, sc.counter);
+                zero_im_kernel<<<1, 1, 0, stream>>>(sc.slot + nrm_slot);
+            } else {
+                stream_axpy_kernel<CV, C, false><<<pl.grid, pl.threads, pl.smem, stream>>>(n, kk, Vb, ldv, w, cf, sign,
+                        pl.tile, pl.stages, o, sc.partials, sc.counter);
+            }
+        } else if (last && nrm_slot >= 0) {
+            double* o = (double*)(sc.slot + nrm_slot);
+            if (pairs) multi_axpy_kernel<CV, C, true, 2><<<grid, kThreads, 0, stream>>>(n, kk, Vb, ldv, w, cf, sign, o, sc.partials, sc.counter);
+            else multi_axpy_kernel<CV, C, true, 1><<<grid, kThreads, 0, stream>>>(n, kk, Vb, ldv, w, cf, sign, o, sc.partials, sc.counter);
             zero_im_kernel<<<1, 1, 0, stream>>>(sc.slot + nrm_slot);
         } else {
-            multi_axpy_kernel<C, false><<<grid, kThreads, 0, stream>>>(n, kk, V + (int64_t)base * ldv,
-                    ldv, w, sc.slot + s0 + base, sign, nullptr, sc.partials, sc.counter);
+            if (pairs) multi_axpy_kernel<CV, C, false, 2><<<grid, kThreads, 0, stream>>>(n, kk, Vb, ldv, w, cf, sign, nullptr, sc.partials, sc.counter);
+            else multi_axpy_kernel<CV, C, false, 1><<<grid, kThreads, 0, stream>>>(n, kk, Vb, ldv, w, cf, sign, nullptr, sc.partials, sc.counter);
         }
     }
     FDFD_CUDA(cudaGetLastError());
     return FDFD_OK;
 }
 
-template <typename C>
+template <typename C, typename C2>
 __global__ void __launch_bounds__(kThreads) scale_inv_sqrt_kernel(int64_t n, C* __restrict__ out,
-        const C* __restrict__ x, const double2* nrm2) {
+        C2* __restrict__ out2, const C* __restrict__ x, const double2* nrm2) {
     using R = typename real_of<C>::type;
     const R s = (R)(1.0 / sqrt(nrm2->x));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = cscale(s, x[i]);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+        const C v = cscale(s, x[i]);
+        out[i] = v;
+        if (out2) out2[i] = cvt<C2>(v);
+    }
 }
 
 template <typename C>
 int scale_inv_sqrt(int64_t n, C* out, const C* x, int nrm2_slot, Scalars& sc, cudaStream_t stream) {
-    scale_inv_sqrt_kernel<C><<<stream_grid(n), kThreads, 0, stream>>>(n, out, x, sc.slot + nrm2_slot);
+    scale_inv_sqrt_kernel<C, C><<<stream_grid(n), kThreads, 0, stream>>>(n, out, (C*)nullptr, x, sc.slot + nrm2_slot);
+    FDFD_CUDA(cudaGetLastError());
+    return FDFD_OK;
+}
+
+int scale_inv_sqrt_dual(int64_t n, double2* out, float2* out_single, const double2* x, int nrm2_slot, Scalars& sc,
+                        cudaStream_t stream) {
+    scale_inv_sqrt_kernel<double2, float2><<<stream_grid(n), kThreads, 0, stream>>>(n, out, out_single, x, sc.slot + nrm2_slot);
     FDFD_CUDA(cudaGetLastError());
     return FDFD_OK;
 }
@@ -328,18 +625,25 @@ int pointwise_mul(int64_t n, C* out, const C* x, const C* d, cudaStream_t stream
     return FDFD_OK;
 }
 
-template <typename Cin, typename Cout>
+template <typename Cin, typename Cout, int U>
 __global__ void __launch_bounds__(kThreads) convert_kernel(int64_t n, const Cin* __restrict__ in, Cout* __restrict__ out) {
-    using R = typename real_of<Cout>::type;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
-        const Cin v = in[i];
-        out[i] = mk<Cout>((R)v.x, (R)v.y);
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (U == 2) {
+        const int64_t n2 = n >> 1;
+        for (int64_t i = tid; i < n2; i += stride) {
+            const Pair<Cin> v = ld_pair(in, i);
+            st_pair(out, i, cvt<Cout>(v.a), cvt<Cout>(v.b));
+        }
+        if ((n & 1) && tid == 0) out[n - 1] = cvt<Cout>(in[n - 1]);
+    } else {
+        for (int64_t i = tid; i < n; i += stride) out[i] = cvt<Cout>(in[i]);
     }
 }
 template <typename Cin, typename Cout>
 int convert(int64_t n, const Cin* in, Cout* out, cudaStream_t stream) {
-    convert_kernel<Cin, Cout><<<stream_grid(n), kThreads, 0, stream>>>(n, in, out);
+    if (pair_ok(in, 0, out)) convert_kernel<Cin, Cout, 2><<<stream_grid((n + 1) / 2), kThreads, 0, stream>>>(n, in, out);
+    else convert_kernel<Cin, Cout, 1><<<stream_grid(n), kThreads, 0, stream>>>(n, in, out);
     FDFD_CUDA(cudaGetLastError());
     return FDFD_OK;
 }
@@ -385,12 +689,15 @@ int scalar_op(int op, int a, int b, int c, int d, int e, double p, double q, Sca
     template int lincomb<C>(int64_t, C*, const double2*, const C*, const double2*, const C*,      \
                             const double2*, const C*, int, const C*, int, int, Scalars&, cudaStream_t); \
     template int dots<C>(int64_t, int, const C* const*, const C* const*, int, Scalars&, cudaStream_t); \
-    template int multi_dot<C>(int64_t, int, const C*, int64_t, const C*, int, Scalars&, cudaStream_t); \
-    template int multi_axpy<C>(int64_t, int, const C*, int64_t, C*, int, double, int, Scalars&, cudaStream_t); \
+    template int multi_dot<C, C>(int64_t, int, const C*, int64_t, const C*, int, Scalars&, cudaStream_t); \
+    template int multi_axpy<C, C>(int64_t, int, const C*, int64_t, C*, int, double, int, Scalars&, cudaStream_t); \
     template int scale_inv_sqrt<C>(int64_t, C*, const C*, int, Scalars&, cudaStream_t);                \
     template int pointwise_mul<C>(int64_t, C*, const C*, const C*, cudaStream_t);
 INST(double2)
 INST(float2)
 #undef INST
+// compressed Krylov basis: complex64 storage, complex128 arithmetic
+template int multi_dot<float2, double2>(int64_t, int, const float2*, int64_t, const double2*, int, Scalars&, cudaStream_t);
+template int multi_axpy<float2, double2>(int64_t, int, const float2*, int64_t, double2*, int, double, int, Scalars&, cudaStream_t);
 
 }  // namespace fdfd

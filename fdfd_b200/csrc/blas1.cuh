@@ -39,16 +39,21 @@ int dots(int64_t n, int ndots, const C* const* xs, const C* const* ys, int s0, S
 // Multi-vector kernels for (F)GMRES: V holds vectors of length n at stride ldv.
 //   multi_dot:  slot[s0 + i] = sum conj(V_i) * w , i < k
 //   multi_axpy: w += sign * sum_i slot[s0 + i] * V_i  ; optional ||w||^2 -> slot[nrm_slot]
-template <typename C>
-int multi_dot(int64_t n, int k, const C* V, int64_t ldv, const C* w, int s0, Scalars& sc,
+// The basis may be stored in lower precision than w (CV = float2, C = double2): arithmetic in C.
+template <typename CV, typename C>
+int multi_dot(int64_t n, int k, const CV* V, int64_t ldv, const C* w, int s0, Scalars& sc,
               cudaStream_t stream);
-template <typename C>
-int multi_axpy(int64_t n, int k, const C* V, int64_t ldv, C* w, int s0, double sign,
+template <typename CV, typename C>
+int multi_axpy(int64_t n, int k, const CV* V, int64_t ldv, C* w, int s0, double sign,
                int nrm_slot, Scalars& sc, cudaStream_t stream);
 
 // out = x * (1 / sqrt(re(slot[nrm2_slot])))        (normalise by a squared norm on device)
 template <typename C>
 int scale_inv_sqrt(int64_t n, C* out, const C* x, int nrm2_slot, Scalars& sc, cudaStream_t stream);
+
+// same, also writing a complex64 copy (compressed Krylov basis)
+int scale_inv_sqrt_dual(int64_t n, double2* out, float2* out_single, const double2* x, int nrm2_slot, Scalars& sc,
+                        cudaStream_t stream);
 
 // out = x .* d (elementwise complex product; Jacobi preconditioner with d = 1/diag(A))
 template <typename C>

@@ -10,6 +10,7 @@
 
 #include <cmath>
 #include <complex>
+#include <type_traits>
 #include <vector>
 
 namespace fdfd {
@@ -18,11 +19,20 @@ namespace {
 
 struct DeviceBuf {
     void* p = nullptr;
+    bool owned = true;
     int alloc(size_t bytes) {
         FDFD_CUDA(cudaMalloc(&p, bytes));
         return FDFD_OK;
     }
-    ~DeviceBuf() { if (p) cudaFree(p); }
+    // carve from a caller-owned arena (256-byte aligned) when one is given
+    int alloc(size_t bytes, KrylovArena* arena, size_t& cursor) {
+        if (!arena) return alloc(bytes);
+        p = (char*)arena->p + cursor;
+        owned = false;
+        cursor += (bytes + 255) & ~(size_t)255;
+        return FDFD_OK;
+    }
+    ~DeviceBuf() { if (p && owned) cudaFree(p); }
 };
 
 int read_slots(Scalars& sc, int s0, int count, double2* host, cudaStream_t stream) {
@@ -226,7 +236,7 @@ int bicgstab_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x
 // ------------------------------------------------------------------------------------------------
 template <typename C>
 int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, SolveInfo& info,
-             cudaStream_t stream) {
+             cudaStream_t stream, KrylovArena* arena) {
     using cd = std::complex<double>;
     const int64_t n = A.n_local();
     const size_t bytes = (size_t)n * sizeof(C);
@@ -240,12 +250,29 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
     // removes most of the stagnation that restarting causes on the indefinite Helmholtz operator
     int kaug = o.lgmres_k > 0 ? o.lgmres_k : 0;
     if (kaug > m / 2) kaug = m / 2;
-    DeviceBuf bV, bZ, bw, bE;
-    FDFD_TRY(bV.alloc(bytes * (m + 1)));
-    if (M || kaug) FDFD_TRY(bZ.alloc(bytes * m));
-    if (kaug) FDFD_TRY(bE.alloc(bytes * kaug));
-    FDFD_TRY(bw.alloc(bytes));
+    // Compressed basis: V is only read by the Gram-Schmidt kernels, which dominate the traffic of a
+    // restart cycle (2 (j+1) vectors per iteration).  Stored in complex64 (arithmetic stays complex128)
+    // it perturbs the Arnoldi relation by 6e-8 relative per cycle, far below the ~10x a cycle gains;
+    // the residual is recomputed in complex128 at every restart.  Z (the corrections) stays complex128.
+    constexpr bool kCanCompress = std::is_same<C, double2>::value;
+    const bool sb = kCanCompress && o.basis_single && M != nullptr;
+    DeviceBuf bV, bZ, bw, bE, bvc;
+    const size_t vbytes = (sb ? sizeof(float2) : sizeof(C)) * (size_t)n * (m + 1);
+    size_t cursor = 0;
+    if (arena) {
+        // basis / correction vectors of a restart cycle: tens of GB at 4096^2 and beyond; kept in the
+        // operator handle between solves (cudaMalloc / cudaFree of that much memory costs 0.1-0.8 s)
+        const size_t need = vbytes + bytes * ((sb ? 1 : 0) + ((M || kaug) ? m : 0) + kaug + 1) + 256 * 8;
+        FDFD_TRY(arena->ensure(need));
+    }
+    FDFD_TRY(bV.alloc(vbytes, arena, cursor));
+    if (sb) FDFD_TRY(bvc.alloc(bytes, arena, cursor));
+    if (M || kaug) FDFD_TRY(bZ.alloc(bytes * m, arena, cursor));
+    if (kaug) FDFD_TRY(bE.alloc(bytes * kaug, arena, cursor));
+    FDFD_TRY(bw.alloc(bytes, arena, cursor));
     C* V = (C*)bV.p;
+    float2* Vs = (float2*)bV.p;    // the same storage seen as the compressed basis
+    C* vcur = (C*)bvc.p;           // complex128 copy of the newest basis vector (input of M)
     C* Z = (M || kaug) ? (C*)bZ.p : V;
     C* E = (C*)bE.p;
     C* w = (C*)bw.p;
@@ -275,13 +302,16 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
         relres = beta / bnorm;
         if (!std::isfinite(beta)) { status = FDFD_ERR_BREAKDOWN; set_error("FGMRES: non-finite residual"); break; }
         if (relres <= o.rtol || it >= o.maxit) break;
-        FDFD_TRY(scale_inv_sqrt<C>(n, V, w, S_RR, sc, stream));
+        if constexpr (kCanCompress) {
+            if (sb) FDFD_TRY(scale_inv_sqrt_dual(n, vcur, Vs, w, S_RR, sc, stream));
+        }
+        if (!sb) FDFD_TRY(scale_inv_sqrt<C>(n, V, w, S_RR, sc, stream));
         std::fill(H.begin(), H.end(), cd(0));
         std::fill(g.begin(), g.end(), cd(0));
         g[0] = beta;
         int k = 0;
         for (int j = 0; j < m; ++j) {
-            C* vj = V + (int64_t)j * n;
+            C* vj = sb ? vcur : V + (int64_t)j * n;
             C* zj = Z + (int64_t)j * n;
             if (j >= m - naug) {
                 // augmented direction: a previous correction (oldest first)
@@ -296,10 +326,19 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
             // classical Gram-Schmidt with one re-orthogonalisation pass, fused multi-vector kernels
             const int passes = o.reorth ? 2 : 1;
             for (int pass = 0; pass < passes; ++pass) {
-                FDFD_TRY(multi_dot<C>(n, j + 1, V, n, w, S_H0, sc, stream));
-                FDFD_TRY(allreduce_slots(comm, sc, S_H0, j + 1, stream));
                 const bool last = pass == passes - 1;
-                FDFD_TRY(multi_axpy<C>(n, j + 1, V, n, w, S_H0, -1.0, last ? S_TMP0 : -1, sc, stream));
+                if constexpr (kCanCompress) {
+                    if (sb) {
+                        FDFD_TRY((multi_dot<float2, double2>(n, j + 1, Vs, n, w, S_H0, sc, stream)));
+                        FDFD_TRY(allreduce_slots(comm, sc, S_H0, j + 1, stream));
+                        FDFD_TRY((multi_axpy<float2, double2>(n, j + 1, Vs, n, w, S_H0, -1.0, last ? S_TMP0 : -1, sc, stream)));
+                    }
+                }
+                if (!sb) {
+                    FDFD_TRY(multi_dot<C>(n, j + 1, V, n, w, S_H0, sc, stream));
+                    FDFD_TRY(allreduce_slots(comm, sc, S_H0, j + 1, stream));
+                    FDFD_TRY(multi_axpy<C>(n, j + 1, V, n, w, S_H0, -1.0, last ? S_TMP0 : -1, sc, stream));
+                }
                 if (last) FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 1, stream));
                 FDFD_CUDA(cudaMemcpyAsync(hbuf.data(), sc.slot + S_H0, sizeof(double2) * (j + 1), cudaMemcpyDeviceToHost, stream));
                 if (last) FDFD_CUDA(cudaMemcpyAsync(hbuf.data() + j + 1, sc.slot + S_TMP0, sizeof(double2), cudaMemcpyDeviceToHost, stream));
@@ -308,8 +347,12 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
             }
             const double hn = std::sqrt(hbuf[j + 1].x);
             H[(size_t)(j + 1) * m + j] = hn;
-            if (j + 1 < m + 1 && hn > 0)
-                FDFD_TRY(scale_inv_sqrt<C>(n, V + (int64_t)(j + 1) * n, w, S_TMP0, sc, stream));
+            if (hn > 0) {
+                if constexpr (kCanCompress) {
+                    if (sb) FDFD_TRY(scale_inv_sqrt_dual(n, vcur, Vs + (int64_t)(j + 1) * n, w, S_TMP0, sc, stream));
+                }
+                if (!sb) FDFD_TRY(scale_inv_sqrt<C>(n, V + (int64_t)(j + 1) * n, w, S_TMP0, sc, stream));
+            }
             // Givens rotations on the new column
             for (int i = 0; i < j; ++i) {
                 const cd a = H[(size_t)i * m + j], bb = H[(size_t)(i + 1) * m + j];
@@ -404,10 +447,22 @@ int bicgstab_solve(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const void* 
     if (A.dtype == FDFD_C128) return bicgstab_t<double2>(A, M, o, (const double2*)b, (double2*)x, info, stream, ws, fixed_its);
     return bicgstab_t<float2>(A, M, o, (const float2*)b, (float2*)x, info, stream, ws, fixed_its);
 }
+int KrylovArena::ensure(size_t bytes) {
+    if (cap >= bytes) return FDFD_OK;
+    release();
+    FDFD_CUDA(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return FDFD_OK;
+}
+void KrylovArena::release() {
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+}
+
 int fgmres_solve(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
-                 SolveInfo& info, cudaStream_t stream) {
-    if (A.dtype == FDFD_C128) return fgmres_t<double2>(A, M, o, (const double2*)b, (double2*)x, info, stream);
-    return fgmres_t<float2>(A, M, o, (const float2*)b, (float2*)x, info, stream);
+                 SolveInfo& info, cudaStream_t stream, KrylovArena* arena) {
+    if (A.dtype == FDFD_C128) return fgmres_t<double2>(A, M, o, (const double2*)b, (double2*)x, info, stream, arena);
+    return fgmres_t<float2>(A, M, o, (const float2*)b, (float2*)x, info, stream, arena);
 }
 
 }  // namespace fdfd

@@ -65,7 +65,15 @@ struct BicgWorkspace {
 int bicgstab_solve(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
                    SolveInfo& info, cudaStream_t stream, BicgWorkspace* ws = nullptr,
                    bool fixed_its = false);
+// device memory of the (F)GMRES basis, reusable across solves with the same operator
+struct KrylovArena {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    ~KrylovArena() { release(); }
+};
 int fgmres_solve(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const void* b, void* x,
-                 SolveInfo& info, cudaStream_t stream);
+                 SolveInfo& info, cudaStream_t stream, KrylovArena* arena = nullptr);
 
 }  // namespace fdfd

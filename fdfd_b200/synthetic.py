@@ -86,7 +86,7 @@ def sharded_scattering_solve(Nx, Ny, pol="TE", comm=None, rank=0, world=1, devic
     qf = q.reshape(-1)
     b = qf * A.apply(s) - A.apply(qf * s)           # (Q A - A Q) src with two sharded stencil applies
     opts = dict(method="fgmres", precond="mg", rtol=1e-8, maxit=20000, restart=40 if pol.upper() == "TE" else 30,
-                mg_single=1,
+                mg_single=1, basis_single=1,
                 line_x_lo=pml, line_x_hi=pml, line_y_lo=pml, line_y_hi=pml)
     opts.update(solver or {})
     x, info = A.solve(b, raise_on_noconv=False, **opts)

@@ -175,3 +175,27 @@ def test_mixed_precision_preconditioner(pol):
     sim2.add_source("plane_wave", angle_deg=45.0)
     getattr(sim2, "solve_total_field_" + pol)()
     assert its_mixed <= 1.3 * sim2.solver_info[pol]["iterations"] + 3
+
+
+@pytest.mark.parametrize("pol", ["TE", "TM"])
+def test_compressed_krylov_basis(pol):
+    """FGMRES with the basis V stored in complex64 (arithmetic, corrections and residual in complex128):
+    same 1e-8 residual / 1e-6 field bars, iteration count within a few of the complex128 basis."""
+    import fdfd_b200
+    N = 192
+    f0 = 10e9
+    lam = 299792458 / f0
+    its = {}
+    for bs in (0, 1):
+        sim = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N)
+        sim.add_object(-1e6, 1.0, (sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
+        sim.add_UPML(pml_width=20, sigma_max=10)
+        sim.add_mask(40)
+        sim.add_source("plane_wave", angle_deg=45.0)
+        sim.solver_options.update(basis_single=bs, restart=10)      # several restart cycles at this size
+        F = getattr(sim, "solve_total_field_" + pol)()
+        its[bs] = sim.solver_info[pol]["iterations"]
+        assert sim.solver_info[pol]["relres"] <= 1e-8
+    ref = so.solve_total_field(so.cylinder_problem(N, eps_r=-1e6, pml_width=20, mask=40), pol)
+    assert np.linalg.norm(F - ref) <= 1e-6 * np.linalg.norm(ref)
+    assert its[1] <= 1.15 * its[0] + 3
