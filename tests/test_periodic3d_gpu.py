@@ -96,6 +96,13 @@ def test_periodic3d_cfg4_vs_reference():
     assert np.allclose(np.sort_complex(s.gammas), np.sort_complex(ref_g), rtol=1e-8, atol=0)
     assert np.all(s.refined_residuals <= max(1e-9, 10 * ref_res.max()))
     assert s.refined_restarts == 0
+    if os.path.exists(path):                        # decimated fields, each mode up to a phase
+        for fld in ("Ex", "Hy"):
+            dec, rdec = s.fields[fld][:, ::3, ::3, ::4], g[f"{fld}_dec"]
+            for m_ref in range(2):
+                m_got = int(np.argmin(np.abs(s.eigenvalues - ref_ev[m_ref])))
+                ph = np.vdot(rdec[m_ref], dec[m_got])
+                assert np.linalg.norm(dec[m_got] - ph / abs(ph) * rdec[m_ref]) <= 1e-5 * np.linalg.norm(rdec[m_ref])
 
 
 def test_periodic3d_refuses_oversized_dense_solve(tmp_path):
