@@ -41,7 +41,7 @@ class KrylovOpts(C.Structure):
         ("mg_cycle", C.c_int), ("mg_coarse_its", C.c_int), ("verbose", C.c_int),
         ("line_x_lo", C.c_int), ("line_x_hi", C.c_int), ("line_y_lo", C.c_int), ("line_y_hi", C.c_int),
         ("mg_wfrom", C.c_int), ("mg_min_n", C.c_int), ("reorth", C.c_int),
-        ("mg_coarse_mode", C.c_int), ("lgmres_k", C.c_int), ("mg_coarse_replicate", C.c_int), ("mg_single", C.c_int), ("mg_graph", C.c_int), ("mg_kh_max", C.c_double), ("basis_single", C.c_int),
+        ("mg_coarse_mode", C.c_int), ("lgmres_k", C.c_int), ("mg_coarse_replicate", C.c_int), ("mg_single", C.c_int), ("mg_graph", C.c_int), ("mg_kh_max", C.c_double), ("mg_fuse_len", C.c_int), ("basis_single", C.c_int),
     ]
 
 

@@ -242,6 +242,7 @@ extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
     o->lgmres_k = 0;
     o->restart = 30;
     o->mg_kh_max = 1.3;
+    o->mg_fuse_len = 1024;
     o->basis_single = 0;
     o->verbose = 0;
     o->line_x_lo = o->line_x_hi = o->line_y_lo = o->line_y_hi = 0;
@@ -256,7 +257,7 @@ static bool same_precond(const fdfd_krylov_opts& a, const fdfd_krylov_opts& b) {
            a.mg_cycle == b.mg_cycle && a.mg_coarse_its == b.mg_coarse_its && a.line_x_lo == b.line_x_lo &&
            a.line_x_hi == b.line_x_hi && a.line_y_lo == b.line_y_lo && a.line_y_hi == b.line_y_hi &&
            a.mg_wfrom == b.mg_wfrom && a.mg_min_n == b.mg_min_n && a.mg_coarse_mode == b.mg_coarse_mode &&
-           a.mg_coarse_replicate == b.mg_coarse_replicate && a.mg_single == b.mg_single && a.mg_graph == b.mg_graph && a.mg_kh_max == b.mg_kh_max;
+           a.mg_coarse_replicate == b.mg_coarse_replicate && a.mg_single == b.mg_single && a.mg_graph == b.mg_graph && a.mg_kh_max == b.mg_kh_max && a.mg_fuse_len == b.mg_fuse_len;
 }
 
 extern "C" int fdfd_helm2d_invalidate(fdfd_helm2d_t* h) {

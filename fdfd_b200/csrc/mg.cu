@@ -25,6 +25,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <utility>
 #include <vector>
@@ -392,6 +393,145 @@ __global__ void __launch_bounds__(256) strip_rows_scatter_kernel(LineView<C> v, 
     }
 }
 
+// Fused line relaxation for short, unsharded lines (coarse levels): one CTA per line does what the
+// five kernels above do for that line — (x-lines: residual of the strip row) -> chunk-local solves ->
+// interface mat-vec -> spike correction -> x += omega e — with the line staged in shared memory.
+// On the coarse levels every one of those kernels is a few microseconds of launch latency for a
+// handful of CTAs; a smoothing sweep drops from nine launches to three.
+constexpr int kFusedMaxLen = 1024;
+constexpr int kFusedThreads = 256;
+constexpr int kFusedRows = 2 * kMaxChunks / (kFusedThreads / 32);   // interface rows per warp (8)
+constexpr int kFusedPts = kFusedMaxLen / kFusedThreads;             // line points per thread (4)
+
+template <typename C, bool TM, int DIR>
+__global__ void __launch_bounds__(kFusedThreads) line_fused_kernel(LineView<C> v, C* x, const C* b,
+        const C* ca, const C* cb, const C* cd, typename real_of<C>::type sx, typename real_of<C>::type sy,
+        C shift, typename real_of<C>::type omega) {
+    // dynamic shared memory: the line (right-hand side, then solution) and its three factor arrays
+    extern __shared__ __align__(16) unsigned char fused_smem[];
+    __shared__ C sg[2 * kMaxChunks], su[2 * kMaxChunks];
+    const int l = blockIdx.x;
+    const int64_t nl = v.nl;
+    const int len = v.len;
+    C* sl = reinterpret_cast<C*>(fused_smem);
+    C* s_fl = sl + len; C* s_fc = s_fl + len; C* s_ip = s_fc + len;
+    const int fixed = l < v.lo ? l : (DIR == 0 ? v.Nx : v.Ny) - v.hi + (l - v.lo);   // column (DIR 0) / row (DIR 1)
+    const int n = 2 * v.Ptot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // everything the later (latency-bound) phases need is requested up front: the factor arrays go to
+    // shared memory, this warp's rows of the interface inverse and this thread's spike entries to registers
+    for (int t = threadIdx.x; t < len; t += kFusedThreads) {
+        s_fl[t] = v.fl[t * nl + l]; s_fc[t] = v.fc[t * nl + l]; s_ip[t] = v.fip[t * nl + l];
+    }
+    C rreg[kFusedRows][2], svr[kFusedPts], swr[kFusedPts];
+    if (v.Ptot > 1) {
+#pragma unroll
+        for (int r = 0; r < kFusedRows; ++r) {
+            const int row = warp + r * (kFusedThreads / 32);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int q = lane + 32 * c;
+                rreg[r][c] = (row < n && q < n) ? v.rinv[((int64_t)l * n + row) * n + q] : czero<C>();
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kFusedPts; ++q) {
+            const int t = threadIdx.x + q * kFusedThreads;
+            svr[q] = t < len ? v.sv[t * nl + l] : czero<C>();
+            swr[q] = t < len ? v.sw[t * nl + l] : czero<C>();
+        }
+    }
+    if (DIR == 0) {
+        for (int t = threadIdx.x; t < len; t += kFusedThreads) sl[t] = v.g[t * nl + l];   // written by the SMOOTH pass
+    } else {
+        const int j = fixed;
+        for (int i = threadIdx.x; i < len; i += kFusedThreads) {
+            PointCoefs<C> p = point_coefs<C, TM>(ca, cb, cd, v.Nx, v.Ny, sx, sy, shift, i, j);
+            const int64_t pn = (int64_t)j * v.Nx + i;
+            C ax = cmul(p.dg, x[pn]);
+            if (i > 0) ax = cfma(p.kw, x[pn - 1], ax);
+            if (i < v.Nx - 1) ax = cfma(p.ke, x[pn + 1], ax);
+            if (j > 0) ax = cfma(p.ks, x[pn - v.Nx], ax);
+            if (j < v.Ny - 1) ax = cfma(p.kn, x[pn + v.Nx], ax);
+            sl[i] = csub(b[pn], ax);
+        }
+    }
+    __syncthreads();
+    // chunk-local solves, one thread per chunk, operands in shared memory
+    if ((int)threadIdx.x < v.P) {
+        const int k = threadIdx.x;
+        const int t0 = k * v.m, t1 = min(len, t0 + v.m);
+        if (t0 < t1) {
+            C y = sl[t0];
+            for (int t = t0 + 1; t < t1; ++t) { y = csub(sl[t], cmul(s_fl[t], y)); sl[t] = y; }
+            C e = cmul(y, s_ip[t1 - 1]);
+            sl[t1 - 1] = e;
+            const C e_last = e;
+            for (int t = t1 - 2; t >= t0; --t) { e = cmul(csub(sl[t], cmul(s_fc[t], e)), s_ip[t]); sl[t] = e; }
+            sg[2 * k] = e; sg[2 * k + 1] = e_last;
+        }
+    }
+    __syncthreads();
+    if (v.Ptot > 1) {
+        // interface mat-vec u = R^-1 g: one warp per row, the row already sits in registers
+#pragma unroll
+        for (int r = 0; r < kFusedRows; ++r) {
+            const int row = warp + r * (kFusedThreads / 32);
+            double ax = 0.0, ay = 0.0;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int q = lane + 32 * c;
+                if (q < n) {
+                    const C rv = rreg[r][c], g = sg[q];
+                    ax += (double)rv.x * g.x - (double)rv.y * g.y;
+                    ay += (double)rv.x * g.y + (double)rv.y * g.x;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                ax += __shfl_down_sync(0xffffffffu, ax, off);
+                ay += __shfl_down_sync(0xffffffffu, ay, off);
+            }
+            if (lane == 0 && row < n) su[row] = mk<C>((typename real_of<C>::type)ax, (typename real_of<C>::type)ay);
+        }
+        __syncthreads();
+    }
+    // spike correction and update.  x-lines of one strip are adjacent rows whose residuals were read
+    // by the neighbouring CTAs above: their update goes through g and line_fused_apply_kernel, which
+    // keeps the Jacobi-between-lines semantics of the separate kernels; y-lines own whole columns of
+    // the SMOOTH pass output, which no other CTA reads here.
+#pragma unroll
+    for (int q = 0; q < kFusedPts; ++q) {
+        const int t = threadIdx.x + q * kFusedThreads;
+        if (t < len) {
+            C e = sl[t];
+            if (v.Ptot > 1) {
+                const int kg = t / v.m;
+                if (kg > 0) e = csub(e, cmul(svr[q], su[2 * (kg - 1) + 1]));
+                if (kg < v.Ptot - 1) e = csub(e, cmul(swr[q], su[2 * (kg + 1)]));
+            }
+            if (DIR == 0) {
+                const int64_t pn = (int64_t)t * v.Nx + fixed;
+                x[pn] = cadd(x[pn], cscale(omega, e));
+            } else {
+                v.g[t * nl + l] = e;
+            }
+        }
+    }
+}
+
+// x-lines, second phase: x[row(l)][i] += omega * e[i][l] once every line has been solved
+template <typename C>
+__global__ void __launch_bounds__(kFusedThreads) line_fused_apply_kernel(LineView<C> v, C* x,
+        typename real_of<C>::type omega) {
+    const int l = blockIdx.x;
+    const int j = l < v.lo ? l : v.Ny - v.hi + (l - v.lo);
+    for (int i = threadIdx.x; i < v.len; i += blockDim.x) {
+        const int64_t n = (int64_t)j * v.Nx + i;
+        x[n] = cadd(x[n], cscale(omega, v.g[(int64_t)i * v.nl + l]));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // grid transfer and coarse coefficients
 template <typename C, bool TM>
@@ -482,6 +622,7 @@ struct MGPrecond : Precond {
     cudaStream_t gstream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     cudaGraphExec_t graph = nullptr;
+    C* zero_buf = nullptr;     // all-zero vector of the coarsest level's size (initial guess of its smoother)
     C* in_buf = nullptr;       // fixed right-hand-side buffer of the captured cycle
     C* out_ptr = nullptr;      // where the captured cycle leaves its result (level-0 x after the swaps)
 
@@ -490,22 +631,21 @@ struct MGPrecond : Precond {
         MGPrecond* mg = nullptr;
         int level = 0;
         int apply(const void* v, void* z, cudaStream_t st) override {
+            // one sweep from a zero guess, written straight into z: the sweep reads lv.x (a buffer that
+            // stays zero: the kernels only write their output array) and leaves its result in lv.t
             Level<C>& lv = mg->L[level];
-            C* saved = lv.b;
-            lv.b = (C*)v;
-            const size_t bytes = (size_t)lv.op.n_local() * sizeof(C);
-            FDFD_CUDA(cudaMemsetAsync(lv.x, 0, bytes, st));
+            C *sb = lv.b, *sx = lv.x, *stt = lv.t;
+            lv.b = (C*)v; lv.x = mg->zero_buf; lv.t = (C*)z;
             int s = mg->smooth(level, st);
-            lv.b = saved;
-            FDFD_TRY(s);
-            FDFD_CUDA(cudaMemcpyAsync(z, lv.x, bytes, cudaMemcpyDeviceToDevice, st));
-            return FDFD_OK;
+            lv.b = sb; lv.x = sx; lv.t = stt;
+            return s;
         }
     } coarse_pre;
 
     ~MGPrecond() override {
         if (graph) cudaGraphExecDestroy(graph);
         cudaFree(in_buf);
+        cudaFree(zero_buf);
         if (gstream) cudaStreamDestroy(gstream);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
@@ -605,16 +745,47 @@ struct MGPrecond : Precond {
         HelmArgs<C> a = helm2d_args<C>(lv.op, lv.x, lv.t, lv.b, lv.ca, lv.cb, lv.cd, shift_re, shift_im, o.mg_omega);
         a.strip_lo = lv.ylines.lo; a.strip_hi = lv.ylines.hi; a.line_rhs = lv.ylines.g; a.row0 = 0;
         FDFD_TRY(helm2d_launch_args<C>(lv.op, APPLY_SMOOTH, a, st));
-        if (lv.ylines.nl) FDFD_TRY(line_solve(lv, lv.ylines, lv.t, o.mg_omega, st));
+        if (lv.ylines.nl) {
+            if (fused_ok(lv.ylines)) {
+                LineView<C> v = view(lv.ylines, lv.op.Nx, lv.op.Ny);
+                if (TM()) line_fused_kernel<C, true, 0><<<lv.ylines.nl, kFusedThreads, fused_smem(lv.ylines), st>>>(v, lv.t, lv.b, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), (R)o.mg_omega);
+                else line_fused_kernel<C, false, 0><<<lv.ylines.nl, kFusedThreads, fused_smem(lv.ylines), st>>>(v, lv.t, lv.b, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), (R)o.mg_omega);
+                FDFD_CUDA(cudaGetLastError());
+            } else {
+                FDFD_TRY(line_solve(lv, lv.ylines, lv.t, o.mg_omega, st));
+            }
+        }
         std::swap(lv.x, lv.t);
         if (lv.xlines.nl) {
             LineView<C> v = view(lv.xlines, lv.op.Nx, lv.op.Ny);
-            dim3 grid((lv.op.Nx + 31) / 32, (lv.xlines.nl + 31) / 32);
-            if (TM()) strip_rows_resid_kernel<C, true><<<grid, 256, 0, st>>>(v, lv.x, lv.b, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift());
-            else strip_rows_resid_kernel<C, false><<<grid, 256, 0, st>>>(v, lv.x, lv.b, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift());
-            FDFD_TRY(line_solve(lv, lv.xlines, lv.x, o.mg_omega, st));
+            if (fused_ok(lv.xlines)) {
+                if (TM()) line_fused_kernel<C, true, 1><<<lv.xlines.nl, kFusedThreads, fused_smem(lv.xlines), st>>>(v, lv.x, lv.b, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), (R)o.mg_omega);
+                else line_fused_kernel<C, false, 1><<<lv.xlines.nl, kFusedThreads, fused_smem(lv.xlines), st>>>(v, lv.x, lv.b, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), (R)o.mg_omega);
+                line_fused_apply_kernel<C><<<lv.xlines.nl, kFusedThreads, 0, st>>>(v, lv.x, (R)o.mg_omega);
+                FDFD_CUDA(cudaGetLastError());
+            } else {
+                dim3 grid((lv.op.Nx + 31) / 32, (lv.xlines.nl + 31) / 32);
+                if (TM()) strip_rows_resid_kernel<C, true><<<grid, 256, 0, st>>>(v, lv.x, lv.b, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift());
+                else strip_rows_resid_kernel<C, false><<<grid, 256, 0, st>>>(v, lv.x, lv.b, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift());
+                FDFD_TRY(line_solve(lv, lv.xlines, lv.x, o.mg_omega, st));
+            }
         }
         return FDFD_OK;
+    }
+
+    // short lines that live on one rank go through the fused one-CTA-per-line kernel
+    static size_t fused_smem(const LineSet<C>& s) { return (size_t)4 * s.len * sizeof(C); }
+    static int fused_attr() {
+        const int bytes = 4 * kFusedMaxLen * (int)sizeof(C);
+        FDFD_CUDA(cudaFuncSetAttribute(line_fused_kernel<C, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FDFD_CUDA(cudaFuncSetAttribute(line_fused_kernel<C, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FDFD_CUDA(cudaFuncSetAttribute(line_fused_kernel<C, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        FDFD_CUDA(cudaFuncSetAttribute(line_fused_kernel<C, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        return FDFD_OK;
+    }
+    bool fused_ok(const LineSet<C>& s) const {
+        static const bool off = getenv("FDFD_NO_FUSED_LINES") != nullptr;
+        return !off && s.nranks == 1 && s.len <= kFusedMaxLen && s.len <= o.mg_fuse_len && s.P <= kFusedThreads;
     }
 
     int cycle(int l, cudaStream_t st) {
@@ -728,6 +899,7 @@ struct MGPrecond : Precond {
         using R = typename real_of<C>::type;
         o = opts;
         shift_re = opts.mg_shift_re; shift_im = opts.mg_shift_im;
+        FDFD_TRY(fused_attr());
         const bool sharded = A.Ny != A.Ny_global;
         if (sharded) {
             FDFD_CHECK_ARG(A.comm && A.comm->nranks > 1, "sharded operator needs a communicator");
@@ -833,6 +1005,8 @@ struct MGPrecond : Precond {
             // the inner solver must not allocate inside the (captured) cycle
             const Level<C>& c = L.back();      // the replicated level when present (the larger one)
             FDFD_TRY(coarse_ws.ensure((size_t)c.op.n_local() * sizeof(C), true));
+            FDFD_CUDA(cudaMalloc(&zero_buf, (size_t)c.op.n_local() * sizeof(C)));
+            FDFD_CUDA(cudaMemsetAsync(zero_buf, 0, (size_t)c.op.n_local() * sizeof(C), st));
         }
         if (o.mg_graph) {
             FDFD_CUDA(cudaMalloc(&in_buf, (size_t)L[0].op.n_local() * sizeof(C)));

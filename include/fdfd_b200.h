@@ -142,6 +142,7 @@ typedef struct {
     int mg_single;    /* 1 = run the multigrid cycle in complex64 inside a complex128 solve (mixed precision) */
     int mg_graph;     /* 1 = replay the multigrid cycle as a captured CUDA graph (default)            */
     double mg_kh_max; /* stop coarsening once k*h = 1/sqrt(min(sx,sy)) of the next level exceeds this */
+    int mg_fuse_len;  /* levels whose relaxation lines are at most this long (and unsharded) use the fused one-CTA-per-line kernel */
     int basis_single; /* FGMRES (complex128, preconditioned): keep the Krylov basis V in complex64 (arithmetic and Z stay complex128) */
 } fdfd_krylov_opts;
 
