@@ -10,6 +10,7 @@ but never forms them: ``apply`` runs the sm_100a stencil kernel through the C-AB
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -62,6 +63,8 @@ class HelmholtzOperator2D:
                 self.bc[0], self.bc[1], ph, self.sx, self.sy, self.ca.data_ptr(), self.cb.data_ptr(),
                 None if self.cd is None else self.cd.data_ptr(),
                 None if comm is None else comm.handle, self._stream()))
+        if comm is not None:
+            comm._register(self)
 
     # -- helpers ------------------------------------------------------------------------------
     def _dev(self, a, shape):
@@ -93,6 +96,12 @@ class HelmholtzOperator2D:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._L.fdfd_helm2d_destroy(self._h)
             self._h = C.c_void_p()
+
+    def _release_comm_state(self):
+        """Called by `SlabComm.close()`: the cached preconditioner of a sharded operator holds a CUDA
+        graph with captured NCCL kernels, and ncclCommDestroy waits until every such graph is gone."""
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.fdfd_helm2d_invalidate(self._h)
 
     def __del__(self):
         try:
@@ -328,9 +337,21 @@ class SlabComm:
         self.handle = C.c_void_p()
         _lib.check(L.fdfd_comm_create(C.byref(self.handle), self.world_size, self.rank, ident))
         self._L = L
+        self._dependants = weakref.WeakSet()
+
+    def _register(self, op):
+        self._dependants.add(op)
 
     def close(self):
+        """Destroy the communicator.  Operators created with it drop their cached preconditioners
+        first: a captured multigrid cycle references the communicator (NCCL keeps a persistent
+        reference per captured graph) and ncclCommDestroy would otherwise wait for ever."""
         if self.handle and self.handle.value:
+            import torch
+            for op in list(self._dependants):
+                op._release_comm_state()
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
             self._L.fdfd_comm_destroy(self.handle)
             self.handle = C.c_void_p()
 

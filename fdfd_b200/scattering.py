@@ -177,6 +177,12 @@ class FDFD2DScatteringSolver:
                                                  comm=self.comm if self._rows is not None else None)
         return self._ops[pol]
 
+    def close(self):
+        """Release the device operators (and their cached preconditioners / Krylov memory)."""
+        for op in self._ops.values():
+            op.close()
+        self._ops = {}
+
     def _build_A_TE(self):
         return self.operator("TE")
 

@@ -208,6 +208,9 @@ int fdfd_precond_apply(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts, const voi
  * ------------------------------------------------------------------------------------------ */
 int fdfd_comm_unique_id(void* id128);
 int fdfd_comm_create(fdfd_comm_t** out, int nranks, int rank, const void* id128);
+/* Destroy (or fdfd_helm2d_invalidate) every sharded operator created with the communicator first: a
+ * cached multigrid preconditioner holds a CUDA graph with captured NCCL kernels, and NCCL does not
+ * release a communicator while such a graph exists (ncclCommDestroy would block). */
 void fdfd_comm_destroy(fdfd_comm_t*);
 
 #ifdef __cplusplus

@@ -107,6 +107,10 @@ def main():
         sim.add_mask(30)
         sim.add_source("plane_wave", angle_deg=45.0)
         fields.append(sim.solve_total_field_TM())
+        if c is None:
+            sim.close()
+        # the sharded solver stays open on purpose: comm.close() below must release its cached
+        # preconditioner (captured NCCL graph) before destroying the communicator
     err = np.linalg.norm(fields[1] - fields[0]) / np.linalg.norm(fields[0])
     if fields[1].shape != (N, N) or err > 1e-6:
         failures.append(f"sharded FDFD2DScatteringSolver: rel diff {err}")
