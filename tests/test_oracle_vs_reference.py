@@ -189,3 +189,26 @@ def test_periodic3d_host_logic_and_oracle(case):
                                                           max_restarts=kw["max_restarts"], seed=0)
     assert np.max(np.abs(vals - ref.eigenvalues)) <= 1e-9 * np.abs(ref.eigenvalues).max()
     assert rs == ref.refined_restarts and np.allclose(res, ref.refined_residuals, rtol=1e-6)
+
+
+@pytest.mark.parametrize("N,pw,direction", [(120, 20, "both"), (97, 11, "x"), (64, 9, "y"), (40, 20, "both")])
+def test_scattering_dropin_host_arrays_bitwise(N, pw, direction):
+    """Host side of the drop-in class (frame-only UPML scaling, broadcast grid, lazy identity mask) against
+    the unmodified reference class: material tensors and source bit-identical, including overlapping layers."""
+    import fdfd_b200
+    R = ref_loader.load("Scattering_Solver_2D").FDFD2DScatteringSolver
+    f0 = 10e9
+    lam = 299792458 / f0
+    args = (f0, N / 50 * lam, (N + 3) / 50 * lam, N, N + 3)
+    sim, ref = fdfd_b200.FDFD2DScatteringSolver(*args), R(*args)
+    for s in (sim, ref):
+        s.add_object([4.0 - 0.3j, 2.0, 3.0 + 1j], 1.5, (s.X ** 2 + s.Y ** 2) <= (0.5 * lam) ** 2)
+        s.add_UPML(pml_width=pw, sigma_max=10, direction=direction)
+        s.add_source("plane_wave", angle_deg=33.0)
+    for name in ("ERxx", "ERyy", "ERzz", "MRxx", "MRyy", "MRzz", "source"):
+        assert np.array_equal(getattr(sim, name), getattr(ref, name)), name
+    assert (sim.Q != ref.Q).nnz == 0
+    assert np.array_equal(sim.X, ref.X) and np.array_equal(sim.Y, ref.Y)
+    sim.add_mask(7)
+    ref.add_mask(7)
+    assert (sim.Q != ref.Q).nnz == 0
