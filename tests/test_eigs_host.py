@@ -1,0 +1,60 @@
+"""Host-runnable checks of the eigen-solver algebra that is written with torch tensor ops (the same
+code runs on the device in the product: batched Krylov-Schur of the Bloch sweep, folded
+block-tridiagonal direct solver of the 3-D pencil).  These run the torch code on CPU tensors; the
+parity tests proper are the GPU tests against the reference goldens."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+
+def test_krylov_schur_batched_matches_dense_eig():
+    import torch
+    from fdfd_b200 import eigs
+    rng = np.random.default_rng(0)
+    P, n, k = 6, 90, 4
+    mats = []
+    for p in range(P):
+        G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        mats.append(G @ G.conj().T / n + (0.01 + 0.02 * p) * np.eye(n))
+    inv = torch.from_numpy(np.stack([np.linalg.inv(M) for M in mats]))
+    state = {"inv": inv}
+
+    def set_active(idx):
+        state["inv"] = inv if idx is None else inv.index_select(0, idx)
+
+    def op(W):
+        return torch.bmm(state["inv"], W.unsqueeze(2)).squeeze(2)
+
+    mu, X, res, restarts = eigs.krylov_schur_batched(op, set_active, P, n, k, tol=1e-12, device="cpu")
+    assert restarts >= 1                      # the active set shrinks over several restart cycles
+    for p in range(P):
+        ref = np.sort(np.linalg.eigvalsh(mats[p]))[:k]
+        got = np.sort((1 / mu[p]).real)
+        assert np.max(np.abs(got - ref) / ref) <= 1e-10
+        x = X[p].numpy()
+        for i in range(k):
+            assert np.linalg.norm(mats[p] @ x[i] - (1 / mu[p][i]) * x[i]) <= 1e-9
+
+
+@pytest.mark.parametrize("Nz", [4, 5, 8])
+def test_plane_block_solver_algebra(Nz):
+    import torch
+    import fdfd_b200
+    from fdfd_b200 import eigs
+    s = fdfd_b200.PeriodicModeSolver3D(6, 5, Nz, 3e-3, 2.5e-3, 2e-3, 30e9, 1, sigma_guess=-200j, tol=1e-8, ncv=10)
+    s.add_block(4, 1, (1e-3, 2e-3), (0, 1e-3), (0, Nz), subpixels=2)
+    s.add_pec((0, 3e-3), (2e-3, 2.5e-3), (0, Nz))
+    A, B = s._build_eigen_matrices()
+    solver = eigs.PlaneBlockShiftedSolver(A.tocsr(), B.tocsr(), s.sigma_guess, s._unknown_planes(), s.Nz, "cpu", refine=False)
+    assert solver.ns == (Nz + 1) // 2
+    rng = np.random.default_rng(1)
+    b = rng.standard_normal(A.shape[0]) + 1j * rng.standard_normal(A.shape[0])
+    x = solver(torch.from_numpy(b)).numpy()
+    S = (A - s.sigma_guess * B).tocsc()
+    assert np.linalg.norm(S @ x - b) <= 1e-9 * np.linalg.norm(b)
+    assert np.linalg.norm(x - spla.splu(S).solve(b)) <= 1e-8 * np.linalg.norm(x)
+    with pytest.raises(ValueError):
+        eigs.PlaneBlockShiftedSolver(A.tocsr(), B.tocsr(), s.sigma_guess, (s._unknown_planes() * 2) % Nz, Nz, "cpu", refine=False)
