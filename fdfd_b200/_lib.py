@@ -50,6 +50,7 @@ _lib = None
 _PROTOTYPES = {
     "fdfd_last_error": (C.c_char_p, []),
     "fdfd_version": (C.c_int, []),
+    "fdfd_krylov_opts_size": (C.c_int, []),
     "fdfd_device_count": (C.c_int, []),
     "fdfd_yee2d_csr_nnz": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -44,6 +44,7 @@ struct fdfd_comm { Comm* c; };
 
 extern "C" const char* fdfd_last_error(void) { return g_err; }
 extern "C" int fdfd_version(void) { return 100; }
+extern "C" int fdfd_krylov_opts_size(void) { return (int)sizeof(fdfd_krylov_opts); }
 extern "C" int fdfd_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

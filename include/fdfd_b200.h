@@ -45,6 +45,8 @@ enum { FDFD_PRECOND_NONE = 0, FDFD_PRECOND_JACOBI = 1, FDFD_PRECOND_MG = 2 };
 
 const char* fdfd_last_error(void);
 int fdfd_version(void);
+/* sizeof(fdfd_krylov_opts) as compiled into the library: bindings check their struct against it */
+int fdfd_krylov_opts_size(void);
 /* number of visible CUDA devices (0 when none) — the Python layer refuses to run on 0. */
 int fdfd_device_count(void);
 

@@ -38,8 +38,18 @@ def test_opts_struct_layout(lib):
     from fdfd_b200 import _lib
     o = _lib.default_opts()
     assert o.rtol == 1e-8 and o.restart == 30 and o.lgmres_k == 0 and o.mg_shift_im == 0.4 and o.reorth == 0 and o.mg_graph == 1
-    # the C side zero-fills beyond the fields it knows; a size mismatch would corrupt the tail
-    assert C.sizeof(_lib.KrylovOpts) % 8 == 0
+    assert o.mg_single == 0 and o.basis_single == 0 and o.mg_fuse_len == 1024 and o.mg_kh_max == 1.3
+    # same size and the same field names in the same order as the C struct of the header
+    assert C.sizeof(_lib.KrylovOpts) == lib.fdfd_krylov_opts_size()
+    import re
+    hdr = open(os.path.join(ROOT, "include", "fdfd_b200.h")).read()
+    end = hdr.index("} fdfd_krylov_opts;")
+    body = hdr[hdr.rindex("typedef struct", 0, end):end]
+    body = body[body.index("{") + 1:]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [name.strip() for d in body.split(";") if d.strip()
+              for name in d.strip().split(None, 1)[1].split(",")]
+    assert fields == [f[0] for f in _lib.KrylovOpts._fields_]
 
 
 def test_nnz_and_argument_validation(lib):
