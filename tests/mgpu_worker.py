@@ -1,4 +1,4 @@
-"""Multi-rank worker (launched by torchrun from tests/test_multigpu.py): y-slab sharded operator
+"""Multi-rank worker (launched by torchrun from tests/test_zz_multigpu.py): y-slab sharded operator
 and Krylov solve must reproduce the single-domain result on every rank's slab."""
 import os
 import sys

@@ -1,4 +1,5 @@
-"""Multi-rank tests: world_size-2 gloo on CPU for the host-side sharding logic, and (gpu, needs
+"""(Named test_zz_* so that these multi-process tests run after the single-GPU parity tests.)
+Multi-rank tests: world_size-2 gloo on CPU for the host-side sharding logic, and (gpu, needs
 >= 2 devices) NCCL y-slab sharding of the operator and the Krylov solve against the single-domain
 result."""
 import os
