@@ -23,6 +23,8 @@
 #include "krylov.cuh"
 #include "comm.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -532,6 +534,8 @@ __global__ void __launch_bounds__(kFusedThreads) line_fused_apply_kernel(LineVie
     }
 }
 
+#include "mg_coarse.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // grid transfer and coarse coefficients
 template <typename C, bool TM>
@@ -646,6 +650,7 @@ struct MGPrecond : Precond {
         if (graph) cudaGraphExecDestroy(graph);
         cudaFree(in_buf);
         cudaFree(zero_buf);
+        cudaFree(coarse_partials);
         if (gstream) cudaStreamDestroy(gstream);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
@@ -788,11 +793,62 @@ struct MGPrecond : Precond {
         return !off && s.nranks == 1 && s.len <= kFusedMaxLen && s.len <= o.mg_fuse_len && s.P <= kFusedThreads;
     }
 
+    // ---- mg_coarse_mode = 2: the whole coarsest-level solve as one cooperative kernel (mg_coarse.cuh) ----
+    double* coarse_partials = nullptr;
+    int coarse_grid = 0;
+    bool coarse_persistent_ok(const Level<C>& lv) const {
+        if (o.mg_coarse_mode != 2) return false;
+        if (lv.op.Ny != lv.op.Ny_global) return false;                    // unsharded level only
+        if ((int64_t)lv.op.Nx * lv.op.Ny >= ((int64_t)1 << 31)) return false;
+        if (lv.ylines.nl && (lv.ylines.nranks != 1 || lv.ylines.len > kFusedMaxLen)) return false;
+        if (lv.xlines.nl && (lv.xlines.nranks != 1 || lv.xlines.len > kFusedMaxLen)) return false;
+        return true;
+    }
+    static size_t coarse_smem_bytes(const Level<C>& lv) {
+        const int len = std::max(lv.ylines.nl ? lv.ylines.len : 0, lv.xlines.nl ? lv.xlines.len : 0);
+        return (size_t)4 * len * sizeof(C);
+    }
+    int coarse_setup(const Level<C>& lv) {
+        const size_t smem = coarse_smem_bytes(lv);
+        auto kern = TM() ? coarse_bicgstab_kernel<C, true> : coarse_bicgstab_kernel<C, false>;
+        FDFD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, dev = 0, sms = 0;
+        FDFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCoarseThreads, smem));
+        FDFD_CUDA(cudaGetDevice(&dev));
+        FDFD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        FDFD_CHECK_ARG(per_sm >= 1, "persistent coarse solver does not fit on an SM");
+        const int64_t want = ((int64_t)lv.op.Nx * lv.op.Ny + kCoarseThreads - 1) / kCoarseThreads;
+        coarse_grid = (int)std::min<int64_t>((int64_t)per_sm * sms, want);
+        const int lines = std::max(lv.ylines.nl, lv.xlines.nl);
+        FDFD_CHECK_ARG(coarse_grid >= lines, "persistent coarse solver: more relaxation lines than resident CTAs");
+        FDFD_CUDA(cudaMalloc(&coarse_partials, (size_t)coarse_grid * 2 * kCoarseDots * sizeof(double)));
+        return FDFD_OK;
+    }
+    int coarse_persistent(Level<C>& lv, const C* b, C* x, cudaStream_t st) {
+        using R = typename real_of<C>::type;
+        CoarseArgs<C> a;
+        a.Nx = lv.op.Nx; a.Ny = lv.op.Ny;
+        a.ca = lv.ca; a.cb = lv.cb; a.cd = lv.cd;
+        a.sx = (R)lv.op.sx; a.sy = (R)lv.op.sy; a.omega = (R)o.mg_omega;
+        a.shift = shift();
+        a.its = coarse_its;
+        a.b = b; a.x = x;
+        a.r = (C*)coarse_ws.v[0]; a.rh = (C*)coarse_ws.v[1]; a.p = (C*)coarse_ws.v[2]; a.v = (C*)coarse_ws.v[3];
+        a.t = (C*)coarse_ws.v[4]; a.ph = (C*)coarse_ws.v[5]; a.sh = (C*)coarse_ws.v[6];
+        a.yl = view(lv.ylines, lv.op.Nx, lv.op.Ny);
+        a.xl = view(lv.xlines, lv.op.Nx, lv.op.Ny);
+        a.partials = coarse_partials;
+        void* args[] = {&a};
+        const void* kern = TM() ? (const void*)coarse_bicgstab_kernel<C, true> : (const void*)coarse_bicgstab_kernel<C, false>;
+        FDFD_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coarse_grid), dim3(kCoarseThreads), args, coarse_smem_bytes(lv), st));
+        return FDFD_OK;
+    }
+
     int cycle(int l, cudaStream_t st) {
         using R = typename real_of<C>::type;
         Level<C>& lv = L[l];
         const int last = nlev - 1;
-        if (l == last && rep >= 0 && o.mg_coarse_mode == 1) {
+        if (l == last && rep >= 0 && o.mg_coarse_mode >= 1) {
             // Sharded grid: the coarsest problem is latency bound (its kernels do not fill one GPU),
             // so every rank gathers the coarse right-hand side and solves the WHOLE coarse problem
             // redundantly with no communication inside, instead of ~90 latency-bound NCCL calls of a
@@ -800,28 +856,36 @@ struct MGPrecond : Precond {
             Level<C>& R = L[rep];
             const size_t loc = (size_t)lv.op.n_local() * sizeof(C);
             FDFD_TRY(comm_allgather(lv.op.comm, lv.b, R.b, loc, st));
-            FDFD_CUDA(cudaMemsetAsync(R.r, 0, (size_t)R.op.n_local() * sizeof(C), st));
-            fdfd_krylov_opts io = o;
-            io.maxit = coarse_its;
-            SolveInfo ii;
-            coarse_pre.mg = this; coarse_pre.level = rep;
-            HelmOp cop(R.op);
-            FDFD_TRY(bicgstab_solve(cop, &coarse_pre, io, R.b, R.r, ii, st, &coarse_ws, true));
+            if (coarse_persistent_ok(R)) {
+                FDFD_TRY(coarse_persistent(R, R.b, R.r, st));
+            } else {
+                FDFD_CUDA(cudaMemsetAsync(R.r, 0, (size_t)R.op.n_local() * sizeof(C), st));
+                fdfd_krylov_opts io = o;
+                io.maxit = coarse_its;
+                SolveInfo ii;
+                coarse_pre.mg = this; coarse_pre.level = rep;
+                HelmOp cop(R.op);
+                FDFD_TRY(bicgstab_solve(cop, &coarse_pre, io, R.b, R.r, ii, st, &coarse_ws, true));
+            }
             FDFD_CUDA(cudaMemcpyAsync(lv.x, R.r + (int64_t)lv.op.j0 * lv.op.Nx, loc, cudaMemcpyDeviceToDevice, st));
             return FDFD_OK;
         }
         if (l == last) {
-            if (o.mg_coarse_mode == 1) {
+            if (o.mg_coarse_mode >= 1) {
                 // coarse_its sync-free BiCGSTAB iterations on the shifted coarse operator; the
                 // solution lives in lv.r (the smoother ping-pongs lv.x / lv.t underneath)
                 const size_t bytes = (size_t)lv.op.n_local() * sizeof(C);
-                FDFD_CUDA(cudaMemcpyAsync(lv.r, lv.x, bytes, cudaMemcpyDeviceToDevice, st));
-                fdfd_krylov_opts io = o;
-                io.maxit = coarse_its;
-                SolveInfo ii;
-                coarse_pre.mg = this; coarse_pre.level = l;
-                HelmOp cop(lv.op);
-                FDFD_TRY(bicgstab_solve(cop, &coarse_pre, io, lv.b, lv.r, ii, st, &coarse_ws, true));
+                if (coarse_persistent_ok(lv)) {
+                    FDFD_TRY(coarse_persistent(lv, lv.b, lv.r, st));      // starts from a zero guess, as lv.x is here
+                } else {
+                    FDFD_CUDA(cudaMemcpyAsync(lv.r, lv.x, bytes, cudaMemcpyDeviceToDevice, st));
+                    fdfd_krylov_opts io = o;
+                    io.maxit = coarse_its;
+                    SolveInfo ii;
+                    coarse_pre.mg = this; coarse_pre.level = l;
+                    HelmOp cop(lv.op);
+                    FDFD_TRY(bicgstab_solve(cop, &coarse_pre, io, lv.b, lv.r, ii, st, &coarse_ws, true));
+                }
                 std::swap(lv.x, lv.r);
             } else {
                 for (int s = 0; s < coarse_its; ++s) FDFD_TRY(smooth(l, st));
@@ -960,7 +1024,7 @@ struct MGPrecond : Precond {
         // bandwidth bound and keep the distributed BiCGSTAB (16384^2: 2048^2 coarse grid).
         const int64_t coarse_pts = (int64_t)L.back().op.Nx * L.back().op.Ny_global;
         const bool replicate = opts.mg_coarse_replicate > 0 || (opts.mg_coarse_replicate < 0 && coarse_pts <= ((int64_t)1 << 20));
-        if (sharded && o.mg_coarse_mode == 1 && replicate) {
+        if (sharded && o.mg_coarse_mode >= 1 && replicate) {
             // replicated copy of the coarsest level: gather its coefficient slabs (equal slabs in rank
             // order -> the gathered arrays are the global arrays) and set it up as a single-rank level
             const Level<C> c = L.back();
@@ -1001,12 +1065,13 @@ struct MGPrecond : Precond {
                 fprintf(stderr, "[fdfd] multigrid: %d levels, coarsest %d x %d (k*h = %.3f), coarse mode %d its %d\n",
                         nlev, c.op.Nx, c.op.Ny_global, kh, o.mg_coarse_mode, coarse_its);
         }
-        if (o.mg_coarse_mode == 1) {
+        if (o.mg_coarse_mode >= 1) {
             // the inner solver must not allocate inside the (captured) cycle
             const Level<C>& c = L.back();      // the replicated level when present (the larger one)
             FDFD_TRY(coarse_ws.ensure((size_t)c.op.n_local() * sizeof(C), true));
             FDFD_CUDA(cudaMalloc(&zero_buf, (size_t)c.op.n_local() * sizeof(C)));
             FDFD_CUDA(cudaMemsetAsync(zero_buf, 0, (size_t)c.op.n_local() * sizeof(C), st));
+            if (coarse_persistent_ok(c)) FDFD_TRY(coarse_setup(c));
         }
         if (o.mg_graph) {
             FDFD_CUDA(cudaMalloc(&in_buf, (size_t)L[0].op.n_local() * sizeof(C)));

@@ -137,7 +137,8 @@ typedef struct {
     int mg_min_n;     /* stop coarsening when min(Nx, Ny) of the next level would drop below this */
     int reorth;       /* FGMRES: 1 = second Gram-Schmidt pass                                   */
     int mg_coarse_mode; /* coarsest level: 0 = mg_coarse_its smoothing sweeps, 1 = mg_coarse_its
-                         * iterations of BiCGSTAB preconditioned by one smoothing sweep              */
+                         * iterations of BiCGSTAB preconditioned by one smoothing sweep, 2 = the same
+                         * iterations inside one persistent cooperative kernel (experimental, opt-in) */
     int lgmres_k;     /* FGMRES: number of previous-cycle corrections that augment each restart cycle */
     int mg_coarse_replicate; /* sharded grids: 1 = every rank solves the whole coarsest level, 0 = distributed,
                               * -1 = automatic (replicate while the coarse grid has <= 2^20 points)        */

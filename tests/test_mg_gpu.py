@@ -3,6 +3,8 @@ oracle/mg_oracle.py: one preconditioner application z = M^-1 v must agree to rou
 every combination of polarisation type, number of levels, cycle shape and strip layout
 (this exercises coarsening, restriction, prolongation, the Jacobi/line smoother, the
 partitioned tridiagonal solver with 1, 8 and 32 chunks, and the W-cycle recursion)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -78,3 +80,24 @@ def test_precond_reduces_shifted_residual():
                         mg_shift_re=1.0, mg_shift_im=0.5)
     res = torch.linalg.vector_norm(v - Ms.apply(z)) / torch.linalg.vector_norm(v)
     assert res.item() < 0.5
+
+
+@pytest.mark.skipif(not os.environ.get("FDFD_TEST_EXPERIMENTAL"), reason="opt-in: experimental persistent coarse solver")
+@pytest.mark.parametrize("pol", ["TE", "TM"])
+@pytest.mark.parametrize("graph", [0, 1])
+def test_persistent_coarse_solver_matches_mode1(pol, graph):
+    """mg_coarse_mode=2 (one cooperative kernel for the coarsest-level BiCGSTAB) runs the same arithmetic as
+    mode 1 (separate kernels): the cycle output must agree to inner-product rounding.  Not part of the default
+    suite until the kernel has been validated on hardware (NOTES_r01.md)."""
+    import torch
+    import fdfd_b200
+    N = 256
+    ca, cb, cd, sx, sy = _problem(N, pol, eps=-1e6, pw=24)
+    A = fdfd_b200.HelmholtzOperator2D(pol, N, N, ca, cb, cd, sx, sy)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    v = torch.complex(torch.randn(N * N, generator=g, device="cuda", dtype=torch.float64),
+                      torch.randn(N * N, generator=g, device="cuda", dtype=torch.float64))
+    kw = dict(precond="mg", line_x_lo=24, line_x_hi=24, line_y_lo=24, line_y_hi=24, mg_graph=graph)
+    z1 = A.precond_apply(v, mg_coarse_mode=1, **kw)
+    z2 = A.precond_apply(v, mg_coarse_mode=2, **kw)
+    assert (torch.linalg.vector_norm(z2 - z1) / torch.linalg.vector_norm(z1)).item() <= 1e-7
