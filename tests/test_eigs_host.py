@@ -58,3 +58,45 @@ def test_plane_block_solver_algebra(Nz):
     assert np.linalg.norm(x - spla.splu(S).solve(b)) <= 1e-8 * np.linalg.norm(x)
     with pytest.raises(ValueError):
         eigs.PlaneBlockShiftedSolver(A.tocsr(), B.tocsr(), s.sigma_guess, (s._unknown_planes() * 2) % Nz, Nz, "cpu", refine=False)
+
+
+@pytest.mark.parametrize("pol", ["TE", "TM"])
+@pytest.mark.parametrize("shape,bc", [((10, 15), (1, 1)), ((8, 9), (1, 1)), ((7, 11), (1, 1)), ((12, 7), (0, 0)),
+                                      ((9, 10), (1, 0)), ((3, 4), (1, 1)), ((2, 5), (1, 1))])
+def test_probed_dense_assembly_matches_explicit_matrix(pol, shape, bc):
+    """Coloured probing of a five-point operator (BandDiagramSolver2D._dense_probed) against the explicit sparse
+    matrix of the same operator; the operator is a stub that applies the oracle's matrix to CPU tensors."""
+    import scipy.sparse as sp
+    import torch
+    import fdfd_b200
+    from oracle import yee_oracle
+    Nx, Ny = shape
+    rng = np.random.default_rng(Nx * 100 + Ny)
+    ca, cb, cd = (rng.uniform(0.5, 2, (Ny, Nx)) + 1j * rng.uniform(-1, 1, (Ny, Nx)) for _ in range(3))
+    kinc = rng.standard_normal(2)
+    DEX, DEY, DHX, DHY = yee_oracle.yeeder2d([Nx, Ny], [1.0, 1.0], list(bc), kinc)
+    a, b, d = sp.diags(ca.ravel()), sp.diags(cb.ravel()), sp.diags(cd.ravel())
+    M = ((DHX @ a @ DEX) + (DHY @ b @ DEY) + d if pol == "TE" else (DEX @ a @ DHX) + (DEY @ b @ DHY) + d).tocsr()
+
+    class StubOperator:
+        n, tdtype, device = Nx * Ny, torch.complex128, torch.device("cpu")
+        applies = 0
+
+        def apply(self, x, out=None):
+            StubOperator.applies += 1
+            y = torch.from_numpy(M @ x.numpy())
+            if out is None:
+                return y
+            out.copy_(y)
+            return out
+    op = StubOperator()
+    op.Nx, op.Ny, op.bc = Nx, Ny, bc
+    solver = fdfd_b200.BandDiagramSolver2D.__new__(fdfd_b200.BandDiagramSolver2D)
+    D = solver._dense_probed(op).numpy()
+    assert np.array_equal(D, M.toarray())
+    px = solver._probe_period(Nx, bc[0] == 1)
+    py = solver._probe_period(Ny, bc[1] == 1)
+    if px is not None and py is not None:
+        assert StubOperator.applies == px * py <= Nx * Ny
+    else:
+        assert StubOperator.applies == Nx * Ny          # too short to colour: one apply per column
