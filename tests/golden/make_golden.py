@@ -89,6 +89,21 @@ def scatter_cfg1():
     np.savez_compressed(os.path.join(HERE, "scatter_cfg1.npz"), **out)
 
 
+def scatter_1024():
+    """SURVEY.md §8c "scaled 1024^2" case (same script, L = N/50 lambda): probes, norm and a 32x-decimated
+    field of the reference's direct (SuperLU) solve, TM and TE.  ~2 min, ~6 GB."""
+    N = 1024
+    sim = _ref_sim(N, -1e6, 40, 80)
+    out = dict(N=N)
+    for pol in ("TM", "TE"):
+        F = getattr(sim, "solve_total_field_" + pol)()
+        out[f"probe_{pol}"] = F[512, 256]
+        out[f"max_{pol}"] = np.abs(F).max()
+        out[f"norm_{pol}"] = np.linalg.norm(F)
+        out[f"dec_{pol}"] = F[::32, ::32].copy()
+    np.savez_compressed(os.path.join(HERE, "scatter_1024.npz"), **out)
+
+
 def band_fixture():
     """BASELINE config 3 (example_square_lattice.py: a=1, 40x40, eps_bg=10.2, air hole r=0.4, 200-point
     Gamma-X-M-Gamma path, 5 bands) at path indices 0, 33, 59, 100, 117, 199, and the rectangular
@@ -239,6 +254,9 @@ def periodic3d_fixture():
 
 
 if __name__ == "__main__":
+    if "--scatter-1024" in sys.argv:
+        scatter_1024()
+        sys.exit(0)
     if "--p3d-cfg4" in sys.argv:
         periodic3d_cfg4_fixture()
         sys.exit(0)

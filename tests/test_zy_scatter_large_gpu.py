@@ -1,0 +1,29 @@
+"""(Runs late in the suite.)  Parity of the drop-in scattering solver at 1024^2 — SURVEY.md §8c "scaled 1024^2"
+case, the largest size whose reference (SuperLU) solution is cheap to regenerate — against
+tests/golden/scatter_1024.npz (made by tests/golden/make_golden.py --scatter-1024 from the unmodified
+reference).  Bars of BASELINE.json: residual <= 1e-8, field relative L2 error <= 1e-6 (complex128)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("pol", ["TM", "TE"])
+def test_scattering_1024_vs_reference(golden, pol):
+    import fdfd_b200
+    g = golden("scatter_1024.npz")
+    N = int(g["N"])
+    f0 = 10e9
+    lam = 299792458 / f0
+    sim = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N)
+    sim.add_object(-1e6, 1.0, (sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
+    sim.add_UPML(pml_width=40, sigma_max=10)
+    sim.add_mask(80)
+    sim.add_source("plane_wave", angle_deg=45.0, polarization="TE")
+    F = getattr(sim, "solve_total_field_" + pol)()
+    sim.close()
+    assert sim.solver_info[pol]["relres"] <= 1e-8
+    dec = g[f"dec_{pol}"]
+    assert np.linalg.norm(F[::32, ::32] - dec) <= 1e-6 * np.linalg.norm(dec)
+    assert abs(F[512, 256] - g[f"probe_{pol}"]) <= 1e-6 * g[f"max_{pol}"]
+    assert abs(np.linalg.norm(F) - g[f"norm_{pol}"]) <= 1e-6 * g[f"norm_{pol}"]
