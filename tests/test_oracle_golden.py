@@ -65,6 +65,16 @@ def test_scatter_cfg1_golden(golden):
     assert np.linalg.norm(Hz[::10, ::10] - g["dec_TM"]) <= 1e-11 * np.linalg.norm(g["dec_TM"])
 
 
+def test_scatter_1024_golden(golden):
+    """SURVEY.md §8c scaled 1024^2 case: the oracle's direct solve against the reference's field (TM)."""
+    g = golden("scatter_1024.npz")
+    p = so.cylinder_problem(1024)
+    Hz = so.solve_total_field(p, "TM")
+    assert abs(Hz[512, 256] - (-0.846661030394 - 0.831841310624j)) < 1e-10        # value recorded in the survey
+    assert abs(Hz[512, 256] - g["probe_TM"]) < 1e-11
+    assert np.linalg.norm(Hz[::32, ::32] - g["dec_TM"]) <= 1e-10 * np.linalg.norm(g["dec_TM"])
+
+
 def test_band_golden(golden):
     """Band oracle vs golden eigenvalues of the reference (config 3 at six path points)."""
     from oracle import band_oracle as bo
