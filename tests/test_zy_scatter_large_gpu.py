@@ -20,9 +20,12 @@ def test_scattering_1024_vs_reference(golden, pol):
     sim.add_UPML(pml_width=40, sigma_max=10)
     sim.add_mask(80)
     sim.add_source("plane_wave", angle_deg=45.0, polarization="TE")
+    # an iterative solve bounds the field error by ||A^-1|| ||b|| / ||x|| * relres = 3.0e2 * relres at this size
+    # (power iteration with the oracle's LU; 1.7e2 at 300^2): 2e-9 guarantees the 1e-6 field bar
+    sim.solver_options.update(rtol=2e-9)
     F = getattr(sim, "solve_total_field_" + pol)()
     sim.close()
-    assert sim.solver_info[pol]["relres"] <= 1e-8
+    assert sim.solver_info[pol]["relres"] <= 2e-9
     dec = g[f"dec_{pol}"]
     assert np.linalg.norm(F[::32, ::32] - dec) <= 1e-6 * np.linalg.norm(dec)
     assert abs(F[512, 256] - g[f"probe_{pol}"]) <= 1e-6 * g[f"max_{pol}"]
