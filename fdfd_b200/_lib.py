@@ -41,7 +41,7 @@ class KrylovOpts(C.Structure):
         ("mg_cycle", C.c_int), ("mg_coarse_its", C.c_int), ("verbose", C.c_int),
         ("line_x_lo", C.c_int), ("line_x_hi", C.c_int), ("line_y_lo", C.c_int), ("line_y_hi", C.c_int),
         ("mg_wfrom", C.c_int), ("mg_min_n", C.c_int), ("reorth", C.c_int),
-        ("mg_coarse_mode", C.c_int), ("lgmres_k", C.c_int), ("mg_coarse_replicate", C.c_int), ("mg_single", C.c_int), ("mg_graph", C.c_int), ("mg_kh_max", C.c_double), ("mg_fuse_len", C.c_int), ("basis_single", C.c_int),
+        ("mg_coarse_mode", C.c_int), ("mg_coarse_replicate", C.c_int), ("mg_single", C.c_int), ("mg_graph", C.c_int), ("mg_kh_max", C.c_double), ("mg_fuse_len", C.c_int), ("basis_single", C.c_int),
     ]
 
 
@@ -106,6 +106,9 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
+        if handle.fdfd_krylov_opts_size() != C.sizeof(KrylovOpts):
+            raise FdfdError(f"{LIB_PATH} was built from another include/fdfd_b200.h (fdfd_krylov_opts is "
+                            f"{handle.fdfd_krylov_opts_size()} bytes there, {C.sizeof(KrylovOpts)} here): rebuild it")
         _lib = handle
     return _lib
 

@@ -25,8 +25,6 @@ def _sources():
         p = os.path.join(CSRC, s)
         if os.path.exists(p):
             out.append(p)
-    if not os.path.exists(os.path.join(CSRC, "mg.cu")):
-        out.append(os.path.join(CSRC, "mg_stub.cu"))
     return out
 
 

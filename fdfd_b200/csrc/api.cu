@@ -103,10 +103,10 @@ extern "C" int fdfd_helm2d_create(fdfd_helm2d_t** out, int dtype, int pol, int N
 static void destroy_pipe(HostPipe* p);
 extern "C" void fdfd_helm2d_destroy(fdfd_helm2d_t* h) {
     if (!h) return;
-    cudaFree(h->op.halo_south); cudaFree(h->op.halo_north); cudaFree(h->op.cb_ghost_buf);
+    delete h->cached_M;          // first: a captured cycle may still reference the ghost buffers
+    helm2d_release_sharding(h->op);
     cudaFree(h->op.h_x); cudaFree(h->op.h_y);
     destroy_pipe(h->pipe);
-    delete h->cached_M;
     delete h;
 }
 
@@ -240,7 +240,6 @@ extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
     o->mg_graph = 1;
     o->mg_coarse_replicate = -1;
     o->mg_single = 0;
-    o->lgmres_k = 0;
     o->restart = 30;
     o->mg_kh_max = 1.3;
     o->mg_fuse_len = 1024;

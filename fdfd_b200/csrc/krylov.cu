@@ -234,10 +234,104 @@ int bicgstab_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x
 }
 
 // ------------------------------------------------------------------------------------------------
+// FGMRES.  The Hessenberg matrix, the Givens rotations and the rotated right-hand side live on the
+// device: one single-thread kernel per iteration folds the Gram-Schmidt coefficients into column j,
+// applies / generates the rotations and leaves |g_{j+1}|^2 (the squared residual estimate) in a small
+// result record, which is copied to pinned host memory asynchronously.  The host checks the record of
+// iteration j-1 only after iteration j has been enqueued, so the device never waits for the host; the
+// price is at most one iteration more than strictly needed.  The triangular solve for the update
+// coefficients is a one-warp kernel at the end of a restart cycle.
+struct GivensDev {
+    double2* H = nullptr;    // column j at H + j*(m+1), entries 0..j+1
+    double2* cs = nullptr;   // [m]
+    double2* sn = nullptr;   // [m]
+    double2* g = nullptr;    // [m+1]
+    double2* rec = nullptr;  // [m] per-iteration record: (|g_{j+1}|^2, h_{j+1,j}^2)
+};
+
+__global__ void fgmres_givens_kernel(int j, int m, int add, int finalize, const double2* __restrict__ hslots,
+                                     const double2* __restrict__ nrm2, const double2* __restrict__ rr, GivensDev G) {
+    double2* col = G.H + (size_t)j * (m + 1);
+    for (int i = 0; i <= j; ++i) {
+        const double2 h = hslots[i];
+        col[i] = add ? make_double2(col[i].x + h.x, col[i].y + h.y) : h;
+    }
+    if (!finalize) return;
+    const double hn2 = nrm2->x;
+    const double hn = sqrt(hn2 > 0.0 ? hn2 : 0.0);
+    if (j == 0) G.g[0] = make_double2(sqrt(rr->x), 0.0);
+    double2 a = col[0];
+    for (int i = 0; i < j; ++i) {
+        const double2 c = G.cs[i], s = G.sn[i], bb = col[i + 1];
+        col[i] = cadd(cmulc(c, a), cmulc(s, bb));       // conj(c) a + conj(s) b
+        a = csub(cmul(c, bb), cmul(s, a));              // -s a + c b
+    }
+    const double d = sqrt(a.x * a.x + a.y * a.y + hn * hn);
+    double2 c = make_double2(1.0, 0.0), s = make_double2(0.0, 0.0);
+    if (d > 0.0) { c = make_double2(a.x / d, a.y / d); s = make_double2(hn / d, 0.0); }
+    G.cs[j] = c; G.sn[j] = s;
+    col[j] = cadd(cmulc(c, a), cscale(hn, cconj(s)));
+    col[j + 1] = make_double2(0.0, 0.0);
+    const double2 gj = G.g[j];
+    G.g[j] = cmulc(c, gj);
+    const double2 gn = cneg(cmul(s, gj));
+    G.g[j + 1] = gn;
+    G.rec[j] = make_double2(gn.x * gn.x + gn.y * gn.y, hn2);
+}
+
+// y = R^-1 g for the leading k x k block (upper triangular after the rotations) -> slots[0..k)
+__global__ void __launch_bounds__(32) fgmres_ysolve_kernel(int k, int m, GivensDev G, double2* __restrict__ yslots) {
+    __shared__ double2 y[160];
+    const int lane = threadIdx.x;
+    for (int i = k - 1; i >= 0; --i) {
+        double sx = 0.0, sy = 0.0;
+        for (int q = i + 1 + lane; q < k; q += 32) {
+            const double2 h = G.H[(size_t)q * (m + 1) + i], v = y[q];
+            sx += h.x * v.x - h.y * v.y;
+            sy += h.x * v.y + h.y * v.x;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            sx += __shfl_down_sync(0xffffffffu, sx, off);
+            sy += __shfl_down_sync(0xffffffffu, sy, off);
+        }
+        if (lane == 0) {
+            const double2 gi = G.g[i], r = G.H[(size_t)i * (m + 1) + i];
+            const double2 num = make_double2(gi.x - sx, gi.y - sy);
+            const double dd = r.x * r.x + r.y * r.y;
+            y[i] = dd > 0.0 ? make_double2((num.x * r.x + num.y * r.y) / dd, (num.y * r.x - num.x * r.y) / dd)
+                            : make_double2(0.0, 0.0);
+        }
+        __syncwarp();
+    }
+    for (int i = lane; i < k; i += 32) yslots[i] = y[i];
+}
+
+struct FgmresHost {
+    GivensDev G;
+    double2* pinned = nullptr;           // [m] copies of the per-iteration records
+    std::vector<cudaEvent_t> ev;
+    int init(int m) {
+        FDFD_CUDA(cudaMalloc(&G.H, sizeof(double2) * (size_t)(m + 1) * m));
+        FDFD_CUDA(cudaMalloc(&G.cs, sizeof(double2) * m));
+        FDFD_CUDA(cudaMalloc(&G.sn, sizeof(double2) * m));
+        FDFD_CUDA(cudaMalloc(&G.g, sizeof(double2) * (m + 1)));
+        FDFD_CUDA(cudaMalloc(&G.rec, sizeof(double2) * m));
+        FDFD_CUDA(cudaMallocHost(&pinned, sizeof(double2) * m));
+        ev.resize(m, nullptr);
+        for (auto& e : ev) FDFD_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return FDFD_OK;
+    }
+    ~FgmresHost() {
+        cudaFree(G.H); cudaFree(G.cs); cudaFree(G.sn); cudaFree(G.g); cudaFree(G.rec);
+        if (pinned) cudaFreeHost(pinned);
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+    }
+};
+
 template <typename C>
 int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, SolveInfo& info,
              cudaStream_t stream, KrylovArena* arena) {
-    using cd = std::complex<double>;
     const int64_t n = A.n_local();
     const size_t bytes = (size_t)n * sizeof(C);
     int m = o.restart > 0 ? o.restart : 30;
@@ -245,41 +339,34 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
     Scalars sc;
     ScalarsGuard guard{sc};
     FDFD_TRY(sc.alloc());
-    // LGMRES-style augmentation: the last `kaug` slots of every cycle are filled with the
-    // (normalised) corrections of the previous cycles instead of new Krylov directions; this
-    // removes most of the stagnation that restarting causes on the indefinite Helmholtz operator
-    int kaug = o.lgmres_k > 0 ? o.lgmres_k : 0;
-    if (kaug > m / 2) kaug = m / 2;
+    FgmresHost hs;
+    FDFD_TRY(hs.init(m));
     // Compressed basis: V is only read by the Gram-Schmidt kernels, which dominate the traffic of a
     // restart cycle (2 (j+1) vectors per iteration).  Stored in complex64 (arithmetic stays complex128)
     // it perturbs the Arnoldi relation by 6e-8 relative per cycle, far below the ~10x a cycle gains;
     // the residual is recomputed in complex128 at every restart.  Z (the corrections) stays complex128.
     constexpr bool kCanCompress = std::is_same<C, double2>::value;
     const bool sb = kCanCompress && o.basis_single && M != nullptr;
-    DeviceBuf bV, bZ, bw, bE, bvc;
+    DeviceBuf bV, bZ, bw, bvc;
     const size_t vbytes = (sb ? sizeof(float2) : sizeof(C)) * (size_t)n * (m + 1);
     size_t cursor = 0;
     if (arena) {
         // basis / correction vectors of a restart cycle: tens of GB at 4096^2 and beyond; kept in the
         // operator handle between solves (cudaMalloc / cudaFree of that much memory costs 0.1-0.8 s)
-        const size_t need = vbytes + bytes * ((sb ? 1 : 0) + ((M || kaug) ? m : 0) + kaug + 1) + 256 * 8;
+        const size_t need = vbytes + bytes * ((sb ? 1 : 0) + (M ? m : 0) + 1) + 256 * 8;
         FDFD_TRY(arena->ensure(need));
     }
     FDFD_TRY(bV.alloc(vbytes, arena, cursor));
     if (sb) FDFD_TRY(bvc.alloc(bytes, arena, cursor));
-    if (M || kaug) FDFD_TRY(bZ.alloc(bytes * m, arena, cursor));
-    if (kaug) FDFD_TRY(bE.alloc(bytes * kaug, arena, cursor));
+    if (M) FDFD_TRY(bZ.alloc(bytes * m, arena, cursor));
     FDFD_TRY(bw.alloc(bytes, arena, cursor));
     C* V = (C*)bV.p;
     float2* Vs = (float2*)bV.p;    // the same storage seen as the compressed basis
     C* vcur = (C*)bvc.p;           // complex128 copy of the newest basis vector (input of M)
-    C* Z = (M || kaug) ? (C*)bZ.p : V;
-    C* E = (C*)bE.p;
+    C* Z = M ? (C*)bZ.p : V;
     C* w = (C*)bw.p;
-    int naug = 0, aug_next = 0;
     Comm* comm = A.comm;
-    std::vector<double2> hbuf(m + 8);
-    std::vector<cd> H((size_t)(m + 1) * m), g(m + 1), cs(m), sn(m), y(m);
+    double2 hbuf[2];
     int status = FDFD_OK;
     int it = 0;
     double bnorm2 = 0, relres = 1.0;
@@ -287,17 +374,64 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
         const C* xs[1] = {b}; const C* ys[1] = {b};
         FDFD_TRY(dots<C>(n, 1, xs, ys, S_BB, sc, stream));
         FDFD_TRY(allreduce_slots(comm, sc, S_BB, 1, stream));
-        FDFD_TRY(read_slots(sc, S_BB, 1, hbuf.data(), stream));
+        FDFD_TRY(read_slots(sc, S_BB, 1, hbuf, stream));
         bnorm2 = hbuf[0].x > 0 ? hbuf[0].x : 1.0;
     }
     const double bnorm = std::sqrt(bnorm2);
+    const int passes = o.reorth ? 2 : 1;
+
+    // one Arnoldi step, fully asynchronous
+    auto enqueue = [&](int j) -> int {
+        C* vj = sb ? vcur : V + (int64_t)j * n;
+        C* zj = Z + (int64_t)j * n;
+        if (M) { FDFD_TRY(M->apply(vj, zj, stream)); ++info.precond_applies; }
+        FDFD_TRY(A.apply(zj, w, stream)); ++info.op_applies;
+        // classical Gram-Schmidt (optionally a second pass), fused multi-vector kernels
+        for (int pass = 0; pass < passes; ++pass) {
+            const bool last = pass == passes - 1;
+            if constexpr (kCanCompress) {
+                if (sb) {
+                    FDFD_TRY((multi_dot<float2, double2>(n, j + 1, Vs, n, w, S_H0, sc, stream)));
+                    FDFD_TRY(allreduce_slots(comm, sc, S_H0, j + 1, stream));
+                    FDFD_TRY((multi_axpy<float2, double2>(n, j + 1, Vs, n, w, S_H0, -1.0, last ? S_TMP0 : -1, sc, stream)));
+                }
+            }
+            if (!sb) {
+                FDFD_TRY(multi_dot<C>(n, j + 1, V, n, w, S_H0, sc, stream));
+                FDFD_TRY(allreduce_slots(comm, sc, S_H0, j + 1, stream));
+                FDFD_TRY(multi_axpy<C>(n, j + 1, V, n, w, S_H0, -1.0, last ? S_TMP0 : -1, sc, stream));
+            }
+            if (last) FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 1, stream));
+            fgmres_givens_kernel<<<1, 1, 0, stream>>>(j, m, pass > 0, last, sc.slot + S_H0, sc.slot + S_TMP0,
+                                                       sc.slot + S_RR, hs.G);
+        }
+        FDFD_CUDA(cudaMemcpyAsync(hs.pinned + j, hs.G.rec + j, sizeof(double2), cudaMemcpyDeviceToHost, stream));
+        FDFD_CUDA(cudaEventRecord(hs.ev[j], stream));
+        // next basis vector (a zero norm gives a non-finite vector: that step is discarded by the host)
+        if constexpr (kCanCompress) {
+            if (sb) FDFD_TRY(scale_inv_sqrt_dual(n, vcur, Vs + (int64_t)(j + 1) * n, w, S_TMP0, sc, stream));
+        }
+        if (!sb) FDFD_TRY(scale_inv_sqrt<C>(n, V + (int64_t)(j + 1) * n, w, S_TMP0, sc, stream));
+        return FDFD_OK;
+    };
+    // outcome of step j once its record has arrived: 0 = continue, 1 = converged, 2 = exact breakdown
+    // (h_{j+1,j} = 0: the Krylov space is invariant, the step itself is valid), -1 = non-finite
+    auto outcome = [&](int j, double& rel) -> int {
+        if (cudaEventSynchronize(hs.ev[j]) != cudaSuccess) return -1;
+        const double g2 = hs.pinned[j].x, hn2 = hs.pinned[j].y;
+        if (!std::isfinite(g2) || !std::isfinite(hn2)) return -1;
+        rel = std::sqrt(g2) / bnorm;
+        if (!(hn2 > 0.0)) return 2;
+        return rel <= o.rtol ? 1 : 0;
+    };
+
     bool done = false;
     while (!done) {
         // r = b - A x -> V0 (normalised)
         FDFD_TRY(A.residual(x, w, b, stream)); ++info.op_applies;
         { const C* xs[1] = {w}; const C* ys[1] = {w}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_RR, sc, stream)); }
         FDFD_TRY(allreduce_slots(comm, sc, S_RR, 1, stream));
-        FDFD_TRY(read_slots(sc, S_RR, 1, hbuf.data(), stream));
+        FDFD_TRY(read_slots(sc, S_RR, 1, hbuf, stream));
         const double beta = std::sqrt(hbuf[0].x);
         relres = beta / bnorm;
         if (!std::isfinite(beta)) { status = FDFD_ERR_BREAKDOWN; set_error("FGMRES: non-finite residual"); break; }
@@ -306,106 +440,47 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
             if (sb) FDFD_TRY(scale_inv_sqrt_dual(n, vcur, Vs, w, S_RR, sc, stream));
         }
         if (!sb) FDFD_TRY(scale_inv_sqrt<C>(n, V, w, S_RR, sc, stream));
-        std::fill(H.begin(), H.end(), cd(0));
-        std::fill(g.begin(), g.end(), cd(0));
-        g[0] = beta;
-        int k = 0;
-        for (int j = 0; j < m; ++j) {
-            C* vj = sb ? vcur : V + (int64_t)j * n;
-            C* zj = Z + (int64_t)j * n;
-            if (j >= m - naug) {
-                // augmented direction: a previous correction (oldest first)
-                const int q = (aug_next + kaug - naug + (j - (m - naug))) % kaug;
-                FDFD_CUDA(cudaMemcpyAsync(zj, E + (int64_t)q * n, bytes, cudaMemcpyDeviceToDevice, stream));
-            } else if (M) {
-                FDFD_TRY(M->apply(vj, zj, stream)); ++info.precond_applies;
-            } else if (kaug) {
-                FDFD_CUDA(cudaMemcpyAsync(zj, vj, bytes, cudaMemcpyDeviceToDevice, stream));
+        int k = 0;            // valid columns of this cycle
+        int enq = 0;          // steps enqueued in this cycle
+        int why = 0;          // outcome that ended the cycle
+        // consume the record of step j; false = the cycle ends here
+        auto examine = [&](int j) -> bool {
+            double rel = relres;
+            why = outcome(j, rel);
+            if (why < 0) {
+                if (k == 0) { status = FDFD_ERR_BREAKDOWN; set_error("FGMRES: non-finite Hessenberg entry"); }
+                return false;                 // keep the k valid columns found so far
             }
-            FDFD_TRY(A.apply(zj, w, stream)); ++info.op_applies;
-            // classical Gram-Schmidt with one re-orthogonalisation pass, fused multi-vector kernels
-            const int passes = o.reorth ? 2 : 1;
-            for (int pass = 0; pass < passes; ++pass) {
-                const bool last = pass == passes - 1;
-                if constexpr (kCanCompress) {
-                    if (sb) {
-                        FDFD_TRY((multi_dot<float2, double2>(n, j + 1, Vs, n, w, S_H0, sc, stream)));
-                        FDFD_TRY(allreduce_slots(comm, sc, S_H0, j + 1, stream));
-                        FDFD_TRY((multi_axpy<float2, double2>(n, j + 1, Vs, n, w, S_H0, -1.0, last ? S_TMP0 : -1, sc, stream)));
-                    }
-                }
-                if (!sb) {
-                    FDFD_TRY(multi_dot<C>(n, j + 1, V, n, w, S_H0, sc, stream));
-                    FDFD_TRY(allreduce_slots(comm, sc, S_H0, j + 1, stream));
-                    FDFD_TRY(multi_axpy<C>(n, j + 1, V, n, w, S_H0, -1.0, last ? S_TMP0 : -1, sc, stream));
-                }
-                if (last) FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 1, stream));
-                FDFD_CUDA(cudaMemcpyAsync(hbuf.data(), sc.slot + S_H0, sizeof(double2) * (j + 1), cudaMemcpyDeviceToHost, stream));
-                if (last) FDFD_CUDA(cudaMemcpyAsync(hbuf.data() + j + 1, sc.slot + S_TMP0, sizeof(double2), cudaMemcpyDeviceToHost, stream));
-                FDFD_CUDA(cudaStreamSynchronize(stream));
-                for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] += cd(hbuf[i].x, hbuf[i].y);
+            k = j + 1; relres = rel;
+            if (o.verbose && ((it - (enq - k)) % o.verbose == 0))
+                fprintf(stderr, "[fdfd] fgmres it %d relres %.3e\n", it - (enq - k), relres);
+            return why == 0;
+        };
+        while (true) {
+            FDFD_TRY(enqueue(enq));
+            ++enq; ++it;
+            // the record of the step BEFORE the one just enqueued: the device always has work queued
+            if (enq >= 2 && !examine(enq - 2)) {
+                if (why == 1) examine(enq - 1);   // converged: the step in flight is valid as well
+                break;
             }
-            const double hn = std::sqrt(hbuf[j + 1].x);
-            H[(size_t)(j + 1) * m + j] = hn;
-            if (hn > 0) {
-                if constexpr (kCanCompress) {
-                    if (sb) FDFD_TRY(scale_inv_sqrt_dual(n, vcur, Vs + (int64_t)(j + 1) * n, w, S_TMP0, sc, stream));
-                }
-                if (!sb) FDFD_TRY(scale_inv_sqrt<C>(n, V + (int64_t)(j + 1) * n, w, S_TMP0, sc, stream));
-            }
-            // Givens rotations on the new column
-            for (int i = 0; i < j; ++i) {
-                const cd a = H[(size_t)i * m + j], bb = H[(size_t)(i + 1) * m + j];
-                H[(size_t)i * m + j] = std::conj(cs[i]) * a + std::conj(sn[i]) * bb;
-                H[(size_t)(i + 1) * m + j] = -sn[i] * a + cs[i] * bb;
-            }
-            {
-                const cd a = H[(size_t)j * m + j], bb = H[(size_t)(j + 1) * m + j];
-                const double d = std::sqrt(std::norm(a) + std::norm(bb));
-                if (d == 0) { cs[j] = 1; sn[j] = 0; }
-                else { cs[j] = a / d; sn[j] = bb / d; }
-                H[(size_t)j * m + j] = std::conj(cs[j]) * a + std::conj(sn[j]) * bb;
-                H[(size_t)(j + 1) * m + j] = 0;
-                const cd gj = g[j];
-                g[j] = std::conj(cs[j]) * gj;
-                g[j + 1] = -sn[j] * gj;
-            }
-            ++it; k = j + 1;
-            relres = std::abs(g[j + 1]) / bnorm;
-            if (o.verbose && (it % o.verbose == 0))
-                fprintf(stderr, "[fdfd] fgmres it %d relres %.3e\n", it, relres);
-            if (!std::isfinite(relres)) { status = FDFD_ERR_BREAKDOWN; set_error("FGMRES: non-finite Hessenberg entry"); done = true; break; }
-            if (relres <= o.rtol || it >= o.maxit || hn == 0) break;
+            if (enq >= m || it >= o.maxit) { examine(enq - 1); break; }
         }
         if (status != FDFD_OK) break;
-        // y = H^-1 g (upper triangular), x += Z y
-        for (int i = k - 1; i >= 0; --i) {
-            cd s = g[i];
-            for (int q = i + 1; q < k; ++q) s -= H[(size_t)i * m + q] * y[q];
-            y[i] = s / H[(size_t)i * m + i];
-        }
-        for (int i = 0; i < k; ++i) hbuf[i] = make_double2(y[i].real(), y[i].imag());
-        FDFD_CUDA(cudaMemcpyAsync(sc.slot + S_H0, hbuf.data(), sizeof(double2) * k, cudaMemcpyHostToDevice, stream));
-        if (kaug) {
-            // dx = Z y kept (normalised) as an augmentation vector for the next cycles
-            C* e = E + (int64_t)aug_next * n;
-            FDFD_CUDA(cudaMemsetAsync(e, 0, bytes, stream));
-            FDFD_TRY(multi_axpy<C>(n, k, Z, n, e, S_H0, 1.0, S_TMP1, sc, stream));
-            FDFD_TRY(allreduce_slots(comm, sc, S_TMP1, 1, stream));
-            FDFD_TRY(lincomb<C>(n, x, nullptr, x, nullptr, e, nullptr, nullptr, 0, nullptr, -1, -1, sc, stream));
-            FDFD_TRY(scale_inv_sqrt<C>(n, e, e, S_TMP1, sc, stream));
-            aug_next = (aug_next + 1) % kaug;
-            if (naug < kaug) ++naug;
-        } else {
+        if (it >= o.maxit) done = true;
+        // y = R^-1 g, x += Z y
+        if (k > 0) {
+            fgmres_ysolve_kernel<<<1, 32, 0, stream>>>(k, m, hs.G, sc.slot + S_H0);
             FDFD_TRY(multi_axpy<C>(n, k, Z, n, x, S_H0, 1.0, -1, sc, stream));
         }
         FDFD_CUDA(cudaStreamSynchronize(stream));
+        if (k == 0) { status = FDFD_ERR_BREAKDOWN; set_error("FGMRES: breakdown in the first step of a cycle"); break; }
     }
     // true residual
     FDFD_TRY(A.residual(x, w, b, stream)); ++info.op_applies;
     { const C* xs[1] = {w}; const C* ys[1] = {w}; FDFD_TRY(dots<C>(n, 1, xs, ys, S_RR, sc, stream)); }
     FDFD_TRY(allreduce_slots(comm, sc, S_RR, 1, stream));
-    FDFD_TRY(read_slots(sc, S_RR, 1, hbuf.data(), stream));
+    FDFD_TRY(read_slots(sc, S_RR, 1, hbuf, stream));
     info.iterations = it;
     info.relres = std::sqrt(hbuf[0].x) / bnorm;
     if (status == FDFD_OK && !(info.relres <= o.rtol * 1.0000001)) {

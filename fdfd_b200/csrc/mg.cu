@@ -23,8 +23,6 @@
 #include "krylov.cuh"
 #include "comm.cuh"
 
-#include <cooperative_groups.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -650,7 +648,7 @@ struct MGPrecond : Precond {
         if (graph) cudaGraphExecDestroy(graph);
         cudaFree(in_buf);
         cudaFree(zero_buf);
-        cudaFree(coarse_partials);
+        cudaFree(coarse_partials); cudaFree(coarse_bar); cudaFree(coarse_extra[0]); cudaFree(coarse_extra[1]);
         if (gstream) cudaStreamDestroy(gstream);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
@@ -793,35 +791,48 @@ struct MGPrecond : Precond {
         return !off && s.nranks == 1 && s.len <= kFusedMaxLen && s.len <= o.mg_fuse_len && s.P <= kFusedThreads;
     }
 
-    // ---- mg_coarse_mode = 2: the whole coarsest-level solve as one cooperative kernel (mg_coarse.cuh) ----
+    // ---- mg_coarse_mode = 2: the whole coarsest-level solve as one persistent kernel (mg_coarse.cuh) ----
     double* coarse_partials = nullptr;
+    unsigned int* coarse_bar = nullptr;
+    C* coarse_extra[2] = {nullptr, nullptr};
     int coarse_grid = 0;
-    bool coarse_persistent_ok(const Level<C>& lv) const {
+    bool coarse_ready = false;
+    static size_t coarse_smem_bytes(const Level<C>& lv) {
+        const int len = std::max(lv.ylines.nl ? lv.ylines.len : 0, lv.xlines.nl ? lv.xlines.len : 0);
+        return (line_smem_elems<C>(lv.ylines.nl, lv.ylines.len, lv.ylines.Ptot) +
+                line_smem_elems<C>(lv.xlines.nl, lv.xlines.len, lv.xlines.Ptot) + (size_t)len) * sizeof(C);
+    }
+    // shape limits of the persistent kernel; anything else keeps the launch chain of mode 1
+    bool coarse_persistent_shape_ok(const Level<C>& lv) const {
         if (o.mg_coarse_mode != 2) return false;
         if (lv.op.Ny != lv.op.Ny_global) return false;                    // unsharded level only
         if ((int64_t)lv.op.Nx * lv.op.Ny >= ((int64_t)1 << 31)) return false;
-        if (lv.ylines.nl && (lv.ylines.nranks != 1 || lv.ylines.len > kFusedMaxLen)) return false;
-        if (lv.xlines.nl && (lv.xlines.nranks != 1 || lv.xlines.len > kFusedMaxLen)) return false;
-        return true;
+        if (lv.ylines.nl && lv.ylines.nranks != 1) return false;
+        if (lv.xlines.nl && lv.xlines.nranks != 1) return false;
+        if (std::max(lv.ylines.P, lv.xlines.P) > kCoarseThreads) return false;
+        return coarse_smem_bytes(lv) <= (size_t)200 * 1024;
     }
-    static size_t coarse_smem_bytes(const Level<C>& lv) {
-        const int len = std::max(lv.ylines.nl ? lv.ylines.len : 0, lv.xlines.nl ? lv.xlines.len : 0);
-        return (size_t)4 * len * sizeof(C);
-    }
+    bool coarse_persistent_ok(const Level<C>& lv) const { return coarse_ready && coarse_persistent_shape_ok(lv); }
     int coarse_setup(const Level<C>& lv) {
         const size_t smem = coarse_smem_bytes(lv);
         auto kern = TM() ? coarse_bicgstab_kernel<C, true> : coarse_bicgstab_kernel<C, false>;
         FDFD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0, dev = 0, sms = 0;
+        int per_sm = 0, dev = 0, sms = 0, coop = 0;
         FDFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCoarseThreads, smem));
         FDFD_CUDA(cudaGetDevice(&dev));
         FDFD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        FDFD_CHECK_ARG(per_sm >= 1, "persistent coarse solver does not fit on an SM");
+        FDFD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        const int owners = std::max(lv.ylines.nl, lv.xlines.nl);
+        if (per_sm < 1 || !coop || owners > sms) return FDFD_OK;        // stays on the launch chain
         const int64_t want = ((int64_t)lv.op.Nx * lv.op.Ny + kCoarseThreads - 1) / kCoarseThreads;
-        coarse_grid = (int)std::min<int64_t>((int64_t)per_sm * sms, want);
-        const int lines = std::max(lv.ylines.nl, lv.xlines.nl);
-        FDFD_CHECK_ARG(coarse_grid >= lines, "persistent coarse solver: more relaxation lines than resident CTAs");
-        FDFD_CUDA(cudaMalloc(&coarse_partials, (size_t)coarse_grid * 2 * kCoarseDots * sizeof(double)));
+        coarse_grid = (int)std::max<int64_t>(owners, std::min<int64_t>(sms, want));   // one CTA per SM at most
+        const size_t bytes = (size_t)lv.op.n_local() * sizeof(C);
+        FDFD_CUDA(cudaMalloc(&coarse_partials, (size_t)coarse_grid * kCoarseVals * sizeof(double)));
+        FDFD_CUDA(cudaMalloc(&coarse_bar, 4 * sizeof(unsigned int)));
+        FDFD_CUDA(cudaMemset(coarse_bar, 0, 4 * sizeof(unsigned int)));
+        FDFD_CUDA(cudaMalloc(&coarse_extra[0], bytes));
+        FDFD_CUDA(cudaMalloc(&coarse_extra[1], bytes));
+        coarse_ready = true;
         return FDFD_OK;
     }
     int coarse_persistent(Level<C>& lv, const C* b, C* x, cudaStream_t st) {
@@ -835,11 +846,15 @@ struct MGPrecond : Precond {
         a.b = b; a.x = x;
         a.r = (C*)coarse_ws.v[0]; a.rh = (C*)coarse_ws.v[1]; a.p = (C*)coarse_ws.v[2]; a.v = (C*)coarse_ws.v[3];
         a.t = (C*)coarse_ws.v[4]; a.ph = (C*)coarse_ws.v[5]; a.sh = (C*)coarse_ws.v[6];
+        a.phf = coarse_extra[0]; a.shf = coarse_extra[1];
         a.yl = view(lv.ylines, lv.op.Nx, lv.op.Ny);
         a.xl = view(lv.xlines, lv.op.Nx, lv.op.Ny);
         a.partials = coarse_partials;
+        a.bar = coarse_bar;
+        a.owners = std::max(lv.ylines.nl, lv.xlines.nl);
         void* args[] = {&a};
         const void* kern = TM() ? (const void*)coarse_bicgstab_kernel<C, true> : (const void*)coarse_bicgstab_kernel<C, false>;
+        // cooperative launch: the runtime guarantees that all CTAs are co-resident (the barriers need it)
         FDFD_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coarse_grid), dim3(kCoarseThreads), args, coarse_smem_bytes(lv), st));
         return FDFD_OK;
     }
@@ -1071,7 +1086,7 @@ struct MGPrecond : Precond {
             FDFD_TRY(coarse_ws.ensure((size_t)c.op.n_local() * sizeof(C), true));
             FDFD_CUDA(cudaMalloc(&zero_buf, (size_t)c.op.n_local() * sizeof(C)));
             FDFD_CUDA(cudaMemsetAsync(zero_buf, 0, (size_t)c.op.n_local() * sizeof(C), st));
-            if (coarse_persistent_ok(c)) FDFD_TRY(coarse_setup(c));
+            if (coarse_persistent_shape_ok(c)) FDFD_TRY(coarse_setup(c));
         }
         if (o.mg_graph) {
             FDFD_CUDA(cudaMalloc(&in_buf, (size_t)L[0].op.n_local() * sizeof(C)));

@@ -1,36 +1,41 @@
-// Persistent coarsest-level solver of the multigrid cycle (mg_coarse_mode = 2, opt-in).
+// Persistent coarsest-level solver of the multigrid cycle (mg_coarse_mode = 2).
 //
 // Included by mg.cu inside its anonymous namespace (uses PointCoefs / point_coefs / LineView).
 //
 // The coarsest level (512^2 for a 4096^2 grid) is solved by a fixed number of BiCGSTAB iterations
-// preconditioned with one smoothing sweep (mode 1: krylov.cu bicgstab_t with fixed_its + MGPrecond::
-// smooth).  That is ~20 dependent kernel launches per iteration on a problem that does not fill the
-// GPU: ~1.6 ms of the 3.6 ms an outer iteration takes at 4096^2.  Here the same arithmetic runs in ONE
-// cooperative kernel: all CTAs stay resident, every vector (2 MB in complex64) stays in L2, phases are
-// separated by grid-wide barriers and inner products are reduced through a per-CTA partials array that
-// every CTA sums redundantly after the barrier (deterministic, no atomics).
+// preconditioned with one smoothing sweep from a zero guess (mode 1: krylov.cu bicgstab_t with
+// fixed_its + MGPrecond::smooth).  That is ~30 dependent kernel launches per iteration on a problem
+// whose vectors (2 MB in complex64) all sit in L2: pure launch latency, ~1.6 ms of the 3.6 ms an outer
+// iteration took at 4096^2.  Here the same algorithm runs in ONE kernel:
+//   * one CTA per SM (co-residency guaranteed by a cooperative launch), phases separated by a
+//     hand-written generation barrier (one atomic per CTA, ~1.5 us for 148 CTAs);
+//   * every relaxation line is owned by one CTA for the whole solve: its LU factors, spikes and the
+//     inverse of its interface system are loaded into shared memory ONCE and reused by all 2 x its
+//     sweeps, so a line phase is: fetch the right-hand side, 16-step chunk recurrences out of shared
+//     memory, a 64 x 64 mat-vec out of shared memory, store;
+//   * the ADI order (y-lines, then x-lines on the updated values) only needs a barrier among the CTAs
+//     that own lines; the second half of the x-line update (x += omega e) is applied on the fly by the
+//     stencil phase that consumes it, which removes one more grid-wide phase;
+//   * inner products are reduced through a per-CTA partials array that every CTA sums in the same
+//     order after the barrier (deterministic, no floating-point atomics); rho = (r^, r) is obtained
+//     from (r^, s) - omega (r^, t), both accumulated with (t, s) and (t, t), so the update of x, r
+//     and the next search direction share one phase.
+// Per iteration: 6 grid barriers + 2 line-owner barriers (the first version of this file, which used
+// 1024 CTAs, cooperative-groups grid.sync() and 11 phases, was slower than the launch chain).
 //
-// Per iteration (x0 = 0, so the initial residual is b):
-//   A   p = r + beta (p - omega v);  p^ = omega_s D^-1 p  (strip columns: line right-hand side)   | pointwise
-//   L1  y-lines of p^                                                                              | 1 CTA / line
-//   L2  x-lines of p^: row residual, solve                                                         | 1 CTA / line
-//   L3  x-lines of p^: update                                                                      | 1 CTA / line
-//   V   v = M p^ ;  (r^, v)                                                                        | stencil
-//   S   s = r - alpha v ;  s^ = omega_s D^-1 s (as A)                                              | pointwise
-//   L1..L3 for s^
-//   T   t = M s^ ;  (t, s), (t, t)                                                                 | stencil
-//   X   x += alpha p^ + omega s^ ;  r = s - omega t ;  (r^, r)                                     | pointwise
-// 11 grid barriers per iteration.
-//
-// STATUS: written at the end of round 1 without GPU time left — compiled, never run.  Not reachable
-// unless mg_coarse_mode == 2 is requested explicitly.
+//   XA  x += alpha p^ + omega s^ ; r = s - omega t ; p = r + beta (p - omega v) ; p^0 = omega_s D^-1 p
+//       outside the strip columns, strip columns -> y-line right-hand sides               | pointwise
+//   L1  y-lines of p^ (line owners)            -- owner barrier --
+//   L2  x-lines of p^: row residual, solve; correction left in xl.g (line owners)
+//   V   p^ final = p^0 + omega e_x on the fly ; v = M p^ ; (r^, v)                            | stencil
+//   S   s = r - alpha v ; s^0 as in XA                                                      | pointwise
+//   L1, L2 for s^
+//   T   t = M s^ ; (t, s), (t, t), (r^, s), (r^, t)                                          | stencil
 #pragma once
 
-// <cooperative_groups.h> is included by mg.cu at global scope (this file sits inside a namespace)
-namespace cg = ::cooperative_groups;
-
-constexpr int kCoarseThreads = 256;
-constexpr int kCoarseDots = 4;          // partial sums per CTA: 4 complex numbers
+constexpr int kCoarseThreads = 512;
+constexpr int kCoarseWarps = kCoarseThreads / 32;
+constexpr int kCoarseVals = 8;          // doubles per CTA in the partials array
 
 template <typename C>
 struct CoarseArgs {
@@ -42,8 +47,11 @@ struct CoarseArgs {
     const C* b;                          // right-hand side
     C* x;                                // solution (overwritten; initial guess is zero)
     C *r, *rh, *p, *v, *t, *ph, *sh;     // work vectors
+    C *phf, *shf;                        // p^, s^ with the x-line correction applied
     LineView<C> yl, xl;                  // line sets of the level (nl may be 0)
-    double* partials;                    // [gridDim.x][2 * kCoarseDots]
+    double* partials;                    // [gridDim.x][kCoarseVals]
+    unsigned int* bar;                   // {count, generation} of the grid barrier, {count, generation} of the owners'
+    int owners;                          // CTAs that own at least one line
 };
 
 __device__ __forceinline__ double2 cs_div(double2 a, double2 b) {     // as blas1.cu safe_div
@@ -55,49 +63,71 @@ __device__ __forceinline__ double2 cs_mul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
-// M x at one point (five-point stencil of the shifted operator)
-template <typename C>
-__device__ __forceinline__ C coarse_stencil(const PointCoefs<C>& pc, const C* x, int Nx, int Ny, int i, int j, int64_t n) {
-    C ax = cmul(pc.dg, x[n]);
-    if (i > 0) ax = cfma(pc.kw, x[n - 1], ax);
-    if (i < Nx - 1) ax = cfma(pc.ke, x[n + 1], ax);
-    if (j > 0) ax = cfma(pc.ks, x[n - Nx], ax);
-    if (j < Ny - 1) ax = cfma(pc.kn, x[n + Nx], ax);
-    return ax;
+// vectors are rewritten by other SMs between phases: read them through L2 only
+__device__ __forceinline__ double2 ldv(const double2* p) { return __ldcg(p); }
+__device__ __forceinline__ float2 ldv(const float2* p) { return __ldcg(p); }
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// block-wide sum of K doubles -> partials row of this CTA
+// Generation barrier among `count` CTAs.  bar[0] = arrival counter, bar[1] = generation (monotonic over
+// the life of the buffer; every CTA read it at kernel start, before anyone could have advanced it).
+__device__ __forceinline__ void coarse_barrier(unsigned int* bar, unsigned int count, unsigned int& gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++gen;
+        __threadfence();
+        const unsigned int prev = atomicAdd(&bar[0], 1u);
+        if (prev == count - 1) {
+            bar[0] = 0;
+            st_release_u32(&bar[1], gen);
+        } else {
+            while (ld_acquire_u32(&bar[1]) != gen) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// block-wide sum of K doubles -> this CTA's row of the partials array (before the barrier)
 template <int K>
-__device__ __forceinline__ void coarse_block_reduce(double (&v)[K], double* row, double* sm /* [K][8] */) {
+__device__ __forceinline__ void coarse_block_reduce(double (&v)[K], double* row, double* sm /* [K][kCoarseWarps] */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
-        if (lane == 0) sm[k * 8 + warp] = v[k];
+        if (lane == 0) sm[k * kCoarseWarps + warp] = v[k];
     }
     __syncthreads();
     if (threadIdx.x < K) {
         double s = 0.0;
-        for (int w = 0; w < kCoarseThreads / 32; ++w) s += sm[threadIdx.x * 8 + w];
+#pragma unroll
+        for (int w = 0; w < kCoarseWarps; ++w) s += sm[threadIdx.x * kCoarseWarps + w];
         row[threadIdx.x] = s;
     }
-    __syncthreads();
 }
 
-// after the grid barrier: every CTA sums the K partials of all CTAs (same order everywhere)
+// after the barrier: every CTA sums the K partials of all CTAs in the same order
 template <int K>
-__device__ __forceinline__ void coarse_grid_total(const double* partials, int stride, int offset, double (&out)[K], double* sm) {
+__device__ __forceinline__ void coarse_grid_total(const double* partials, double (&out)[K], double* sm) {
     if (threadIdx.x < 32) {
         double acc[K];
 #pragma unroll
         for (int k = 0; k < K; ++k) acc[k] = 0.0;
         for (int bidx = threadIdx.x; bidx < (int)gridDim.x; bidx += 32) {
 #pragma unroll
-            for (int k = 0; k < K; ++k) acc[k] += __ldcg(&partials[(size_t)bidx * stride + offset + k]);
+            for (int k = 0; k < K; ++k) acc[k] += __ldcg(&partials[(size_t)bidx * kCoarseVals + k]);
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) {
+            // fixed butterfly order -> identical bits in every CTA
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], off);
             if (threadIdx.x == 0) sm[k] = acc[k];
@@ -109,50 +139,67 @@ __device__ __forceinline__ void coarse_grid_total(const double* partials, int st
     __syncthreads();
 }
 
-// One relaxation line handled by the calling CTA (copy of line_fused_kernel's body; DIR 0: the update is
-// applied to column `fixed` of x; DIR 1: the correction is left in v.g for coarse_xline_apply).
-template <typename C, bool TM, int DIR>
-__device__ void coarse_line(const LineView<C>& v, int l, C* x, const C* b, const C* ca, const C* cb, const C* cd,
-                            typename real_of<C>::type sx, typename real_of<C>::type sy, C shift,
-                            typename real_of<C>::type omega, unsigned char* smem, C* sg, C* su) {
+// shared-memory image of one relaxation line: factors (and, for partitioned lines, spikes + the inverse
+// of the interface system), resident for the whole solve
+template <typename C>
+struct LineSmem { C *fl, *fc, *ip, *sv, *sw, *rinv; };
+
+template <typename C>
+__host__ __device__ inline size_t line_smem_elems(int nl, int len, int Ptot) {
+    if (nl == 0) return 0;
+    return (size_t)3 * len + (Ptot > 1 ? (size_t)2 * len + (size_t)4 * Ptot * Ptot : 0);
+}
+
+template <typename C>
+__device__ LineSmem<C> line_smem_carve(C*& cursor, const LineView<C>& v) {
+    LineSmem<C> s{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (v.nl == 0) return s;
+    s.fl = cursor; s.fc = s.fl + v.len; s.ip = s.fc + v.len; cursor = s.ip + v.len;
+    if (v.Ptot > 1) {
+        s.sv = cursor; s.sw = s.sv + v.len; s.rinv = s.sw + v.len;
+        cursor = s.rinv + 4 * v.Ptot * v.Ptot;
+    }
+    return s;
+}
+
+template <typename C>
+__device__ void line_smem_load(const LineSmem<C>& s, const LineView<C>& v, int l) {
     const int64_t nl = v.nl;
+    for (int t = threadIdx.x; t < v.len; t += kCoarseThreads) {
+        s.fl[t] = v.fl[t * nl + l]; s.fc[t] = v.fc[t * nl + l]; s.ip[t] = v.fip[t * nl + l];
+        if (v.Ptot > 1) { s.sv[t] = v.sv[t * nl + l]; s.sw[t] = v.sw[t * nl + l]; }
+    }
+    if (v.Ptot > 1) {
+        const int nn = 4 * v.Ptot * v.Ptot;
+        const C* src = v.rinv + (int64_t)l * nn;
+        for (int e = threadIdx.x; e < nn; e += kCoarseThreads) s.rinv[e] = src[e];
+    }
+}
+
+// tridiagonal solve of the line whose right-hand side sits in sl[0..len): chunk-local recurrences, interface
+// mat-vec, spike correction; the solution replaces sl.  Same arithmetic as line_fused_kernel.
+template <typename C>
+__device__ void coarse_line_solve(const LineView<C>& v, const LineSmem<C>& s, C* sl, C* sg, C* su) {
     const int len = v.len;
-    C* sl = reinterpret_cast<C*>(smem);
-    C* s_fl = sl + len; C* s_fc = s_fl + len; C* s_ip = s_fc + len;
-    const int fixed = l < v.lo ? l : (DIR == 0 ? v.Nx : v.Ny) - v.hi + (l - v.lo);
-    const int n = 2 * v.Ptot;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kCoarseThreads / 32;
-    for (int t = threadIdx.x; t < len; t += kCoarseThreads) {
-        s_fl[t] = v.fl[t * nl + l]; s_fc[t] = v.fc[t * nl + l]; s_ip[t] = v.fip[t * nl + l];
-    }
-    if (DIR == 0) {
-        for (int t = threadIdx.x; t < len; t += kCoarseThreads) sl[t] = v.g[t * nl + l];
-    } else {
-        const int j = fixed;
-        for (int i = threadIdx.x; i < len; i += kCoarseThreads) {
-            PointCoefs<C> pc = point_coefs<C, TM>(ca, cb, cd, v.Nx, v.Ny, sx, sy, shift, i, j);
-            const int64_t pn = (int64_t)j * v.Nx + i;
-            sl[i] = csub(b[pn], coarse_stencil<C>(pc, x, v.Nx, v.Ny, i, j, pn));
-        }
-    }
-    __syncthreads();
     if ((int)threadIdx.x < v.P) {
         const int k = threadIdx.x;
         const int t0 = k * v.m, t1 = min(len, t0 + v.m);
         if (t0 < t1) {
             C y = sl[t0];
-            for (int t = t0 + 1; t < t1; ++t) { y = csub(sl[t], cmul(s_fl[t], y)); sl[t] = y; }
-            C e = cmul(y, s_ip[t1 - 1]);
+            for (int t = t0 + 1; t < t1; ++t) { y = csub(sl[t], cmul(s.fl[t], y)); sl[t] = y; }
+            C e = cmul(y, s.ip[t1 - 1]);
             sl[t1 - 1] = e;
             const C e_last = e;
-            for (int t = t1 - 2; t >= t0; --t) { e = cmul(csub(sl[t], cmul(s_fc[t], e)), s_ip[t]); sl[t] = e; }
+            for (int t = t1 - 2; t >= t0; --t) { e = cmul(csub(sl[t], cmul(s.fc[t], e)), s.ip[t]); sl[t] = e; }
             sg[2 * k] = e; sg[2 * k + 1] = e_last;
         }
     }
     __syncthreads();
     if (v.Ptot > 1) {
-        for (int row = warp; row < n; row += nw) {
-            const C* Ri = v.rinv + ((int64_t)l * n + row) * n;
+        const int n = 2 * v.Ptot;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int row = warp; row < n; row += kCoarseWarps) {
+            const C* Ri = s.rinv + row * n;
             double ax = 0.0, ay = 0.0;
             for (int q = lane; q < n; q += 32) {
                 const C rv = Ri[q], g = sg[q];
@@ -167,51 +214,40 @@ __device__ void coarse_line(const LineView<C>& v, int l, C* x, const C* b, const
             if (lane == 0) su[row] = mk<C>((typename real_of<C>::type)ax, (typename real_of<C>::type)ay);
         }
         __syncthreads();
-    }
-    for (int t = threadIdx.x; t < len; t += kCoarseThreads) {
-        C e = sl[t];
-        if (v.Ptot > 1) {
+        for (int t = threadIdx.x; t < len; t += kCoarseThreads) {
+            C e = sl[t];
             const int kg = t / v.m;
-            if (kg > 0) e = csub(e, cmul(v.sv[t * nl + l], su[2 * (kg - 1) + 1]));
-            if (kg < v.Ptot - 1) e = csub(e, cmul(v.sw[t * nl + l], su[2 * (kg + 1)]));
+            if (kg > 0) e = csub(e, cmul(s.sv[t], su[2 * (kg - 1) + 1]));
+            if (kg < v.Ptot - 1) e = csub(e, cmul(s.sw[t], su[2 * (kg + 1)]));
+            sl[t] = e;
         }
-        if (DIR == 0) {
-            const int64_t pn = (int64_t)t * v.Nx + fixed;
-            x[pn] = cadd(x[pn], cscale(omega, e));
-        } else {
-            v.g[t * nl + l] = e;
-        }
+        __syncthreads();
     }
-    __syncthreads();
 }
 
-// the three line phases of one smoothing sweep from a zero guess: z holds omega D^-1 rhs outside the
-// strip columns and 0 inside, yl.g holds the strip-column right-hand sides
-template <typename C, bool TM>
-__device__ void coarse_line_phases(const CoarseArgs<C>& a, cg::grid_group& grid, C* z, const C* rhs,
-                                   unsigned char* smem, C* sg, C* su) {
-    const int l = blockIdx.x;
-    if (a.yl.nl > 0) {
-        if (l < a.yl.nl) coarse_line<C, TM, 0>(a.yl, l, z, rhs, a.ca, a.cb, a.cd, a.sx, a.sy, a.shift, a.omega, smem, sg, su);
-        grid.sync();
-    }
-    if (a.xl.nl > 0) {
-        if (l < a.xl.nl) coarse_line<C, TM, 1>(a.xl, l, z, rhs, a.ca, a.cb, a.cd, a.sx, a.sy, a.shift, a.omega, smem, sg, su);
-        grid.sync();
-        if (l < a.xl.nl) {
-            const int j = l < a.xl.lo ? l : a.Ny - a.xl.hi + (l - a.xl.lo);
-            for (int i = threadIdx.x; i < a.xl.len; i += kCoarseThreads) {
-                const int64_t pn = (int64_t)j * a.Nx + i;
-                z[pn] = cadd(z[pn], cscale(a.omega, a.xl.g[(int64_t)i * a.xl.nl + l]));
-            }
-        }
-        grid.sync();
-    }
+// M x at one point from the five values (out-of-range neighbours have zero coefficients)
+template <typename C>
+__device__ __forceinline__ C coarse_stencil5(const PointCoefs<C>& pc, C xc, C xw, C xe, C xs, C xn) {
+    C ax = cmul(pc.dg, xc);
+    ax = cfma(pc.kw, xw, ax);
+    ax = cfma(pc.ke, xe, ax);
+    ax = cfma(pc.ks, xs, ax);
+    ax = cfma(pc.kn, xn, ax);
+    return ax;
 }
+
+template <typename C>
+struct CoarseCtx {
+    CoarseArgs<C> a;
+    LineSmem<C> ys, xs;
+    C *sl, *sg, *su;
+    double* red;
+    unsigned int gen_all, gen_own;
+};
 
 // pointwise part of the zero-guess smoothing sweep for the value `val` at point (i, j)
 template <typename C, bool TM>
-__device__ __forceinline__ C coarse_point_relax(const CoarseArgs<C>& a, int i, int j, int64_t n, C val) {
+__device__ __forceinline__ C coarse_point_relax(const CoarseArgs<C>& a, int i, int j, int q, C val) {
     const LineView<C>& yl = a.yl;
     if (yl.nl > 0 && (i < yl.lo || i >= a.Nx - yl.hi)) {
         const int l = i < yl.lo ? i : yl.lo + (i - (a.Nx - yl.hi));
@@ -222,103 +258,185 @@ __device__ __forceinline__ C coarse_point_relax(const CoarseArgs<C>& a, int i, i
     return cscale(a.omega, cdiv(val, pc.dg));
 }
 
+// line phases of one smoothing sweep from a zero guess.  z holds omega D^-1 rhs outside the strip columns
+// and 0 inside; yl.g holds the strip-column right-hand sides.  On return (after the caller's grid barrier)
+// z is final except for the rows of the x-lines, whose correction e sits in xl.g (applied by coarse_zfin).
 template <typename C, bool TM>
-__global__ void __launch_bounds__(kCoarseThreads) coarse_bicgstab_kernel(CoarseArgs<C> a) {
-    cg::grid_group grid = cg::this_grid();
+__device__ void coarse_line_phases(CoarseCtx<C>& c, C* z, const C* rhs) {
+    const CoarseArgs<C>& a = c.a;
+    const int l = blockIdx.x;
+    if (l >= a.owners) return;
+    if (a.yl.nl > 0) {
+        if (l < a.yl.nl) {
+            const LineView<C>& v = a.yl;
+            for (int t = threadIdx.x; t < v.len; t += kCoarseThreads) c.sl[t] = ldv(&v.g[(int64_t)t * v.nl + l]);
+            __syncthreads();
+            coarse_line_solve<C>(v, c.ys, c.sl, c.sg, c.su);
+            const int col = l < v.lo ? l : v.Nx - v.hi + (l - v.lo);
+            for (int t = threadIdx.x; t < v.len; t += kCoarseThreads)
+                z[(int64_t)t * v.Nx + col] = cscale(a.omega, c.sl[t]);      // the column was zero
+        }
+        if (a.xl.nl > 0) coarse_barrier(a.bar + 2, (unsigned)a.owners, c.gen_own);
+    }
+    if (a.xl.nl > 0 && l < a.xl.nl) {
+        const LineView<C>& v = a.xl;
+        const int j = l < v.lo ? l : v.Ny - v.hi + (l - v.lo);
+        for (int i = threadIdx.x; i < v.len; i += kCoarseThreads) {
+            const PointCoefs<C> pc = point_coefs<C, TM>(a.ca, a.cb, a.cd, a.Nx, a.Ny, a.sx, a.sy, a.shift, i, j);
+            const int64_t pn = (int64_t)j * a.Nx + i;
+            const C zc = ldv(&z[pn]);
+            const C zw = i > 0 ? ldv(&z[pn - 1]) : czero<C>();
+            const C ze = i < a.Nx - 1 ? ldv(&z[pn + 1]) : czero<C>();
+            const C zs = j > 0 ? ldv(&z[pn - a.Nx]) : czero<C>();
+            const C zn = j < a.Ny - 1 ? ldv(&z[pn + a.Nx]) : czero<C>();
+            c.sl[i] = csub(ldv(&rhs[pn]), coarse_stencil5<C>(pc, zc, zw, ze, zs, zn));
+        }
+        __syncthreads();
+        coarse_line_solve<C>(v, c.xs, c.sl, c.sg, c.su);
+        for (int i = threadIdx.x; i < v.len; i += kCoarseThreads) v.g[(int64_t)i * v.nl + l] = c.sl[i];
+    }
+}
+
+// value of the swept vector at (i, j): z plus the pending x-line correction of its row
+template <typename C>
+__device__ __forceinline__ C coarse_zfin(const CoarseArgs<C>& a, const C* z, int i, int j, int64_t q) {
+    C v = ldv(&z[q]);
+    const LineView<C>& xl = a.xl;
+    if (xl.nl > 0 && (j < xl.lo || j >= a.Ny - xl.hi)) {
+        const int l = j < xl.lo ? j : xl.lo + (j - (a.Ny - xl.hi));
+        v = cadd(v, cscale(a.omega, ldv(&xl.g[(int64_t)i * xl.nl + l])));
+    }
+    return v;
+}
+
+// out = M zfin at the thread's points, zfin stored to zf; K = 1: acc = (rh, out);
+// K = 4: acc = (out, s), (out, out), (rh, s), (rh, out) with s = a.r
+template <typename C, bool TM, int MODE>
+__device__ __forceinline__ void coarse_apply_phase(const CoarseArgs<C>& a, const C* z, C* zf, C* out, double* acc,
+                                                   int tid, int stride, int n) {
+    for (int q = tid; q < n; q += stride) {
+        const int j = q / a.Nx, i = q - j * a.Nx;
+        const PointCoefs<C> pc = point_coefs<C, TM>(a.ca, a.cb, a.cd, a.Nx, a.Ny, a.sx, a.sy, a.shift, i, j);
+        const C zc = coarse_zfin<C>(a, z, i, j, q);
+        const C zw = i > 0 ? coarse_zfin<C>(a, z, i - 1, j, q - 1) : czero<C>();
+        const C ze = i < a.Nx - 1 ? coarse_zfin<C>(a, z, i + 1, j, q + 1) : czero<C>();
+        const C zs = j > 0 ? coarse_zfin<C>(a, z, i, j - 1, q - a.Nx) : czero<C>();
+        const C zn = j < a.Ny - 1 ? coarse_zfin<C>(a, z, i, j + 1, q + a.Nx) : czero<C>();
+        const C o = coarse_stencil5<C>(pc, zc, zw, ze, zs, zn);
+        zf[q] = zc;
+        out[q] = o;
+        const C rhv = ldv(&a.rh[q]);
+        if (MODE == 0) {
+            acc[0] += (double)rhv.x * o.x + (double)rhv.y * o.y;        // conj(r^) * v
+            acc[1] += (double)rhv.x * o.y - (double)rhv.y * o.x;
+        } else {
+            const C sv = ldv(&a.r[q]);
+            acc[0] += (double)o.x * sv.x + (double)o.y * sv.y;          // conj(t) * s
+            acc[1] += (double)o.x * sv.y - (double)o.y * sv.x;
+            acc[2] += (double)o.x * o.x + (double)o.y * o.y;            // (t, t)
+            acc[3] += (double)rhv.x * sv.x + (double)rhv.y * sv.y;      // conj(r^) * s
+            acc[4] += (double)rhv.x * sv.y - (double)rhv.y * sv.x;
+            acc[5] += (double)rhv.x * o.x + (double)rhv.y * o.y;        // conj(r^) * t
+            acc[6] += (double)rhv.x * o.y - (double)rhv.y * o.x;
+        }
+    }
+}
+
+template <typename C, bool TM>
+__global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(CoarseArgs<C> a) {
+    using R = typename real_of<C>::type;
     extern __shared__ __align__(16) unsigned char coarse_smem[];
     __shared__ C sg[2 * kMaxChunks], su[2 * kMaxChunks];
-    __shared__ double red[2 * kCoarseDots * 8];
+    __shared__ double red[kCoarseVals * kCoarseWarps];
+    CoarseCtx<C> c;
+    c.a = a;
+    C* cursor = reinterpret_cast<C*>(coarse_smem);
+    c.ys = line_smem_carve<C>(cursor, a.yl);
+    c.xs = line_smem_carve<C>(cursor, a.xl);
+    c.sl = cursor;
+    c.sg = sg; c.su = su; c.red = red;
+    if (threadIdx.x == 0) { sg[0] = czero<C>(); }
+    c.gen_all = ld_acquire_u32(&a.bar[1]);
+    c.gen_own = ld_acquire_u32(&a.bar[3]);
     const int n = a.Nx * a.Ny;                       // < 2^31 (checked on the host)
     const int tid = blockIdx.x * kCoarseThreads + threadIdx.x;
     const int stride = gridDim.x * kCoarseThreads;
-    const int pstride = 2 * kCoarseDots;
-    double* prow = a.partials + (size_t)blockIdx.x * pstride;
+    double* prow = a.partials + (size_t)blockIdx.x * kCoarseVals;
+    const unsigned int nblk = gridDim.x;
 
-    // restart: x = 0, r = r^ = b, p = v = 0, rho = (r, r), rho_old = alpha = omega = 1
-    double acc1[2] = {0.0, 0.0};
+    // the lines this CTA owns stay in shared memory for the whole solve
+    if ((int)blockIdx.x < a.yl.nl) line_smem_load<C>(c.ys, a.yl, blockIdx.x);
+    if ((int)blockIdx.x < a.xl.nl) line_smem_load<C>(c.xs, a.xl, blockIdx.x);
+
+    // start: x = 0, r = r^ = p = b, rho = (b, b); first search direction swept
+    double acc2[2] = {0.0, 0.0};
     for (int q = tid; q < n; q += stride) {
+        const int j = q / a.Nx, i = q - j * a.Nx;
         const C bv = a.b[q];
-        a.r[q] = bv; a.rh[q] = bv; a.p[q] = czero<C>(); a.v[q] = czero<C>(); a.x[q] = czero<C>();
-        acc1[0] += (double)bv.x * bv.x + (double)bv.y * bv.y;
+        a.r[q] = bv; a.rh[q] = bv; a.p[q] = bv; a.x[q] = czero<C>();
+        a.ph[q] = coarse_point_relax<C, TM>(a, i, j, q, bv);
+        acc2[0] += (double)bv.x * bv.x + (double)bv.y * bv.y;
     }
-    coarse_block_reduce<2>(acc1, prow, red);
-    grid.sync();
+    coarse_block_reduce<2>(acc2, prow, red);
+    coarse_barrier(a.bar, nblk, c.gen_all);
     double tot2[2];
-    coarse_grid_total<2>(a.partials, pstride, 0, tot2, red);
-    double2 rho = make_double2(tot2[0], 0.0), rho_old = make_double2(1.0, 0.0);
+    coarse_grid_total<2>(a.partials, tot2, red);
+    double2 rho = make_double2(tot2[0], 0.0);
     double2 alpha = make_double2(1.0, 0.0), omega = make_double2(1.0, 0.0);
 
     for (int it = 0; it < a.its; ++it) {
-        // A: p = r + beta (p - omega v), p^ pointwise
-        const double2 beta = cs_mul(cs_div(rho, rho_old), cs_div(alpha, omega));
-        const double2 nbo = make_double2(-(beta.x * omega.x - beta.y * omega.y), -(beta.x * omega.y + beta.y * omega.x));
-        const C betaC = mk<C>((typename real_of<C>::type)beta.x, (typename real_of<C>::type)beta.y);
-        const C nboC = mk<C>((typename real_of<C>::type)nbo.x, (typename real_of<C>::type)nbo.y);
-        for (int q = tid; q < n; q += stride) {
-            const int j = q / a.Nx, i = q - j * a.Nx;
-            C pv = cfma(nboC, a.v[q], cfma(betaC, a.p[q], a.r[q]));
-            a.p[q] = pv;
-            a.ph[q] = coarse_point_relax<C, TM>(a, i, j, q, pv);
-        }
-        grid.sync();
-        coarse_line_phases<C, TM>(a, grid, a.ph, a.p, coarse_smem, sg, su);
+        // (p^0 and the y-line right-hand sides of this iteration were written by the previous phase)
+        coarse_line_phases<C, TM>(c, a.ph, a.p);
+        coarse_barrier(a.bar, nblk, c.gen_all);
         // V: v = M p^, (r^, v)
         double accv[2] = {0.0, 0.0};
-        for (int q = tid; q < n; q += stride) {
-            const int j = q / a.Nx, i = q - j * a.Nx;
-            const PointCoefs<C> pc = point_coefs<C, TM>(a.ca, a.cb, a.cd, a.Nx, a.Ny, a.sx, a.sy, a.shift, i, j);
-            const C vv = coarse_stencil<C>(pc, a.ph, a.Nx, a.Ny, i, j, q);
-            a.v[q] = vv;
-            const C rhv = a.rh[q];
-            accv[0] += (double)rhv.x * vv.x + (double)rhv.y * vv.y;      // conj(r^) * v
-            accv[1] += (double)rhv.x * vv.y - (double)rhv.y * vv.x;
-        }
-        coarse_block_reduce<2>(accv, prow + 2, red);
-        grid.sync();
-        coarse_grid_total<2>(a.partials, pstride, 2, tot2, red);
+        coarse_apply_phase<C, TM, 0>(a, a.ph, a.phf, a.v, accv, tid, stride, n);
+        coarse_block_reduce<2>(accv, prow, red);
+        coarse_barrier(a.bar, nblk, c.gen_all);
+        coarse_grid_total<2>(a.partials, tot2, red);
         alpha = cs_div(rho, make_double2(tot2[0], tot2[1]));
-        // S: s = r - alpha v (in r), s^ pointwise
-        const C alphaC = mk<C>((typename real_of<C>::type)alpha.x, (typename real_of<C>::type)alpha.y);
+        // S: s = r - alpha v (in r), s^0 pointwise
+        const C alphaC = mk<C>((R)alpha.x, (R)alpha.y);
         for (int q = tid; q < n; q += stride) {
             const int j = q / a.Nx, i = q - j * a.Nx;
-            const C sv = csub(a.r[q], cmul(alphaC, a.v[q]));
+            const C sv = csub(ldv(&a.r[q]), cmul(alphaC, a.v[q]));      // v[q] was written by this thread
             a.r[q] = sv;
             a.sh[q] = coarse_point_relax<C, TM>(a, i, j, q, sv);
         }
-        grid.sync();
-        coarse_line_phases<C, TM>(a, grid, a.sh, a.r, coarse_smem, sg, su);
-        // T: t = M s^, (t, s), (t, t)
-        double acct[4] = {0.0, 0.0, 0.0, 0.0};
+        coarse_barrier(a.bar, nblk, c.gen_all);
+        coarse_line_phases<C, TM>(c, a.sh, a.r);
+        coarse_barrier(a.bar, nblk, c.gen_all);
+        // T: t = M s^, (t, s), (t, t), (r^, s), (r^, t)
+        double acct[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        coarse_apply_phase<C, TM, 1>(a, a.sh, a.shf, a.t, acct, tid, stride, n);
+        coarse_block_reduce<8>(acct, prow, red);
+        coarse_barrier(a.bar, nblk, c.gen_all);
+        double tot8[8];
+        coarse_grid_total<8>(a.partials, tot8, red);
+        omega = cs_div(make_double2(tot8[0], tot8[1]), make_double2(tot8[2], 0.0));
+        // rho_new = (r^, s - omega t)
+        const double2 rt = cs_mul(omega, make_double2(tot8[5], tot8[6]));
+        const double2 rho_new = make_double2(tot8[3] - rt.x, tot8[4] - rt.y);
+        const double2 beta = cs_mul(cs_div(rho_new, rho), cs_div(alpha, omega));
+        const double2 nbo = cs_mul(beta, omega);
+        rho = rho_new;
+        // XA: x += alpha p^ + omega s^ ; r = s - omega t ; p = r + beta (p - omega v) ; p^0
+        const C omegaC = mk<C>((R)omega.x, (R)omega.y);
+        const C betaC = mk<C>((R)beta.x, (R)beta.y);
+        const C nboC = mk<C>((R)(-nbo.x), (R)(-nbo.y));
+        const bool more = it + 1 < a.its;
         for (int q = tid; q < n; q += stride) {
-            const int j = q / a.Nx, i = q - j * a.Nx;
-            const PointCoefs<C> pc = point_coefs<C, TM>(a.ca, a.cb, a.cd, a.Nx, a.Ny, a.sx, a.sy, a.shift, i, j);
-            const C tv = coarse_stencil<C>(pc, a.sh, a.Nx, a.Ny, i, j, q);
-            a.t[q] = tv;
-            const C sv = a.r[q];
-            acct[0] += (double)tv.x * sv.x + (double)tv.y * sv.y;        // conj(t) * s
-            acct[1] += (double)tv.x * sv.y - (double)tv.y * sv.x;
-            acct[2] += (double)tv.x * tv.x + (double)tv.y * tv.y;
+            // every array touched here was last written by this same thread (same q mapping)
+            a.x[q] = cfma(omegaC, a.shf[q], cfma(alphaC, a.phf[q], a.x[q]));
+            if (more) {
+                const int j = q / a.Nx, i = q - j * a.Nx;
+                const C rv = csub(a.r[q], cmul(omegaC, a.t[q]));
+                a.r[q] = rv;
+                const C pv = cfma(nboC, a.v[q], cfma(betaC, a.p[q], rv));
+                a.p[q] = pv;
+                a.ph[q] = coarse_point_relax<C, TM>(a, i, j, q, pv);
+            }
         }
-        coarse_block_reduce<4>(acct, prow + 4, red);
-        grid.sync();
-        double tot4[4];
-        coarse_grid_total<4>(a.partials, pstride, 4, tot4, red);
-        omega = cs_div(make_double2(tot4[0], tot4[1]), make_double2(tot4[2], 0.0));
-        // X: x += alpha p^ + omega s^, r = s - omega t, rho = (r^, r)
-        const C omegaC = mk<C>((typename real_of<C>::type)omega.x, (typename real_of<C>::type)omega.y);
-        double accr[2] = {0.0, 0.0};
-        for (int q = tid; q < n; q += stride) {
-            a.x[q] = cfma(omegaC, a.sh[q], cfma(alphaC, a.ph[q], a.x[q]));
-            const C rv = csub(a.r[q], cmul(omegaC, a.t[q]));
-            a.r[q] = rv;
-            const C rhv = a.rh[q];
-            accr[0] += (double)rhv.x * rv.x + (double)rhv.y * rv.y;
-            accr[1] += (double)rhv.x * rv.y - (double)rhv.y * rv.x;
-        }
-        coarse_block_reduce<2>(accr, prow, red);
-        grid.sync();
-        coarse_grid_total<2>(a.partials, pstride, 0, tot2, red);
-        rho_old = rho;
-        rho = make_double2(tot2[0], tot2[1]);
+        if (more) coarse_barrier(a.bar, nblk, c.gen_all);
     }
 }

@@ -139,7 +139,6 @@ typedef struct {
     int mg_coarse_mode; /* coarsest level: 0 = mg_coarse_its smoothing sweeps, 1 = mg_coarse_its
                          * iterations of BiCGSTAB preconditioned by one smoothing sweep, 2 = the same
                          * iterations inside one persistent cooperative kernel (experimental, opt-in) */
-    int lgmres_k;     /* FGMRES: number of previous-cycle corrections that augment each restart cycle */
     int mg_coarse_replicate; /* sharded grids: 1 = every rank solves the whole coarsest level, 0 = distributed,
                               * -1 = automatic (replicate while the coarse grid has <= 2^20 points)        */
     int mg_single;    /* 1 = run the multigrid cycle in complex64 inside a complex128 solve (mixed precision) */

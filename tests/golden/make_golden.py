@@ -104,6 +104,45 @@ def scatter_1024():
     np.savez_compressed(os.path.join(HERE, "scatter_1024.npz"), **out)
 
 
+def scatter_2048():
+    """SURVEY.md §8c "scaled 2048^2" case: the largest size the reference's SuperLU solve fits in this
+    container (17.6 GB, ~5 min per polarisation).  Besides probes / norm / a 32x-decimated field it stores
+    the error amplification ||A^-1||_2 ||b|| / ||x|| of an iterative solve (power iteration on A^-H A^-1 with
+    the reference's own cached LU), which the default residual tolerance of the GPU solver is derived from.
+    Also re-measures the same factor at 300^2 and 1024^2 (key amp_N)."""
+    import time
+    out = dict(N=2048)
+    for N in (300, 1024, 2048):
+        for pol in ("TM", "TE"):
+            sim = _ref_sim(N, -1e6, 40, 80)
+            t0 = time.time()
+            F = getattr(sim, "solve_total_field_" + pol)()
+            dt = time.time() - t0
+            A = getattr(sim, "_A_" + pol)
+            b = np.asarray((sim.Q @ A - A @ sim.Q) @ sim.source).ravel()
+            lu = getattr(sim, "_LU_" + pol).__self__          # scipy SuperLU object behind factorized()
+            rng = np.random.default_rng(1)
+            v = rng.standard_normal(N * N) + 1j * rng.standard_normal(N * N)
+            v /= np.linalg.norm(v)
+            s2 = 0.0
+            for _ in range(12):
+                w = lu.solve(v)
+                w = lu.solve(w, trans="H")
+                s2 = np.linalg.norm(w)
+                v = w / s2
+            amp = np.sqrt(s2) * np.linalg.norm(b) / np.linalg.norm(F)
+            out[f"amp_{N}_{pol}"] = amp
+            print(N, pol, "solve", round(dt, 1), "s  amp", amp, flush=True)
+            if N == 2048:
+                out[f"probe_{pol}"] = F[1024, 512]
+                out[f"max_{pol}"] = np.abs(F).max()
+                out[f"norm_{pol}"] = np.linalg.norm(F)
+                out[f"dec_{pol}"] = F[::32, ::32].copy()
+                out[f"reference_seconds_{pol}"] = np.float64(dt)
+            del sim, lu, A, F
+    np.savez_compressed(os.path.join(HERE, "scatter_2048.npz"), **out)
+
+
 def band_fixture():
     """BASELINE config 3 (example_square_lattice.py: a=1, 40x40, eps_bg=10.2, air hole r=0.4, 200-point
     Gamma-X-M-Gamma path, 5 bands) at path indices 0, 33, 59, 100, 117, 199, and the rectangular
@@ -256,6 +295,9 @@ def periodic3d_fixture():
 if __name__ == "__main__":
     if "--scatter-1024" in sys.argv:
         scatter_1024()
+        sys.exit(0)
+    if "--scatter-2048" in sys.argv:
+        scatter_2048()
         sys.exit(0)
     if "--p3d-cfg4" in sys.argv:
         periodic3d_cfg4_fixture()

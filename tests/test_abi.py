@@ -37,7 +37,7 @@ def test_header_symbols_exported(lib):
 def test_opts_struct_layout(lib):
     from fdfd_b200 import _lib
     o = _lib.default_opts()
-    assert o.rtol == 1e-8 and o.restart == 30 and o.lgmres_k == 0 and o.mg_shift_im == 0.4 and o.reorth == 0 and o.mg_graph == 1
+    assert o.rtol == 1e-8 and o.restart == 30 and o.mg_shift_im == 0.4 and o.reorth == 0 and o.mg_graph == 1
     assert o.mg_single == 0 and o.basis_single == 0 and o.mg_fuse_len == 1024 and o.mg_kh_max == 1.3
     # same size and the same field names in the same order as the C struct of the header
     assert C.sizeof(_lib.KrylovOpts) == lib.fdfd_krylov_opts_size()
@@ -118,3 +118,20 @@ def test_host_setup_matches_oracle():
         sim.add_mask(np.ones((3, 3)))
     with pytest.raises(TypeError):
         sim.add_mask({})
+
+
+def test_amplification_model_covers_the_measurements(golden):
+    """default_rtol's model 71 sqrt(L / lambda) is an upper envelope of the factors measured with the
+    reference's LU at 300^2, 1024^2 and 2048^2 (both polarisations)."""
+    import fdfd_b200
+    g = golden("scatter_2048.npz")
+    f0 = 10e9
+    lam = 299792458 / f0
+    for N in (300, 1024, 2048):
+        sim = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N)
+        model = 1e-6 / (1.25 * sim.default_rtol(1e-6)) if sim.default_rtol(1e-6) < 1e-8 else None
+        for pol in ("TM", "TE"):
+            amp = float(g[f"amp_{N}_{pol}"])
+            assert amp <= sim.AMPLIFICATION_PER_SQRT_WAVELENGTH * np.sqrt(N / 50)
+            if model is not None:
+                assert amp <= model * 1.0000001

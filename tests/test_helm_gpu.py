@@ -128,6 +128,32 @@ def test_apply_linearity_full_size():
         assert err <= 1e-13
 
 
+@pytest.mark.parametrize("pol", ["TE", "TM"])
+def test_apply_4096_full_grid_vs_oracle(pol):
+    """the BASELINE-size operator (4096^2 scaled cylinder problem with UPML, complex128)
+    against the numpy restatement of A @ x on the WHOLE grid, <= 1e-13 relative (the oracle's explicit sparse
+    A equals its matrix-free form to 1e-16, tests/test_oracle_golden.py)."""
+    import torch
+    import fdfd_b200
+    N = 4096
+    f0 = 10e9
+    lam = 299792458 / f0
+    sim = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N)
+    sim.add_object(-1e6, 1.0, (sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
+    sim.add_UPML(pml_width=40, sigma_max=10)
+    ca, cb, cd, sx, sy = sim.stencil_coefficients(pol)
+    rng = np.random.default_rng(0)                       # SURVEY §8d apply micro-benchmark vector
+    x = rng.standard_normal(N * N) + 1j * rng.standard_normal(N * N)
+    y = sim.operator(pol).apply(torch.from_numpy(x).cuda()).cpu().numpy()
+    sim.close()
+    ref = so.apply_stencil(pol, ca, cb, cd, sx, sy, x).ravel()
+    err = np.linalg.norm(y - ref) / np.linalg.norm(ref)
+    assert err <= 1e-13, err
+    # and row by row, so a defect confined to a wall / PML row cannot hide in the global norm
+    d = np.abs(y - ref).reshape(N, N).max(axis=1) / np.abs(ref).reshape(N, N).max(axis=1)
+    assert d.max() <= 1e-12, (int(d.argmax()), d.max())
+
+
 def test_apply_rejects_bad_input():
     import torch
     import fdfd_b200

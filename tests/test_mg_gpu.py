@@ -82,22 +82,31 @@ def test_precond_reduces_shifted_residual():
     assert res.item() < 0.5
 
 
-@pytest.mark.skipif(not os.environ.get("FDFD_TEST_EXPERIMENTAL"), reason="opt-in: experimental persistent coarse solver")
 @pytest.mark.parametrize("pol", ["TE", "TM"])
-@pytest.mark.parametrize("graph", [0, 1])
-def test_persistent_coarse_solver_matches_mode1(pol, graph):
-    """mg_coarse_mode=2 (one cooperative kernel for the coarsest-level BiCGSTAB) runs the same arithmetic as
-    mode 1 (separate kernels): the cycle output must agree to inner-product rounding.  Not part of the default
-    suite until the kernel has been validated on hardware (NOTES_r01.md)."""
+@pytest.mark.parametrize("N,levels,graph,lines", [
+    (256, 0, 0, (24, 24, 24, 24)),      # coarsest 32^2: unpartitioned lines (1 chunk)
+    (256, 0, 1, (24, 24, 24, 24)),      # same, replayed as a CUDA graph (cooperative launch captured)
+    (256, 2, 1, (24, 24, 24, 24)),      # coarsest 128^2: 8 chunks per line, interface system in shared memory
+    (256, 2, 1, (24, 0, 0, 24)),        # one-sided strips (owners' barrier with unequal line sets)
+    (256, 2, 1, (0, 0, 24, 24)),        # x-lines only
+    (256, 2, 1, (0, 0, 0, 0)),          # point Jacobi only
+    (1024, 2, 1, (40, 40, 40, 40)),     # coarsest 512^2: 32 chunks per line (the 4096^2 production shape)
+])
+def test_persistent_coarse_solver_matches_mode1(pol, N, levels, graph, lines):
+    """mg_coarse_mode=2 (ONE persistent kernel for the coarsest-level BiCGSTAB, csrc/mg_coarse.cuh) runs the
+    algorithm of mode 1 (a chain of ~30 launches per iteration, itself checked against oracle/mg_oracle.py
+    above): the cycle output must agree to inner-product rounding (mode 2 obtains rho from (r^,s) - omega (r^,t))."""
     import torch
     import fdfd_b200
-    N = 256
-    ca, cb, cd, sx, sy = _problem(N, pol, eps=-1e6, pw=24)
+    ca, cb, cd, sx, sy = _problem(N, pol, eps=-1e6, pw=max(lines) if max(lines) else 12)
     A = fdfd_b200.HelmholtzOperator2D(pol, N, N, ca, cb, cd, sx, sy)
     g = torch.Generator(device="cuda").manual_seed(2)
     v = torch.complex(torch.randn(N * N, generator=g, device="cuda", dtype=torch.float64),
                       torch.randn(N * N, generator=g, device="cuda", dtype=torch.float64))
-    kw = dict(precond="mg", line_x_lo=24, line_x_hi=24, line_y_lo=24, line_y_hi=24, mg_graph=graph)
+    kw = dict(precond="mg", line_x_lo=lines[0], line_x_hi=lines[1], line_y_lo=lines[2], line_y_hi=lines[3],
+              mg_graph=graph, mg_levels=levels, mg_coarse_its=6)
     z1 = A.precond_apply(v, mg_coarse_mode=1, **kw)
     z2 = A.precond_apply(v, mg_coarse_mode=2, **kw)
+    z3 = A.precond_apply(v, mg_coarse_mode=2, **kw)
+    assert torch.equal(z2, z3)                           # deterministic reductions
     assert (torch.linalg.vector_norm(z2 - z1) / torch.linalg.vector_norm(z1)).item() <= 1e-7
