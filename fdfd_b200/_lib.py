@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfdfd_b200.so")
+LIB_PATH = os.environ.get("FDFD_B200_LIB") or os.path.join(_HERE, "libfdfd_b200.so")   # override: debug builds only
 
 FDFD_OK = 0
 FDFD_ERR_ARG, FDFD_ERR_CUDA, FDFD_ERR_BREAKDOWN, FDFD_ERR_NOCONV, FDFD_ERR_NCCL, FDFD_ERR_STATE = -1, -2, -3, -4, -5, -6
@@ -87,6 +87,7 @@ _PROTOTYPES = {
     "fdfd_precond_apply": (C.c_int, [C.c_void_p, C.POINTER(KrylovOpts), C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdfd_comm_unique_id": (C.c_int, [C.c_void_p]),
     "fdfd_comm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]),
+    "fdfd_comm_peer_mapped": (C.c_int, [C.c_void_p]),
     "fdfd_comm_destroy": (None, [C.c_void_p]),
 }
 

@@ -8,8 +8,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libfdfd_b200.so")
-SOURCES = ["api.cu", "yee_assemble.cu", "helm2d.cu", "blas1.cu", "krylov.cu", "comm.cu", "mg.cu", "csr_ops.cu"]
+# FDFD_COARSE_TRACE=1 builds an instrumented copy next to the product library (load it with FDFD_B200_LIB=...)
+LIB = os.path.join(HERE, "libfdfd_b200_trace.so" if os.environ.get("FDFD_COARSE_TRACE") else "libfdfd_b200.so")
+SOURCES = ["api.cu", "yee_assemble.cu", "helm2d.cu", "blas1.cu", "krylov.cu", "comm.cu", "p2p.cu", "mg.cu", "csr_ops.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -17,6 +18,10 @@ NVCC_FLAGS = [
     "--fmad=true",
     "-cudart", "static",
 ]
+
+
+if os.environ.get("FDFD_COARSE_TRACE"):
+    NVCC_FLAGS.append("-DFDFD_COARSE_TRACE")      # phase timings of the persistent coarse solver (debug)
 
 
 def _sources():
@@ -46,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == fp:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build_trace" if os.environ.get("FDFD_COARSE_TRACE") else "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []

@@ -59,6 +59,7 @@ extern "C" int fdfd_comm_create(fdfd_comm_t** out, int nranks, int rank, const v
     *out = new fdfd_comm{c};
     return FDFD_OK;
 }
+extern "C" int fdfd_comm_peer_mapped(const fdfd_comm_t* c) { return c && c->c && p2p_enabled(c->c) ? 1 : 0; }
 extern "C" void fdfd_comm_destroy(fdfd_comm_t* c) {
     if (!c) return;
     comm_destroy(c->c);

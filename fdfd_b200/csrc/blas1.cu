@@ -587,27 +587,28 @@ int multi_axpy(int64_t n, int k, const CV* V, int64_t ldv, C* w, int s0, double 
 
 template <typename C, typename C2>
 __global__ void __launch_bounds__(kThreads) scale_inv_sqrt_kernel(int64_t n, C* __restrict__ out,
-        C2* __restrict__ out2, const C* __restrict__ x, const double2* nrm2) {
+        C2* __restrict__ out2, C2* __restrict__ out3, const C* __restrict__ x, const double2* nrm2) {
     using R = typename real_of<C>::type;
     const R s = (R)(1.0 / sqrt(nrm2->x));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
         const C v = cscale(s, x[i]);
-        out[i] = v;
-        if (out2) out2[i] = cvt<C2>(v);
+        if (out) out[i] = v;
+        if (out2) { const C2 c = cvt<C2>(v); out2[i] = c; if (out3) out3[i] = c; }
     }
 }
 
 template <typename C>
 int scale_inv_sqrt(int64_t n, C* out, const C* x, int nrm2_slot, Scalars& sc, cudaStream_t stream) {
-    scale_inv_sqrt_kernel<C, C><<<stream_grid(n), kThreads, 0, stream>>>(n, out, (C*)nullptr, x, sc.slot + nrm2_slot);
+    scale_inv_sqrt_kernel<C, C><<<stream_grid(n), kThreads, 0, stream>>>(n, out, (C*)nullptr, (C*)nullptr, x, sc.slot + nrm2_slot);
     FDFD_CUDA(cudaGetLastError());
     return FDFD_OK;
 }
 
-int scale_inv_sqrt_dual(int64_t n, double2* out, float2* out_single, const double2* x, int nrm2_slot, Scalars& sc,
-                        cudaStream_t stream) {
-    scale_inv_sqrt_kernel<double2, float2><<<stream_grid(n), kThreads, 0, stream>>>(n, out, out_single, x, sc.slot + nrm2_slot);
+int scale_inv_sqrt_dual(int64_t n, double2* out, float2* out_single, float2* out_single2, const double2* x,
+                        int nrm2_slot, Scalars& sc, cudaStream_t stream) {
+    scale_inv_sqrt_kernel<double2, float2><<<stream_grid(n), kThreads, 0, stream>>>(n, out, out_single, out_single2, x,
+                                                                                     sc.slot + nrm2_slot);
     FDFD_CUDA(cudaGetLastError());
     return FDFD_OK;
 }

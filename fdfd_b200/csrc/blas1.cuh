@@ -51,9 +51,10 @@ int multi_axpy(int64_t n, int k, const CV* V, int64_t ldv, C* w, int s0, double 
 template <typename C>
 int scale_inv_sqrt(int64_t n, C* out, const C* x, int nrm2_slot, Scalars& sc, cudaStream_t stream);
 
-// same, also writing a complex64 copy (compressed Krylov basis)
-int scale_inv_sqrt_dual(int64_t n, double2* out, float2* out_single, const double2* x, int nrm2_slot, Scalars& sc,
-                        cudaStream_t stream);
+// same, also writing a complex64 copy (compressed Krylov basis) and optionally a second complex64 copy (the
+// input buffer of a complex64 preconditioner); `out` may be null when only the complex64 copies are needed
+int scale_inv_sqrt_dual(int64_t n, double2* out, float2* out_single, float2* out_single2, const double2* x,
+                        int nrm2_slot, Scalars& sc, cudaStream_t stream);
 
 // out = x .* d (elementwise complex product; Jacobi preconditioner with d = 1/diag(A))
 template <typename C>

@@ -1,5 +1,6 @@
 // NCCL-backed slab communication (see comm.cuh).  Function pointers are looked up with dlsym.
 #include "comm.cuh"
+#include "p2p.cuh"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -70,7 +71,7 @@ int comm_unique_id(void* id128) {
 
 int comm_create(Comm** out, int nranks, int rank, const void* id128) {
     FDFD_CHECK_ARG(out && nranks >= 1 && rank >= 0 && rank < nranks, "bad communicator shape");
-    Comm* c = new Comm{nranks, rank, nullptr};
+    Comm* c = new Comm{nranks, rank, nullptr, nullptr};
     if (nranks > 1) {
         int st = need_api();
         if (st != FDFD_OK) { delete c; return st; }
@@ -80,6 +81,9 @@ int comm_create(Comm** out, int nranks, int rank, const void* id128) {
         ncclResult_t r = g_api.CommInitRank(&comm, nranks, id, rank);
         if (r != ncclSuccess) { delete c; return nccl_fail(r, "ncclCommInitRank"); }
         c->nccl = comm;
+        // peer-mapped symmetric heap for the data path (collective; falls back to NCCL when unavailable)
+        st = p2p_init(c);
+        if (st != FDFD_OK) { g_api.CommDestroy(comm); delete c; return st; }
     }
     *out = c;
     return FDFD_OK;
@@ -87,12 +91,14 @@ int comm_create(Comm** out, int nranks, int rank, const void* id128) {
 
 void comm_destroy(Comm* c) {
     if (!c) return;
+    p2p_shutdown(c);
     if (c->nccl && g_ok) g_api.CommDestroy((ncclComm_t)c->nccl);
     delete c;
 }
 
 int comm_allreduce_sum(Comm* c, double* buf, int count, cudaStream_t stream) {
     if (!c || c->nranks == 1) return FDFD_OK;
+    if (p2p_enabled(c) && count <= kP2PRedMax) return p2p_allreduce_sum(c, buf, count, stream);
     FDFD_NCCL(g_api.AllReduce(buf, buf, count, ncclDouble, ncclSum, (ncclComm_t)c->nccl, stream));
     return FDFD_OK;
 }
@@ -102,6 +108,10 @@ int comm_allgather(Comm* c, const void* send, void* recv, size_t bytes, cudaStre
         if (send != recv) FDFD_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, stream));
         return FDFD_OK;
     }
+    return comm_allgather_nccl(c, send, recv, bytes, stream);
+}
+
+int comm_allgather_nccl(Comm* c, const void* send, void* recv, size_t bytes, cudaStream_t stream) {
     FDFD_NCCL(g_api.AllGather(send, recv, bytes, ncclChar, (ncclComm_t)c->nccl, stream));
     return FDFD_OK;
 }
@@ -109,10 +119,14 @@ int comm_allgather(Comm* c, const void* send, void* recv, size_t bytes, cudaStre
 int comm_sendrecv(Comm* c, const void* send, int dst, void* recv, int src, size_t bytes,
                   cudaStream_t stream) {
     if (!c || c->nranks == 1) return FDFD_OK;
+    // inside a group the first failure is remembered and the group is always closed
+    ncclResult_t first = ncclSuccess;
+    auto keep = [&](ncclResult_t r) { if (first == ncclSuccess && r != ncclSuccess) first = r; };
     FDFD_NCCL(g_api.GroupStart());
-    if (send && dst >= 0) FDFD_NCCL(g_api.Send(send, bytes, ncclChar, dst, (ncclComm_t)c->nccl, stream));
-    if (recv && src >= 0) FDFD_NCCL(g_api.Recv(recv, bytes, ncclChar, src, (ncclComm_t)c->nccl, stream));
-    FDFD_NCCL(g_api.GroupEnd());
+    if (send && dst >= 0) keep(g_api.Send(send, bytes, ncclChar, dst, (ncclComm_t)c->nccl, stream));
+    if (recv && src >= 0) keep(g_api.Recv(recv, bytes, ncclChar, src, (ncclComm_t)c->nccl, stream));
+    keep(g_api.GroupEnd());
+    if (first != ncclSuccess) return nccl_fail(first, "ncclSend/ncclRecv group");
     return FDFD_OK;
 }
 
@@ -129,12 +143,15 @@ int comm_halo_rows(Comm* c, const void* x, void* halo_south, void* halo_north, i
     // Order matters when both neighbours are the same peer (2 ranks, periodic): NCCL pairs the
     // sends and receives between two ranks in issue order, so "my last row -> north's south ghost"
     // is issued (and received) first on every rank, "my first row -> south's north ghost" second.
+    ncclResult_t first = ncclSuccess;
+    auto keep = [&](ncclResult_t r) { if (first == ncclSuccess && r != ncclSuccess) first = r; };
     FDFD_NCCL(g_api.GroupStart());
-    if (north >= 0) FDFD_NCCL(g_api.Send(last_row, bytes, ncclChar, north, comm, stream));
-    if (south >= 0) FDFD_NCCL(g_api.Recv(halo_south, bytes, ncclChar, south, comm, stream));
-    if (south >= 0) FDFD_NCCL(g_api.Send(first_row, bytes, ncclChar, south, comm, stream));
-    if (north >= 0) FDFD_NCCL(g_api.Recv(halo_north, bytes, ncclChar, north, comm, stream));
-    FDFD_NCCL(g_api.GroupEnd());
+    if (north >= 0) keep(g_api.Send(last_row, bytes, ncclChar, north, comm, stream));
+    if (south >= 0) keep(g_api.Recv(halo_south, bytes, ncclChar, south, comm, stream));
+    if (south >= 0) keep(g_api.Send(first_row, bytes, ncclChar, south, comm, stream));
+    if (north >= 0) keep(g_api.Recv(halo_north, bytes, ncclChar, north, comm, stream));
+    keep(g_api.GroupEnd());
+    if (first != ncclSuccess) return nccl_fail(first, "halo ncclSend/ncclRecv group");
     return FDFD_OK;
 }
 

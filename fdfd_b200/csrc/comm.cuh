@@ -7,9 +7,12 @@
 
 namespace fdfd {
 
+struct P2PHeap;   // p2p.cuh
+
 struct Comm {
     int nranks, rank;
-    void* nccl;   // ncclComm_t
+    void* nccl;             // ncclComm_t (bootstrap, fallback data path)
+    P2PHeap* p2p = nullptr; // peer-mapped symmetric heap (null: NCCL data path)
 };
 
 int comm_unique_id(void* id128);
@@ -24,8 +27,10 @@ int comm_allreduce_sum(Comm* c, double* buf, int count, cudaStream_t stream);
 // (cyclic when `periodic`).  x is the local slab.
 int comm_halo_rows(Comm* c, const void* x, void* halo_south, void* halo_north, int Nx, int Ny,
                    size_t elem, bool periodic, cudaStream_t stream);
-// recv (nranks * bytes) <- concatenation of every rank's `send` (bytes each), rank order
+// recv (nranks * bytes) <- concatenation of every rank's `send` (bytes each), rank order (NCCL; set-up paths and
+// the fallback data path — the hot paths use the peer-memory plans of p2p.cuh)
 int comm_allgather(Comm* c, const void* send, void* recv, size_t bytes, cudaStream_t stream);
+int comm_allgather_nccl(Comm* c, const void* send, void* recv, size_t bytes, cudaStream_t stream);
 // Generic neighbour exchange of arbitrary rows (used once for static coefficient ghosts).
 int comm_sendrecv(Comm* c, const void* send, int dst, void* recv, int src, size_t bytes,
                   cudaStream_t stream);

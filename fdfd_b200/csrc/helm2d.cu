@@ -31,15 +31,77 @@ template <typename C> __host__ __device__ constexpr int default_min_blocks(int m
     return sizeof(C) == 16 ? (mode >= APPLY_JACOBI ? 6 : 7) : (mode >= APPLY_JACOBI ? 8 : 9);
 }
 
-template <typename C, bool TM, int MODE, int MINB = default_min_blocks<C>(MODE)>
+// load an element of the input vector, stored as X (complex64 input of a complex128 operator: the
+// flexible-GMRES corrections are kept in complex64), widened to the arithmetic type C
+template <typename C, typename X> __device__ __forceinline__ C ldx(const X* p) {
+    const X v = *p;
+    return mk<C>((typename real_of<C>::type)v.x, (typename real_of<C>::type)v.y);
+}
+
+// ---- ghost rows over NVLink peer memory (y-slab sharding, P2P = true) -------------------------------
+// The first row of CTAs of a launch PUSHES this rank's two edge rows of x straight into the neighbours'
+// receive buffers (peer-mapped symmetric heap, comm.cu) and raises one flag per column segment; the two
+// rows of tiles that consume ghost rows are issued LAST (the tile index is rotated), so by the time they
+// run the neighbour's push — done by the first CTAs of its own launch — has normally landed and the
+// wait costs nothing.  No NCCL call, no extra launch, no ghost copy.  Receive buffers and flags are double
+// buffered by the parity of a device-resident epoch (a rank can be at most one exchange ahead of its
+// neighbour), which the last participating CTA advances, so the launch is CUDA-graph capturable.
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <typename C, typename X> __device__ __forceinline__ C ldx_cg(const X* p) {
+    const X v = __ldcg(p);
+    return mk<C>((typename real_of<C>::type)v.x, (typename real_of<C>::type)v.y);
+}
+
+template <typename C, bool TM, int MODE, typename X = C, bool P2P = false, int MINB = default_min_blocks<C>(MODE)>
 __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) {
     using R = typename real_of<C>::type;
+    const X* xall = reinterpret_cast<const X*>(a.x);
+    const X* xsouth = reinterpret_cast<const X*>(a.x_south);
+    const X* xnorth = reinterpret_cast<const X*>(a.x_north);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.Nx) return;
     const int Nx = a.Nx, Ny = a.Ny;
-    const int jb = a.row_begin + blockIdx.y * a.rows_per_cta;
+    int tile = blockIdx.y;
+    unsigned int ep = 0, par = 0;
+    bool participant = false;
+    if (P2P) {
+        const int nt = gridDim.y;
+        // pusher row first, ghost-consuming tiles (0 and nt-1) last
+        if (nt >= 3) tile = (int)blockIdx.y == nt - 1 ? nt - 1 : ((int)blockIdx.y == nt - 2 ? 0 : (int)blockIdx.y + 1);
+        participant = blockIdx.y == 0 || tile == 0 || tile == nt - 1;
+        if (participant) {
+            ep = ld_volatile_u32(a.halo.state);
+            par = ep & 1u;
+        }
+        if (blockIdx.y == 0) {
+            if (i < Nx) {
+                if (a.halo.push_north) reinterpret_cast<X*>(a.halo.push_north)[(size_t)par * Nx + i] = xall[(int64_t)(Ny - 1) * Nx + i];
+                if (a.halo.push_south) reinterpret_cast<X*>(a.halo.push_south)[(size_t)par * Nx + i] = xall[i];
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                if (a.halo.flag_push_north) st_release_sys_u32(a.halo.flag_push_north + par * a.halo.segs + blockIdx.x, ep + 1);
+                if (a.halo.flag_push_south) st_release_sys_u32(a.halo.flag_push_south + par * a.halo.segs + blockIdx.x, ep + 1);
+            }
+        }
+        xsouth = a.halo.flag_south ? reinterpret_cast<const X*>(a.halo.rx_south) + (size_t)par * Nx : nullptr;
+        xnorth = a.halo.flag_north ? reinterpret_cast<const X*>(a.halo.rx_north) + (size_t)par * Nx : nullptr;
+    }
+    const int jb = a.row_begin + tile * a.rows_per_cta;
     const int je = min(jb + a.rows_per_cta, a.row_end);
-    if (jb >= je) return;
+    if (i < Nx && jb < je) {
 
     // x-direction neighbour bookkeeping (column constants)
     const bool west_edge = (i == 0), east_edge = (i == Nx - 1);
@@ -60,7 +122,7 @@ __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) 
     const bool west_wall_val = west_edge && !a.bcx;   // x_-1 = 0
     const bool east_wall_val = east_edge && !a.bcx;   // x_N  = 0
 
-    const C* xcol = a.x + i;
+    const X* xcol = xall + i;
     const C* cbcol = a.cb + i;
     // APPLY_SMOOTH: is this column relaxed by y-lines?
     bool in_strip = false;
@@ -74,14 +136,19 @@ __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) 
     // ---- prime the register window --------------------------------------------------------
     C xs, xc, cb_lo;  // cb_lo: TE -> cb[j-1] ; TM -> cb[j]
     if (jb > 0) {
-        xs = xcol[(int64_t)(jb - 1) * Nx];
-    } else if (a.x_south) {
-        xs = a.x_south[i];
+        xs = ldx<C>(xcol + (int64_t)(jb - 1) * Nx);
+    } else if (xsouth) {
+        if (P2P) {
+            while (ld_acquire_sys_u32(a.halo.flag_south + par * a.halo.segs + blockIdx.x) != ep + 1) { }
+            xs = ldx_cg<C>(xsouth + i);
+        } else {
+            xs = ldx<C>(xsouth + i);
+        }
         if (a.south_wrap) xs = cmulc(a.phy, xs);      // conj(phy) * x_{Ny-1}
     } else {
         xs = czero<C>();
     }
-    xc = xcol[(int64_t)jb * Nx];
+    xc = ldx<C>(xcol + (int64_t)jb * Nx);
     if (!TM) {
         if (jb > 0) cb_lo = ld_stream(cbcol + (int64_t)(jb - 1) * Nx);
         else if (a.cb_ghost) cb_lo = a.cb_ghost[i];
@@ -96,11 +163,16 @@ __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) 
         C xn, cb_hi;
         R n_on = 1, s_c2 = 1, n_c2 = 1;
         if (j + 1 < Ny) {
-            xn = xcol[row + Nx];
+            xn = ldx<C>(xcol + row + Nx);
             cb_hi = TM ? ld_stream(cbcol + row + Nx) : ld_stream(cbcol + row);
         } else {
-            if (a.x_north) {
-                xn = a.x_north[i];
+            if (xnorth) {
+                if (P2P) {
+                    while (ld_acquire_sys_u32(a.halo.flag_north + par * a.halo.segs + blockIdx.x) != ep + 1) { }
+                    xn = ldx_cg<C>(xnorth + i);
+                } else {
+                    xn = ldx<C>(xnorth + i);
+                }
                 if (a.north_wrap) { xn = cmul(a.phy, xn); if (TM) n_c2 = a.phy2; }
             } else {
                 xn = czero<C>();
@@ -115,7 +187,7 @@ __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) 
         if (!TM && j == 0 && a.south_wrap) s_c2 = a.phy2;
 
         // x neighbours of the centre row (L1 hits) and the two ca values
-        C xw = a.x[row + iw], xe = a.x[row + ie];
+        C xw = ldx<C>(xall + row + iw), xe = ldx<C>(xall + row + ie);
         if (w_ph) xw = cmulc(a.phx, xw);
         if (e_ph) xe = cmul(a.phx, xe);
         if (west_wall_val) xw = czero<C>();
@@ -173,6 +245,21 @@ __global__ void __launch_bounds__(128, MINB) helm2d_march_kernel(HelmArgs<C> a) 
         xs = xc; xc = xn;
         cb_lo = TM ? cb_hi : cb_hi;
     }
+    }   // active column / non-empty tile
+    if (P2P && participant) {
+        // the last of the CTAs that read the epoch advances it
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int nt = gridDim.y;
+            const unsigned int rows = nt >= 3 ? 3u : (unsigned int)nt;
+            const unsigned int prev = atomicAdd(a.halo.state + 1, 1u);
+            if (prev == rows * gridDim.x - 1) {
+                a.halo.state[1] = 0;
+                __threadfence();
+                a.halo.state[0] = ep + 1;
+            }
+        }
+    }
 }
 
 struct Variant { int bx, ry; };
@@ -198,6 +285,7 @@ HelmArgs<C> helm2d_args(const Helm2D& op, const C* x, C* y, const C* b, const C*
     a.omega = (R)omega;
     a.strip_lo = a.strip_hi = 0; a.line_rhs = nullptr; a.row0 = 0;
     a.row_begin = 0; a.row_end = op.Ny;
+    a.halo = op.halo;
     // ghost rows
     const bool first = op.j0 == 0, last = op.j0 + op.Ny == op.Ny_global;
     const bool sharded = op.Ny != op.Ny_global;
@@ -239,7 +327,12 @@ int helm2d_launch_args(const Helm2D& op, int mode, HelmArgs<C>& a, cudaStream_t 
     if (a.row_end <= a.row_begin) return FDFD_OK;
     dim3 grid(ceil_div(op.Nx, bx), ceil_div(a.row_end - a.row_begin, v.ry));
     FDFD_CHECK_ARG(grid.y <= 65535, "too many row tiles for one launch");
-#define LAUNCH(TMv, MODEv) helm2d_march_kernel<C, TMv, MODEv><<<grid, bx, 0, stream>>>(a)
+    // peer-memory ghost rows: the launch itself exchanges the edge rows of a.x (whole-slab launches only;
+    // APPLY_DINV does not read x)
+    const bool p2p = a.halo.state != nullptr && mode != APPLY_DINV && a.row_begin == 0 && a.row_end == op.Ny;
+    if (!p2p) a.halo = HaloP2P();
+#define LAUNCH(TMv, MODEv) do { if (p2p) helm2d_march_kernel<C, TMv, MODEv, C, true><<<grid, bx, 0, stream>>>(a); \
+                                else helm2d_march_kernel<C, TMv, MODEv><<<grid, bx, 0, stream>>>(a); } while (0)
 #define LAUNCH_MODE(MODEv) do { if (TM) LAUNCH(true, MODEv); else LAUNCH(false, MODEv); } while (0)
     switch (mode) {
         case APPLY_AX: LAUNCH_MODE(APPLY_AX); break;
@@ -281,7 +374,7 @@ template int helm2d_launch_args<float2>(const Helm2D&, int, HelmArgs<float2>&, c
 // TE needs cb row j0-1 (the south rank's last row), TM needs cb row j0+Ny (the north rank's first).
 int helm2d_setup_sharding(Helm2D& op, cudaStream_t st) {
     op.halo_south = op.halo_north = op.cb_ghost_buf = nullptr;
-    op.comm_stream = nullptr; op.ev_x = op.ev_h = nullptr;
+    op.halo = HaloP2P();
     if (op.Ny == op.Ny_global) return FDFD_OK;
     FDFD_CHECK_ARG(op.comm && op.comm->nranks > 1, "sharded operator needs a communicator");
     const size_t rb = (size_t)op.Nx * op.elem();
@@ -291,13 +384,11 @@ int helm2d_setup_sharding(Helm2D& op, cudaStream_t st) {
     FDFD_CUDA(cudaMemsetAsync(op.halo_south, 0, rb, st));
     FDFD_CUDA(cudaMemsetAsync(op.halo_north, 0, rb, st));
     FDFD_CUDA(cudaMemsetAsync(op.cb_ghost_buf, 0, rb, st));
-    FDFD_CUDA(cudaStreamCreateWithFlags(&op.comm_stream, cudaStreamNonBlocking));
-    FDFD_CUDA(cudaEventCreateWithFlags(&op.ev_x, cudaEventDisableTiming));
-    FDFD_CUDA(cudaEventCreateWithFlags(&op.ev_h, cudaEventDisableTiming));
     const int P = op.comm->nranks, r = op.comm->rank;
     const bool per = op.bcy == FDFD_BC_BLOCH;
     const int south = r > 0 ? r - 1 : (per ? P - 1 : -1);
     const int north = r < P - 1 ? r + 1 : (per ? 0 : -1);
+    if (p2p_enabled(op.comm)) FDFD_TRY(p2p_halo_create(op.comm, op.Nx, south, north, &op.halo, op.halo_offs, st));
     if (op.pol == FDFD_POL_TE)
         return comm_sendrecv(op.comm, (const char*)op.cb + (size_t)(op.Ny - 1) * rb, north, op.cb_ghost_buf, south, rb, st);
     return comm_sendrecv(op.comm, op.cb, south, op.cb_ghost_buf, north, rb, st);
@@ -305,15 +396,16 @@ int helm2d_setup_sharding(Helm2D& op, cudaStream_t st) {
 
 void helm2d_release_sharding(Helm2D& op) {
     cudaFree(op.halo_south); cudaFree(op.halo_north); cudaFree(op.cb_ghost_buf);
-    if (op.comm_stream) cudaStreamDestroy(op.comm_stream);
-    if (op.ev_x) cudaEventDestroy(op.ev_x);
-    if (op.ev_h) cudaEventDestroy(op.ev_h);
+    if (op.halo.state) p2p_halo_destroy(op.comm, &op.halo, op.halo_offs);
     op.halo_south = op.halo_north = op.cb_ghost_buf = nullptr;
-    op.comm_stream = nullptr; op.ev_x = op.ev_h = nullptr;
 }
 
+// Stand-alone ghost-row exchange into op.halo_south / op.halo_north (consumers other than the stencil
+// kernel: the prolongation reads one coarse row beyond the slab).
 int helm2d_halo_exchange(Helm2D& op, const void* x, cudaStream_t stream) {
     if (op.Ny == op.Ny_global) return FDFD_OK;
+    if (op.halo.state)
+        return p2p_halo_exchange(op.halo, x, op.halo_south, op.halo_north, op.Nx, op.Ny, op.elem(), stream);
     return comm_halo_rows(op.comm, x, op.halo_south, op.halo_north, op.Nx, op.Ny, op.elem(),
                           op.bcy == FDFD_BC_BLOCH, stream);
 }
@@ -322,29 +414,47 @@ template <typename C>
 static int helm2d_apply_t(Helm2D& op, int mode, const C* x, C* y, const C* b, double omega, cudaStream_t stream) {
     HelmArgs<C> a = helm2d_args<C>(op, x, y, b, (const C*)op.ca, (const C*)op.cb, (const C*)op.cd,
                                    op.shift_re, op.shift_im, omega);
-    const bool sharded = op.Ny != op.Ny_global;
-    const int edge = 8;                       // rows per boundary launch (one tile of the default shape)
-    // Measured on 2 x B200 (4096^2 per rank): the fork/join below costs ~28 us per apply against
-    // ~10 us for the serial NCCL exchange it hides, so it only pays for slabs whose exchange is slow
-    // relative to the launch overhead; it stays off unless FDFD_OVERLAP_HALO=1.
-    static const bool overlap = getenv("FDFD_OVERLAP_HALO") && atoi(getenv("FDFD_OVERLAP_HALO")) != 0;
-    if (!sharded || !overlap || !op.comm_stream || op.Ny < 4 * edge) {
-        FDFD_TRY(helm2d_halo_exchange(op, x, stream));
-        return helm2d_launch_args<C>(op, mode, a, stream);
-    }
-    // y-slab: exchange the two ghost rows on a side stream while the interior rows (which do not
-    // read them) are computed; the two boundary tiles are launched once the ghosts have arrived
-    FDFD_CUDA(cudaEventRecord(op.ev_x, stream));
-    FDFD_CUDA(cudaStreamWaitEvent(op.comm_stream, op.ev_x, 0));
-    FDFD_TRY(helm2d_halo_exchange(op, x, op.comm_stream));
-    FDFD_CUDA(cudaEventRecord(op.ev_h, op.comm_stream));
-    a.row_begin = edge; a.row_end = op.Ny - edge;
-    FDFD_TRY(helm2d_launch_args<C>(op, mode, a, stream));
-    FDFD_CUDA(cudaStreamWaitEvent(stream, op.ev_h, 0));
-    a.row_begin = 0; a.row_end = edge;
-    FDFD_TRY(helm2d_launch_args<C>(op, mode, a, stream));
-    a.row_begin = op.Ny - edge; a.row_end = op.Ny;
+    // sharded: with a peer-mapped heap the launch exchanges its own ghost rows, else NCCL does it first
+    if (op.Ny != op.Ny_global && !op.halo.state) FDFD_TRY(helm2d_halo_exchange(op, x, stream));
     return helm2d_launch_args<C>(op, mode, a, stream);
+}
+
+// y = A x for a complex128 operator whose input vector is stored in complex64 (72 B/pt instead of 80)
+int helm2d_apply_x32(Helm2D& op, const float2* x, double2* y, cudaStream_t stream) {
+    FDFD_CHECK_ARG(op.dtype == FDFD_C128, "mixed-input apply needs a complex128 operator");
+    using C = double2;
+    HelmArgs<C> a = helm2d_args<C>(op, reinterpret_cast<const C*>(x), y, nullptr, (const C*)op.ca, (const C*)op.cb,
+                                   (const C*)op.cd, op.shift_re, op.shift_im, 0.0);
+    const bool sharded = op.Ny != op.Ny_global;
+    if (!sharded && op.bcy == FDFD_BC_BLOCH) {       // the wrap rows are addressed in float2 elements
+        a.x_south = reinterpret_cast<const C*>(x + (int64_t)(op.Ny - 1) * op.Nx);
+        a.x_north = reinterpret_cast<const C*>(x);
+    }
+    const bool p2p = sharded && op.halo.state != nullptr;
+    if (sharded && !p2p)
+        FDFD_TRY(comm_halo_rows(op.comm, x, op.halo_south, op.halo_north, op.Nx, op.Ny, sizeof(float2),
+                                op.bcy == FDFD_BC_BLOCH, stream));
+    Variant v = kVariants[(op.variant >= 0 && op.variant < kNumVariants) ? op.variant : 0];
+    if (op.variant == 0) {
+        const int64_t n = (int64_t)op.Nx * op.Ny;
+        if (n < ((int64_t)1 << 20)) v = Variant{64, 2};
+        else if (n < ((int64_t)1 << 22)) v = Variant{128, 4};
+    }
+    int bx = v.bx;
+    while (bx > 32 && bx / 2 >= op.Nx) bx /= 2;
+    a.rows_per_cta = v.ry;
+    dim3 grid(ceil_div(op.Nx, bx), ceil_div(op.Ny, v.ry));
+    FDFD_CHECK_ARG(grid.y <= 65535, "too many row tiles for one launch");
+    if (p2p) {
+        if (op.pol == FDFD_POL_TM) helm2d_march_kernel<C, true, APPLY_AX, float2, true><<<grid, bx, 0, stream>>>(a);
+        else helm2d_march_kernel<C, false, APPLY_AX, float2, true><<<grid, bx, 0, stream>>>(a);
+    } else {
+        a.halo = HaloP2P();
+        if (op.pol == FDFD_POL_TM) helm2d_march_kernel<C, true, APPLY_AX, float2><<<grid, bx, 0, stream>>>(a);
+        else helm2d_march_kernel<C, false, APPLY_AX, float2><<<grid, bx, 0, stream>>>(a);
+    }
+    FDFD_CUDA(cudaGetLastError());
+    return FDFD_OK;
 }
 
 int helm2d_apply(Helm2D& op, int mode, const void* x, void* y, const void* b, double omega,

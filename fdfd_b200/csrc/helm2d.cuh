@@ -1,6 +1,7 @@
 // K2 — matrix-free 5-point complex Helmholtz / curl-curl operator on a Yee grid (slab).
 #pragma once
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace fdfd {
 
@@ -42,7 +43,8 @@ struct HelmArgs {
     int strip_lo, strip_hi;
     C* line_rhs;         // workspace [row][line], line = strip column index, row stride = strip_lo + strip_hi
     int row0;            // global row of local row 0 (sharded lines)
-    int row_begin, row_end;  // rows this launch covers (halo overlap splits a pass into 3 launches)
+    int row_begin, row_end;  // rows this launch covers (the pipelined host-buffer apply works in row chunks)
+    HaloP2P halo;            // peer-memory ghost rows (sharded operators with a mapped heap; see helm2d.cu)
 };
 
 struct Helm2D {
@@ -55,11 +57,11 @@ struct Helm2D {
     const void *ca, *cb, *cd;
     Comm* comm;
     int variant;
-    // ghost rows for sharded operation (device, Nx elements each)
+    // ghost rows for sharded operation (device, Nx elements each): landing buffers of the NCCL exchange and
+    // of the stand-alone peer-memory exchange (the stencil kernel itself reads the parity buffers of `halo`)
     void *halo_south, *halo_north, *cb_ghost_buf;
-    // halo exchange overlapped with the interior rows: side stream + fork/join events
-    cudaStream_t comm_stream;
-    cudaEvent_t ev_x, ev_h;
+    HaloP2P halo;            // peer-memory exchange state (halo.state == null: NCCL path)
+    size_t halo_offs[4];     // its allocations in the symmetric heap
     // scratch for *_host entry points
     void *h_x, *h_y;
     int64_t n_local() const { return (int64_t)Nx * Ny; }
@@ -81,6 +83,9 @@ int helm2d_launch(const Helm2D& op, int mode, const C* x, C* y, const C* b,
 int helm2d_halo_exchange(Helm2D& op, const void* x, cudaStream_t stream);
 int helm2d_setup_sharding(Helm2D& op, cudaStream_t stream);
 void helm2d_release_sharding(Helm2D& op);
+
+// y = A x for a complex128 operator with the input vector stored in complex64 (APPLY_AX only)
+int helm2d_apply_x32(Helm2D& op, const float2* x, double2* y, cudaStream_t stream);
 
 // y = A x including halo exchange when sharded (dispatches on dtype).
 int helm2d_apply(Helm2D& op, int mode, const void* x, void* y, const void* b, double omega,

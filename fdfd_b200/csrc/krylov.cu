@@ -347,23 +347,30 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
     // the residual is recomputed in complex128 at every restart.  Z (the corrections) stays complex128.
     constexpr bool kCanCompress = std::is_same<C, double2>::value;
     const bool sb = kCanCompress && o.basis_single && M != nullptr;
+    // ... and with a complex64 preconditioner the corrections Z are complex64 as well: FGMRES applies A to
+    // the STORED z_j (K2 reads complex64 x directly), so A Z = V H holds for the rounded vectors and the
+    // update x += Z y (accumulated in complex128) is exact for them — no precision conversion passes at all,
+    // and the normalisation kernel writes the next basis vector straight into the preconditioner's input
+    const bool zs = sb && A.has_apply_x32() && M->single_io();
     DeviceBuf bV, bZ, bw, bvc;
     const size_t vbytes = (sb ? sizeof(float2) : sizeof(C)) * (size_t)n * (m + 1);
     size_t cursor = 0;
     if (arena) {
         // basis / correction vectors of a restart cycle: tens of GB at 4096^2 and beyond; kept in the
         // operator handle between solves (cudaMalloc / cudaFree of that much memory costs 0.1-0.8 s)
-        const size_t need = vbytes + bytes * ((sb ? 1 : 0) + (M ? m : 0) + 1) + 256 * 8;
+        const size_t need = vbytes + bytes * ((sb && !zs ? 1 : 0) + 1) + (M ? (zs ? bytes / 2 : bytes) * m : 0) + 256 * 8;
         FDFD_TRY(arena->ensure(need));
     }
     FDFD_TRY(bV.alloc(vbytes, arena, cursor));
-    if (sb) FDFD_TRY(bvc.alloc(bytes, arena, cursor));
-    if (M) FDFD_TRY(bZ.alloc(bytes * m, arena, cursor));
+    if (sb && !zs) FDFD_TRY(bvc.alloc(bytes, arena, cursor));
+    if (M) FDFD_TRY(bZ.alloc((zs ? bytes / 2 : bytes) * m, arena, cursor));
     FDFD_TRY(bw.alloc(bytes, arena, cursor));
     C* V = (C*)bV.p;
     float2* Vs = (float2*)bV.p;    // the same storage seen as the compressed basis
     C* vcur = (C*)bvc.p;           // complex128 copy of the newest basis vector (input of M)
     C* Z = M ? (C*)bZ.p : V;
+    float2* Zs = (float2*)bZ.p;    // the corrections seen as complex64 vectors (zs)
+    float2* pin = zs ? M->single_input() : nullptr;   // preconditioner input filled by the normalisation
     C* w = (C*)bw.p;
     Comm* comm = A.comm;
     double2 hbuf[2];
@@ -382,10 +389,19 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
 
     // one Arnoldi step, fully asynchronous
     auto enqueue = [&](int j) -> int {
-        C* vj = sb ? vcur : V + (int64_t)j * n;
-        C* zj = Z + (int64_t)j * n;
-        if (M) { FDFD_TRY(M->apply(vj, zj, stream)); ++info.precond_applies; }
-        FDFD_TRY(A.apply(zj, w, stream)); ++info.op_applies;
+        if constexpr (kCanCompress) {
+            if (zs) {
+                float2* zj = Zs + (int64_t)j * n;
+                FDFD_TRY(M->apply_single(pin ? nullptr : Vs + (int64_t)j * n, zj, stream)); ++info.precond_applies;
+                FDFD_TRY(A.apply_x32(zj, (double2*)w, stream)); ++info.op_applies;
+            }
+        }
+        if (!zs) {
+            C* vj = sb ? vcur : V + (int64_t)j * n;
+            C* zj = Z + (int64_t)j * n;
+            if (M) { FDFD_TRY(M->apply(vj, zj, stream)); ++info.precond_applies; }
+            FDFD_TRY(A.apply(zj, w, stream)); ++info.op_applies;
+        }
         // classical Gram-Schmidt (optionally a second pass), fused multi-vector kernels
         for (int pass = 0; pass < passes; ++pass) {
             const bool last = pass == passes - 1;
@@ -409,7 +425,7 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
         FDFD_CUDA(cudaEventRecord(hs.ev[j], stream));
         // next basis vector (a zero norm gives a non-finite vector: that step is discarded by the host)
         if constexpr (kCanCompress) {
-            if (sb) FDFD_TRY(scale_inv_sqrt_dual(n, vcur, Vs + (int64_t)(j + 1) * n, w, S_TMP0, sc, stream));
+            if (sb) FDFD_TRY(scale_inv_sqrt_dual(n, zs ? nullptr : vcur, Vs + (int64_t)(j + 1) * n, pin, w, S_TMP0, sc, stream));
         }
         if (!sb) FDFD_TRY(scale_inv_sqrt<C>(n, V + (int64_t)(j + 1) * n, w, S_TMP0, sc, stream));
         return FDFD_OK;
@@ -437,7 +453,7 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
         if (!std::isfinite(beta)) { status = FDFD_ERR_BREAKDOWN; set_error("FGMRES: non-finite residual"); break; }
         if (relres <= o.rtol || it >= o.maxit) break;
         if constexpr (kCanCompress) {
-            if (sb) FDFD_TRY(scale_inv_sqrt_dual(n, vcur, Vs, w, S_RR, sc, stream));
+            if (sb) FDFD_TRY(scale_inv_sqrt_dual(n, zs ? nullptr : vcur, Vs, pin, w, S_RR, sc, stream));
         }
         if (!sb) FDFD_TRY(scale_inv_sqrt<C>(n, V, w, S_RR, sc, stream));
         int k = 0;            // valid columns of this cycle
@@ -471,7 +487,10 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
         // y = R^-1 g, x += Z y
         if (k > 0) {
             fgmres_ysolve_kernel<<<1, 32, 0, stream>>>(k, m, hs.G, sc.slot + S_H0);
-            FDFD_TRY(multi_axpy<C>(n, k, Z, n, x, S_H0, 1.0, -1, sc, stream));
+            if constexpr (kCanCompress) {
+                if (zs) FDFD_TRY((multi_axpy<float2, double2>(n, k, Zs, n, (double2*)x, S_H0, 1.0, -1, sc, stream)));
+            }
+            if (!zs) FDFD_TRY(multi_axpy<C>(n, k, Z, n, x, S_H0, 1.0, -1, sc, stream));
         }
         FDFD_CUDA(cudaStreamSynchronize(stream));
         if (k == 0) { status = FDFD_ERR_BREAKDOWN; set_error("FGMRES: breakdown in the first step of a cycle"); break; }

@@ -14,6 +14,10 @@ struct LinOp {
     virtual int64_t n_local() const = 0;
     virtual int apply(const void* x, void* y, cudaStream_t stream) = 0;                         // y = A x
     virtual int residual(const void* x, void* r, const void* b, cudaStream_t stream) = 0;       // r = b - A x
+    // y = A x with x stored in complex64 and a complex128 operator (flexible-GMRES corrections kept in
+    // complex64); operators without such a kernel report false from has_apply_x32()
+    virtual bool has_apply_x32() const { return false; }
+    virtual int apply_x32(const float2*, double2*, cudaStream_t) { return FDFD_ERR_STATE; }
     size_t elem() const { return dtype == FDFD_C128 ? 16 : 8; }
 };
 
@@ -27,12 +31,20 @@ struct HelmOp : LinOp {
     int residual(const void* x, void* r, const void* b, cudaStream_t stream) override {
         return helm2d_apply(A, APPLY_RESID, x, r, b, 0.0, stream);
     }
+    bool has_apply_x32() const override { return A.dtype == FDFD_C128; }
+    int apply_x32(const float2* x, double2* y, cudaStream_t stream) override { return helm2d_apply_x32(A, x, y, stream); }
 };
 
 // z = M^-1 v.  Implementations: identity, Jacobi (1/diag), shifted-Laplacian multigrid (mg.cu).
 struct Precond {
     virtual ~Precond() {}
     virtual int apply(const void* v, void* z, cudaStream_t stream) = 0;
+    // complex64 in / complex64 out interface of a preconditioner that runs in complex64 inside a complex128
+    // solve (mixed-precision multigrid): single_input() is the buffer the caller may fill directly with the
+    // complex64 vector (null = none); apply_single(null, z) then uses that buffer's content
+    virtual bool single_io() const { return false; }
+    virtual float2* single_input() { return nullptr; }
+    virtual int apply_single(const float2*, float2*, cudaStream_t) { return FDFD_ERR_STATE; }
     int64_t applies = 0;
 };
 

@@ -95,7 +95,10 @@ struct LineSet {
     C *ifg_all = nullptr; // [nranks][nl][2P] gathered
     C *ifu = nullptr;     // [nl][2Ptot] interface solution (replicated)
     C *tips = nullptr, *tips_all = nullptr;  // spike tips [nl][P][4] / [nranks][nl][P][4]
+    GatherPlan* plan = nullptr;   // peer-memory all-gather of the interface values (sharded y-lines)
+    Comm* plan_comm = nullptr;
     void release() {
+        if (plan) { p2p_gather_destroy(plan_comm, plan); plan = nullptr; }
         cudaFree(fl); cudaFree(fc); cudaFree(fip); cudaFree(sv); cudaFree(sw); cudaFree(rinv);
         cudaFree(g); cudaFree(ifg); cudaFree(ifu); cudaFree(ifg_all); cudaFree(tips); cudaFree(tips_all);
         fl = fc = fip = sv = sw = rinv = g = ifg = ifu = ifg_all = tips = tips_all = nullptr;
@@ -620,6 +623,8 @@ struct MGPrecond : Precond {
     BicgWorkspace coarse_ws;
     int nlev = 0;       // levels of the cycle = L[0 .. nlev)
     int rep = -1;       // index in L of the replicated (unsharded) copy of the coarsest level, or -1
+    GatherPlan* rep_plan = nullptr;   // peer-memory all-gather of the coarse right-hand side
+    Comm* rep_comm = nullptr;
     // CUDA-graph replay of the cycle, one executable graph per (input, output) pointer pair
     cudaStream_t gstream = nullptr;
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -646,9 +651,11 @@ struct MGPrecond : Precond {
 
     ~MGPrecond() override {
         if (graph) cudaGraphExecDestroy(graph);
+        if (rep_plan) p2p_gather_destroy(rep_comm, rep_plan);
         cudaFree(in_buf);
         cudaFree(zero_buf);
         cudaFree(coarse_partials); cudaFree(coarse_bar); cudaFree(coarse_extra[0]); cudaFree(coarse_extra[1]);
+        cudaFree(coarse_k5); cudaFree(coarse_relax);
         if (gstream) cudaStreamDestroy(gstream);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
@@ -711,6 +718,10 @@ struct MGPrecond : Precond {
         // every rank needs the spike tips of all chunks to build (and invert) the interface system
         FDFD_TRY(comm_allgather(s.nranks > 1 ? comm : nullptr, s.tips, s.tips_all,
                                 (size_t)s.nl * s.P * 4 * sizeof(C), st));
+        if (s.nranks > 1 && p2p_enabled(comm)) {
+            s.plan_comm = comm;
+            FDFD_TRY(p2p_gather_create(comm, nloc * sizeof(C), &s.plan, st));
+        }
         if (s.Ptot > 1) {
             const size_t smem = (size_t)4 * s.Ptot * s.Ptot * sizeof(C);
             FDFD_CUDA(cudaFuncSetAttribute(line_reduced_inverse_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -725,8 +736,9 @@ struct MGPrecond : Precond {
         LineView<C> v = view(s, lv.op.Nx, lv.op.Ny);
         line_local_solve_kernel<C><<<(s.nl * s.P + 63) / 64, 64, 0, st>>>(v);
         if (s.Ptot > 1) {
-            FDFD_TRY(comm_allgather(s.nranks > 1 ? lv.op.comm : nullptr, s.ifg, s.ifg_all,
-                                    (size_t)s.nl * 2 * s.P * sizeof(C), st));
+            if (s.plan) FDFD_TRY(p2p_allgather(s.plan, s.ifg, s.ifg_all, (size_t)s.nl * 2 * s.P * sizeof(C), st));
+            else FDFD_TRY(comm_allgather(s.nranks > 1 ? lv.op.comm : nullptr, s.ifg, s.ifg_all,
+                                         (size_t)s.nl * 2 * s.P * sizeof(C), st));
             line_reduced_kernel<C><<<(int)(((int64_t)s.nl * 2 * s.Ptot * 32 + 255) / 256), 256, 0, st>>>(v);
         }
         const int64_t tot = (int64_t)s.nl * s.len;
@@ -744,7 +756,7 @@ struct MGPrecond : Precond {
     int smooth(int l, cudaStream_t st) {
         using R = typename real_of<C>::type;
         Level<C>& lv = L[l];
-        FDFD_TRY(helm2d_halo_exchange(lv.op, lv.x, st));
+        if (!lv.op.halo.state) FDFD_TRY(helm2d_halo_exchange(lv.op, lv.x, st));   // peer memory: inside the launch
         HelmArgs<C> a = helm2d_args<C>(lv.op, lv.x, lv.t, lv.b, lv.ca, lv.cb, lv.cd, shift_re, shift_im, o.mg_omega);
         a.strip_lo = lv.ylines.lo; a.strip_hi = lv.ylines.hi; a.line_rhs = lv.ylines.g; a.row0 = 0;
         FDFD_TRY(helm2d_launch_args<C>(lv.op, APPLY_SMOOTH, a, st));
@@ -795,6 +807,7 @@ struct MGPrecond : Precond {
     double* coarse_partials = nullptr;
     unsigned int* coarse_bar = nullptr;
     C* coarse_extra[2] = {nullptr, nullptr};
+    C *coarse_k5 = nullptr, *coarse_relax = nullptr;
     int coarse_grid = 0;
     bool coarse_ready = false;
     static size_t coarse_smem_bytes(const Level<C>& lv) {
@@ -832,6 +845,16 @@ struct MGPrecond : Precond {
         FDFD_CUDA(cudaMemset(coarse_bar, 0, 4 * sizeof(unsigned int)));
         FDFD_CUDA(cudaMalloc(&coarse_extra[0], bytes));
         FDFD_CUDA(cudaMalloc(&coarse_extra[1], bytes));
+        FDFD_CUDA(cudaMalloc(&coarse_k5, 5 * bytes));
+        FDFD_CUDA(cudaMalloc(&coarse_relax, bytes));
+        {
+            using R = typename real_of<C>::type;
+            const int64_t n = lv.op.n_local();
+            const int blocks = (int)((n + 255) / 256);
+            if (TM()) coarse_coefs_kernel<C, true><<<blocks, 256>>>(lv.op.Nx, lv.op.Ny, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), (R)o.mg_omega, coarse_k5, coarse_relax);
+            else coarse_coefs_kernel<C, false><<<blocks, 256>>>(lv.op.Nx, lv.op.Ny, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), (R)o.mg_omega, coarse_k5, coarse_relax);
+            FDFD_CUDA(cudaGetLastError());
+        }
         coarse_ready = true;
         return FDFD_OK;
     }
@@ -849,6 +872,7 @@ struct MGPrecond : Precond {
         a.phf = coarse_extra[0]; a.shf = coarse_extra[1];
         a.yl = view(lv.ylines, lv.op.Nx, lv.op.Ny);
         a.xl = view(lv.xlines, lv.op.Nx, lv.op.Ny);
+        a.k5 = coarse_k5; a.relax = coarse_relax;
         a.partials = coarse_partials;
         a.bar = coarse_bar;
         a.owners = std::max(lv.ylines.nl, lv.xlines.nl);
@@ -870,7 +894,8 @@ struct MGPrecond : Precond {
             // distributed BiCGSTAB; each rank keeps its own rows of the result.
             Level<C>& R = L[rep];
             const size_t loc = (size_t)lv.op.n_local() * sizeof(C);
-            FDFD_TRY(comm_allgather(lv.op.comm, lv.b, R.b, loc, st));
+            if (rep_plan) FDFD_TRY(p2p_allgather(rep_plan, lv.b, R.b, loc, st));
+            else FDFD_TRY(comm_allgather(lv.op.comm, lv.b, R.b, loc, st));
             if (coarse_persistent_ok(R)) {
                 FDFD_TRY(coarse_persistent(R, R.b, R.r, st));
             } else {
@@ -908,7 +933,7 @@ struct MGPrecond : Precond {
             return FDFD_OK;
         }
         for (int s = 0; s < o.mg_pre; ++s) FDFD_TRY(smooth(l, st));
-        FDFD_TRY(helm2d_halo_exchange(lv.op, lv.x, st));
+        if (!lv.op.halo.state) FDFD_TRY(helm2d_halo_exchange(lv.op, lv.x, st));
         FDFD_TRY(helm2d_launch<C>(lv.op, APPLY_RESID, lv.x, lv.r, lv.b, lv.ca, lv.cb, lv.cd, shift_re, shift_im, 0.0, st));
         Level<C>& lc = L[l + 1];
         dim3 bt(32, 8);
@@ -941,6 +966,37 @@ struct MGPrecond : Precond {
         return cycle(0, st);
     }
 
+    // graph mode with the right-hand side already sitting in in_buf (written there by the caller)
+    int apply_from_input(void* z, cudaStream_t st) {
+        ++applies;
+        FDFD_TRY(ensure_graph());
+        const size_t bytes = (size_t)L[0].op.n_local() * sizeof(C);
+        FDFD_CUDA(cudaEventRecord(ev_in, st));
+        FDFD_CUDA(cudaStreamWaitEvent(gstream, ev_in, 0));
+        FDFD_CUDA(cudaGraphLaunch(graph, gstream));
+        FDFD_CUDA(cudaEventRecord(ev_out, gstream));
+        FDFD_CUDA(cudaStreamWaitEvent(st, ev_out, 0));
+        FDFD_CUDA(cudaMemcpyAsync(z, out_ptr, bytes, cudaMemcpyDeviceToDevice, st));
+        return FDFD_OK;
+    }
+
+    int ensure_graph() {
+        if (graph) return FDFD_OK;
+        // capture once: the cycle reads its right-hand side from in_buf and its kernel
+        // sequence / buffer roles are identical for every application
+        cudaGraph_t g = nullptr;
+        FDFD_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeRelaxed));
+        int s = run_cycle(in_buf, gstream);
+        cudaError_t e = cudaStreamEndCapture(gstream, &g);
+        if (s != FDFD_OK) { if (g) cudaGraphDestroy(g); return s; }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+        e = cudaGraphInstantiate(&graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { graph = nullptr; return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+        out_ptr = L[0].x;
+        return FDFD_OK;
+    }
+
     int apply(const void* v, void* z, cudaStream_t st) override {
         ++applies;
         Level<C>& l0 = L[0];
@@ -950,20 +1006,7 @@ struct MGPrecond : Precond {
             FDFD_CUDA(cudaMemcpyAsync(z, l0.x, bytes, cudaMemcpyDeviceToDevice, st));
             return FDFD_OK;
         }
-        if (!graph) {
-            // capture once: the cycle reads its right-hand side from in_buf and its kernel
-            // sequence / buffer roles are identical for every application
-            cudaGraph_t g = nullptr;
-            FDFD_CUDA(cudaStreamBeginCapture(gstream, cudaStreamCaptureModeRelaxed));
-            int s = run_cycle(in_buf, gstream);
-            cudaError_t e = cudaStreamEndCapture(gstream, &g);
-            if (s != FDFD_OK) { if (g) cudaGraphDestroy(g); return s; }
-            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
-            e = cudaGraphInstantiate(&graph, g, 0);
-            cudaGraphDestroy(g);
-            if (e != cudaSuccess) { graph = nullptr; return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
-            out_ptr = l0.x;
-        }
+        FDFD_TRY(ensure_graph());
         FDFD_CUDA(cudaMemcpyAsync(in_buf, v, bytes, cudaMemcpyDeviceToDevice, st));
         FDFD_CUDA(cudaEventRecord(ev_in, st));
         FDFD_CUDA(cudaStreamWaitEvent(gstream, ev_in, 0));
@@ -1006,14 +1049,24 @@ struct MGPrecond : Precond {
             FDFD_CUDA(cudaMalloc(&cur.x, bytes)); FDFD_CUDA(cudaMalloc(&cur.r, bytes)); FDFD_CUDA(cudaMalloc(&cur.t, bytes));
             cur.x0 = cur.x; cur.r0 = cur.r; cur.t0 = cur.t;
             if (L.size() > 1) FDFD_CUDA(cudaMalloc(&cur.b, bytes));
+            // evaluated on quantities that are equal on every rank (a rank-dependent failure inside the
+            // collective set-up below would leave the other ranks waiting)
+            FDFD_CHECK_ARG(!(sharded && (ly_lo >= Ny || ly_hi >= Ny)), "absorbing-layer rows exceed the rows of one slab");
             FDFD_TRY(setup_lines(cur, cur.ylines, 0, lx_lo, lx_hi, st));
             FDFD_TRY(setup_lines(cur, cur.xlines, 1, cur.first ? ly_lo : 0, cur.last ? ly_hi : 0, st));
             const bool max_levels = opts.mg_levels > 0 && (int)L.size() >= opts.mg_levels;
             const int Nyg = cur.op.Ny_global;
             const double s_next = std::min(cur.op.sx, cur.op.sy) / 4.0;
             const double kh_next = s_next > 0 ? 1.0 / std::sqrt(std::fabs(s_next)) : 1e30;
-            if (max_levels || (Nx & 1) || (Ny & 1) || (cur.op.j0 & 1) || Nx / 2 < min_n || Nyg / 2 < min_n ||
-                kh_next > kh_max) break;
+            const bool odd = (Nx & 1) || (Ny & 1) || (cur.op.j0 & 1);
+            if (max_levels || Nx / 2 < min_n || Nyg / 2 < min_n || kh_next > kh_max) break;
+            if (odd) {
+                // (same decision on every rank: equal slabs)
+                if (L.size() == 1)
+                    fprintf(stderr, "[fdfd] warning: %d x %d rows per slab cannot be halved: the multigrid hierarchy has a "
+                                    "single level and degrades to its coarse-level solver (use even slab heights)\n", Nx, Ny);
+                break;
+            }
             Level<C> c;
             c.op = cur.op;
             c.op.Nx = Nx / 2; c.op.Ny = Ny / 2; c.op.Ny_global = Nyg / 2; c.op.j0 = cur.op.j0 / 2;
@@ -1047,7 +1100,7 @@ struct MGPrecond : Precond {
             R.op = c.op;
             R.op.Ny = c.op.Ny_global; R.op.j0 = 0; R.op.comm = nullptr;
             R.op.halo_south = R.op.halo_north = R.op.cb_ghost_buf = nullptr;
-            R.op.comm_stream = nullptr; R.op.ev_x = R.op.ev_h = nullptr;
+            R.op.halo = HaloP2P();
             R.first = R.last = true; R.delta = c.delta;
             const size_t loc = (size_t)c.op.n_local() * sizeof(C), full = (size_t)R.op.n_local() * sizeof(C);
             FDFD_CUDA(cudaMalloc(&R.ca, full)); FDFD_CUDA(cudaMalloc(&R.cb, full)); FDFD_CUDA(cudaMalloc(&R.cd, full));
@@ -1064,6 +1117,10 @@ struct MGPrecond : Precond {
             for (int q = 1; q < nlev; ++q) { wx_lo = (wx_lo + 1) / 2; wx_hi = (wx_hi + 1) / 2; wy_lo = (wy_lo + 1) / 2; wy_hi = (wy_hi + 1) / 2; }
             L.push_back(R);
             rep = (int)L.size() - 1;
+            if (p2p_enabled(c.op.comm)) {
+                rep_comm = c.op.comm;
+                FDFD_TRY(p2p_gather_create(rep_comm, loc, &rep_plan, st));
+            }
             FDFD_TRY(setup_lines(L[rep], L[rep].ylines, 0, wx_lo, wx_hi, st));
             FDFD_TRY(setup_lines(L[rep], L[rep].xlines, 1, wy_lo, wy_hi, st));
         }
@@ -1122,7 +1179,7 @@ struct MixedMGPrecond : Precond {
         A32.dtype = FDFD_C64;
         A32.ca = ca; A32.cb = cb; A32.cd = cd;
         A32.halo_south = A32.halo_north = A32.cb_ghost_buf = nullptr;
-        A32.comm_stream = nullptr; A32.ev_x = A32.ev_h = nullptr;
+        A32.halo = HaloP2P();
         A32.h_x = A32.h_y = nullptr;
         mg = new MGPrecond<float2>();
         return mg->build(A32, opts, st);
@@ -1132,6 +1189,14 @@ struct MixedMGPrecond : Precond {
         FDFD_TRY((convert<double2, float2>(n, (const double2*)v, v32, st)));
         FDFD_TRY(mg->apply(v32, z32, st));
         return convert<float2, double2>(n, z32, (double2*)z, st);
+    }
+    // complex64 in / out: no conversion passes (FGMRES keeps basis and corrections in complex64)
+    bool single_io() const override { return true; }
+    float2* single_input() override { return mg->o.mg_graph ? mg->in_buf : nullptr; }
+    int apply_single(const float2* v, float2* z, cudaStream_t st) override {
+        ++applies;
+        if (!v) return mg->apply_from_input(z, st);
+        return mg->apply(v, z, st);
     }
 };
 

@@ -49,6 +49,8 @@ struct CoarseArgs {
     C *r, *rh, *p, *v, *t, *ph, *sh;     // work vectors
     C *phf, *shf;                        // p^, s^ with the x-line correction applied
     LineView<C> yl, xl;                  // line sets of the level (nl may be 0)
+    const C* k5;                         // matrix entries of the level, [5][n]: west, east, south, north, diagonal
+    const C* relax;                      // omega / diagonal, [n]
     double* partials;                    // [gridDim.x][kCoarseVals]
     unsigned int* bar;                   // {count, generation} of the grid barrier, {count, generation} of the owners'
     int owners;                          // CTAs that own at least one line
@@ -245,18 +247,48 @@ struct CoarseCtx {
     unsigned int gen_all, gen_own;
 };
 
-// pointwise part of the zero-guess smoothing sweep for the value `val` at point (i, j)
+// pointwise part of the zero-guess smoothing sweep for the value `val` at point (i, j): returns the swept
+// value; for a strip column (relaxed by a y-line) the value is 0 and `gidx` >= 0 is where `val` goes in yl.g
 template <typename C, bool TM>
-__device__ __forceinline__ C coarse_point_relax(const CoarseArgs<C>& a, int i, int j, int q, C val) {
+__device__ __forceinline__ C coarse_point_relax(const CoarseArgs<C>& a, int i, int j, C val, int64_t& gidx) {
     const LineView<C>& yl = a.yl;
+    gidx = -1;
     if (yl.nl > 0 && (i < yl.lo || i >= a.Nx - yl.hi)) {
         const int l = i < yl.lo ? i : yl.lo + (i - (a.Nx - yl.hi));
-        yl.g[(int64_t)j * yl.nl + l] = val;               // right-hand side of the y-line through this column
+        gidx = (int64_t)j * yl.nl + l;
         return czero<C>();
     }
-    const PointCoefs<C> pc = point_coefs<C, TM>(a.ca, a.cb, a.cd, a.Nx, a.Ny, a.sx, a.sy, a.shift, i, j);
-    return cscale(a.omega, cdiv(val, pc.dg));
+    return cmul(val, a.relax[(int64_t)j * a.Nx + i]);
 }
+
+// the level's matrix entries are computed once per hierarchy (coarse_coefs_kernel) and read back here
+template <typename C>
+__device__ __forceinline__ PointCoefs<C> coarse_coefs(const CoarseArgs<C>& a, int64_t q) {
+    const int64_t n = (int64_t)a.Nx * a.Ny;
+    PointCoefs<C> p;
+    p.kw = a.k5[q]; p.ke = a.k5[n + q]; p.ks = a.k5[2 * n + q]; p.kn = a.k5[3 * n + q]; p.dg = a.k5[4 * n + q];
+    return p;
+}
+
+template <typename C, bool TM>
+__global__ void coarse_coefs_kernel(int Nx, int Ny, const C* ca, const C* cb, const C* cd,
+        typename real_of<C>::type sx, typename real_of<C>::type sy, C shift, typename real_of<C>::type omega,
+        C* k5, C* relax) {
+    const int64_t n = (int64_t)Nx * Ny;
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int j = (int)(q / Nx), i = (int)(q - (int64_t)j * Nx);
+    const PointCoefs<C> p = point_coefs<C, TM>(ca, cb, cd, Nx, Ny, sx, sy, shift, i, j);
+    k5[q] = p.kw; k5[n + q] = p.ke; k5[2 * n + q] = p.ks; k5[3 * n + q] = p.kn; k5[4 * n + q] = p.dg;
+    relax[q] = cscale(omega, cdiv(mk<C>(1, 0), p.dg));
+}
+
+// points a thread handles per batch: all loads of a batch are issued before its first store, so a phase costs
+// about one L2 round trip instead of one per point
+template <typename C> struct CoarseBatch {
+    static constexpr int U = sizeof(C) == 8 ? 4 : 2;     // pointwise phases
+    static constexpr int US = sizeof(C) == 8 ? 2 : 1;    // stencil phases (more live values per point)
+};
 
 // line phases of one smoothing sweep from a zero guess.  z holds omega D^-1 rhs outside the strip columns
 // and 0 inside; yl.g holds the strip-column right-hand sides.  On return (after the caller's grid barrier)
@@ -282,8 +314,8 @@ __device__ void coarse_line_phases(CoarseCtx<C>& c, C* z, const C* rhs) {
         const LineView<C>& v = a.xl;
         const int j = l < v.lo ? l : v.Ny - v.hi + (l - v.lo);
         for (int i = threadIdx.x; i < v.len; i += kCoarseThreads) {
-            const PointCoefs<C> pc = point_coefs<C, TM>(a.ca, a.cb, a.cd, a.Nx, a.Ny, a.sx, a.sy, a.shift, i, j);
             const int64_t pn = (int64_t)j * a.Nx + i;
+            const PointCoefs<C> pc = coarse_coefs<C>(a, pn);
             const C zc = ldv(&z[pn]);
             const C zw = i > 0 ? ldv(&z[pn - 1]) : czero<C>();
             const C ze = i < a.Nx - 1 ? ldv(&z[pn + 1]) : czero<C>();
@@ -309,41 +341,71 @@ __device__ __forceinline__ C coarse_zfin(const CoarseArgs<C>& a, const C* z, int
     return v;
 }
 
-// out = M zfin at the thread's points, zfin stored to zf; K = 1: acc = (rh, out);
-// K = 4: acc = (out, s), (out, out), (rh, s), (rh, out) with s = a.r
+// out = M zfin at the thread's points, zfin stored to zf; MODE 0: acc = (rh, out);
+// MODE 1: acc = (out, s), (out, out), (rh, s), (rh, out) with s = a.r
 template <typename C, bool TM, int MODE>
 __device__ __forceinline__ void coarse_apply_phase(const CoarseArgs<C>& a, const C* z, C* zf, C* out, double* acc,
                                                    int tid, int stride, int n) {
-    for (int q = tid; q < n; q += stride) {
-        const int j = q / a.Nx, i = q - j * a.Nx;
-        const PointCoefs<C> pc = point_coefs<C, TM>(a.ca, a.cb, a.cd, a.Nx, a.Ny, a.sx, a.sy, a.shift, i, j);
-        const C zc = coarse_zfin<C>(a, z, i, j, q);
-        const C zw = i > 0 ? coarse_zfin<C>(a, z, i - 1, j, q - 1) : czero<C>();
-        const C ze = i < a.Nx - 1 ? coarse_zfin<C>(a, z, i + 1, j, q + 1) : czero<C>();
-        const C zs = j > 0 ? coarse_zfin<C>(a, z, i, j - 1, q - a.Nx) : czero<C>();
-        const C zn = j < a.Ny - 1 ? coarse_zfin<C>(a, z, i, j + 1, q + a.Nx) : czero<C>();
-        const C o = coarse_stencil5<C>(pc, zc, zw, ze, zs, zn);
-        zf[q] = zc;
-        out[q] = o;
-        const C rhv = ldv(&a.rh[q]);
-        if (MODE == 0) {
-            acc[0] += (double)rhv.x * o.x + (double)rhv.y * o.y;        // conj(r^) * v
-            acc[1] += (double)rhv.x * o.y - (double)rhv.y * o.x;
-        } else {
-            const C sv = ldv(&a.r[q]);
-            acc[0] += (double)o.x * sv.x + (double)o.y * sv.y;          // conj(t) * s
-            acc[1] += (double)o.x * sv.y - (double)o.y * sv.x;
-            acc[2] += (double)o.x * o.x + (double)o.y * o.y;            // (t, t)
-            acc[3] += (double)rhv.x * sv.x + (double)rhv.y * sv.y;      // conj(r^) * s
-            acc[4] += (double)rhv.x * sv.y - (double)rhv.y * sv.x;
-            acc[5] += (double)rhv.x * o.x + (double)rhv.y * o.y;        // conj(r^) * t
-            acc[6] += (double)rhv.x * o.y - (double)rhv.y * o.x;
+    constexpr int U = CoarseBatch<C>::US;
+    for (int base = tid; base < n; base += U * stride) {
+        C o[U], zc[U], rhv[U], sv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = base + u * stride;
+            if (q < n) {
+                const int j = q / a.Nx, i = q - j * a.Nx;
+                const PointCoefs<C> pc = coarse_coefs<C>(a, q);
+                zc[u] = coarse_zfin<C>(a, z, i, j, q);
+                const C zw = i > 0 ? coarse_zfin<C>(a, z, i - 1, j, q - 1) : czero<C>();
+                const C ze = i < a.Nx - 1 ? coarse_zfin<C>(a, z, i + 1, j, q + 1) : czero<C>();
+                const C zs = j > 0 ? coarse_zfin<C>(a, z, i, j - 1, q - a.Nx) : czero<C>();
+                const C zn = j < a.Ny - 1 ? coarse_zfin<C>(a, z, i, j + 1, q + a.Nx) : czero<C>();
+                o[u] = coarse_stencil5<C>(pc, zc[u], zw, ze, zs, zn);
+                rhv[u] = ldv(&a.rh[q]);
+                if (MODE == 1) sv[u] = ldv(&a.r[q]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = base + u * stride;
+            if (q < n) {
+                zf[q] = zc[u];
+                out[q] = o[u];
+                if (MODE == 0) {
+                    acc[0] += (double)rhv[u].x * o[u].x + (double)rhv[u].y * o[u].y;        // conj(r^) * v
+                    acc[1] += (double)rhv[u].x * o[u].y - (double)rhv[u].y * o[u].x;
+                } else {
+                    acc[0] += (double)o[u].x * sv[u].x + (double)o[u].y * sv[u].y;          // conj(t) * s
+                    acc[1] += (double)o[u].x * sv[u].y - (double)o[u].y * sv[u].x;
+                    acc[2] += (double)o[u].x * o[u].x + (double)o[u].y * o[u].y;            // (t, t)
+                    acc[3] += (double)rhv[u].x * sv[u].x + (double)rhv[u].y * sv[u].y;      // conj(r^) * s
+                    acc[4] += (double)rhv[u].x * sv[u].y - (double)rhv[u].y * sv[u].x;
+                    acc[5] += (double)rhv[u].x * o[u].x + (double)rhv[u].y * o[u].y;        // conj(r^) * t
+                    acc[6] += (double)rhv[u].x * o[u].y - (double)rhv[u].y * o[u].x;
+                }
+            }
         }
     }
 }
 
+// -DFDFD_COARSE_TRACE: CTA 0 prints the time (ns) between the phase boundaries of the second iteration
+#ifdef FDFD_COARSE_TRACE
+__device__ unsigned int g_coarse_trace_count = 0;
+__device__ __forceinline__ unsigned long long coarse_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define COARSE_MARK(k) do { if (it == 1 && blockIdx.x == 0 && threadIdx.x == 0) tr[k] = coarse_now(); } while (0)
+#else
+#define COARSE_MARK(k) do { } while (0)
+#endif
+
 template <typename C, bool TM>
 __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(CoarseArgs<C> a) {
+#ifdef FDFD_COARSE_TRACE
+    unsigned long long tr[16];
+#endif
     using R = typename real_of<C>::type;
     extern __shared__ __align__(16) unsigned char coarse_smem[];
     __shared__ C sg[2 * kMaxChunks], su[2 * kMaxChunks];
@@ -369,13 +431,30 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
     if ((int)blockIdx.x < a.xl.nl) line_smem_load<C>(c.xs, a.xl, blockIdx.x);
 
     // start: x = 0, r = r^ = p = b, rho = (b, b); first search direction swept
+    constexpr int U = CoarseBatch<C>::U;
     double acc2[2] = {0.0, 0.0};
-    for (int q = tid; q < n; q += stride) {
-        const int j = q / a.Nx, i = q - j * a.Nx;
-        const C bv = a.b[q];
-        a.r[q] = bv; a.rh[q] = bv; a.p[q] = bv; a.x[q] = czero<C>();
-        a.ph[q] = coarse_point_relax<C, TM>(a, i, j, q, bv);
-        acc2[0] += (double)bv.x * bv.x + (double)bv.y * bv.y;
+    for (int base = tid; base < n; base += U * stride) {
+        C bv[U], zr[U];
+        int64_t gi[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = base + u * stride;
+            if (q < n) {
+                const int j = q / a.Nx, i = q - j * a.Nx;
+                bv[u] = a.b[q];
+                zr[u] = coarse_point_relax<C, TM>(a, i, j, bv[u], gi[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = base + u * stride;
+            if (q < n) {
+                a.r[q] = bv[u]; a.rh[q] = bv[u]; a.p[q] = bv[u]; a.x[q] = czero<C>();
+                a.ph[q] = zr[u];
+                if (gi[u] >= 0) a.yl.g[gi[u]] = bv[u];
+                acc2[0] += (double)bv[u].x * bv[u].x + (double)bv[u].y * bv[u].y;
+            }
+        }
     }
     coarse_block_reduce<2>(acc2, prow, red);
     coarse_barrier(a.bar, nblk, c.gen_all);
@@ -386,33 +465,62 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
 
     for (int it = 0; it < a.its; ++it) {
         // (p^0 and the y-line right-hand sides of this iteration were written by the previous phase)
+        COARSE_MARK(0);
         coarse_line_phases<C, TM>(c, a.ph, a.p);
+        COARSE_MARK(1);
         coarse_barrier(a.bar, nblk, c.gen_all);
+        COARSE_MARK(2);
         // V: v = M p^, (r^, v)
         double accv[2] = {0.0, 0.0};
         coarse_apply_phase<C, TM, 0>(a, a.ph, a.phf, a.v, accv, tid, stride, n);
+        COARSE_MARK(3);
         coarse_block_reduce<2>(accv, prow, red);
         coarse_barrier(a.bar, nblk, c.gen_all);
+        COARSE_MARK(4);
         coarse_grid_total<2>(a.partials, tot2, red);
+        COARSE_MARK(5);
         alpha = cs_div(rho, make_double2(tot2[0], tot2[1]));
         // S: s = r - alpha v (in r), s^0 pointwise
         const C alphaC = mk<C>((R)alpha.x, (R)alpha.y);
-        for (int q = tid; q < n; q += stride) {
-            const int j = q / a.Nx, i = q - j * a.Nx;
-            const C sv = csub(ldv(&a.r[q]), cmul(alphaC, a.v[q]));      // v[q] was written by this thread
-            a.r[q] = sv;
-            a.sh[q] = coarse_point_relax<C, TM>(a, i, j, q, sv);
+        for (int base = tid; base < n; base += U * stride) {
+            C sv[U], zr[U];
+            int64_t gi[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = base + u * stride;
+                if (q < n) {
+                    const int j = q / a.Nx, i = q - j * a.Nx;
+                    sv[u] = csub(ldv(&a.r[q]), cmul(alphaC, ldv(&a.v[q])));
+                    zr[u] = coarse_point_relax<C, TM>(a, i, j, sv[u], gi[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = base + u * stride;
+                if (q < n) {
+                    a.r[q] = sv[u];
+                    a.sh[q] = zr[u];
+                    if (gi[u] >= 0) a.yl.g[gi[u]] = sv[u];
+                }
+            }
         }
+        COARSE_MARK(6);
         coarse_barrier(a.bar, nblk, c.gen_all);
+        COARSE_MARK(7);
         coarse_line_phases<C, TM>(c, a.sh, a.r);
+        COARSE_MARK(8);
         coarse_barrier(a.bar, nblk, c.gen_all);
+        COARSE_MARK(9);
         // T: t = M s^, (t, s), (t, t), (r^, s), (r^, t)
         double acct[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         coarse_apply_phase<C, TM, 1>(a, a.sh, a.shf, a.t, acct, tid, stride, n);
+        COARSE_MARK(10);
         coarse_block_reduce<8>(acct, prow, red);
         coarse_barrier(a.bar, nblk, c.gen_all);
+        COARSE_MARK(11);
         double tot8[8];
         coarse_grid_total<8>(a.partials, tot8, red);
+        COARSE_MARK(12);
         omega = cs_div(make_double2(tot8[0], tot8[1]), make_double2(tot8[2], 0.0));
         // rho_new = (r^, s - omega t)
         const double2 rt = cs_mul(omega, make_double2(tot8[5], tot8[6]));
@@ -425,18 +533,44 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
         const C betaC = mk<C>((R)beta.x, (R)beta.y);
         const C nboC = mk<C>((R)(-nbo.x), (R)(-nbo.y));
         const bool more = it + 1 < a.its;
-        for (int q = tid; q < n; q += stride) {
-            // every array touched here was last written by this same thread (same q mapping)
-            a.x[q] = cfma(omegaC, a.shf[q], cfma(alphaC, a.phf[q], a.x[q]));
-            if (more) {
-                const int j = q / a.Nx, i = q - j * a.Nx;
-                const C rv = csub(a.r[q], cmul(omegaC, a.t[q]));
-                a.r[q] = rv;
-                const C pv = cfma(nboC, a.v[q], cfma(betaC, a.p[q], rv));
-                a.p[q] = pv;
-                a.ph[q] = coarse_point_relax<C, TM>(a, i, j, q, pv);
+        for (int base = tid; base < n; base += U * stride) {
+            // every array read here was last written by this same thread (same q mapping)
+            C xv[U], rv[U], pv[U], zr[U];
+            int64_t gi[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = base + u * stride;
+                if (q < n) {
+                    xv[u] = cfma(omegaC, ldv(&a.shf[q]), cfma(alphaC, ldv(&a.phf[q]), ldv(&a.x[q])));
+                    if (more) {
+                        const int j = q / a.Nx, i = q - j * a.Nx;
+                        rv[u] = csub(ldv(&a.r[q]), cmul(omegaC, ldv(&a.t[q])));
+                        pv[u] = cfma(nboC, ldv(&a.v[q]), cfma(betaC, ldv(&a.p[q]), rv[u]));
+                        zr[u] = coarse_point_relax<C, TM>(a, i, j, pv[u], gi[u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = base + u * stride;
+                if (q < n) {
+                    a.x[q] = xv[u];
+                    if (more) {
+                        a.r[q] = rv[u]; a.p[q] = pv[u]; a.ph[q] = zr[u];
+                        if (gi[u] >= 0) a.yl.g[gi[u]] = pv[u];
+                    }
+                }
             }
         }
+        COARSE_MARK(13);
         if (more) coarse_barrier(a.bar, nblk, c.gen_all);
+        COARSE_MARK(14);
+#ifdef FDFD_COARSE_TRACE
+        if (it == 1 && blockIdx.x == 0 && threadIdx.x == 0 && atomicAdd(&g_coarse_trace_count, 1u) < 4u)
+            printf("[coarse trace ns] lines %llu | bar %llu | V %llu | red+bar %llu | total %llu | S %llu | bar %llu | lines %llu | bar %llu | T %llu | red+bar %llu | total %llu | XA %llu | bar %llu || iteration %llu\n",
+                   tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6],
+                   tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[11] - tr[10], tr[12] - tr[11], tr[13] - tr[12],
+                   tr[14] - tr[13], tr[14] - tr[0]);
+#endif
     }
 }

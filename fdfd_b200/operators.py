@@ -87,7 +87,7 @@ class HelmholtzOperator2D:
 
     def invalidate(self):
         """Drop the cached preconditioner (after changing the coefficient tensors in place)."""
-        _lib.check(self._L.fdfd_helm2d_invalidate(self._h))
+        _lib.check(self._L.fdfd_helm2d_invalidate(self._handle()))
 
     def set_variant(self, v):
         _lib.check(self._L.fdfd_helm2d_set_variant(self._h, int(v)))
@@ -98,10 +98,15 @@ class HelmholtzOperator2D:
             self._h = C.c_void_p()
 
     def _release_comm_state(self):
-        """Called by `SlabComm.close()`: the cached preconditioner of a sharded operator holds a CUDA
-        graph with captured NCCL kernels, and ncclCommDestroy waits until every such graph is gone."""
-        if getattr(self, "_h", None) is not None and self._h.value:
-            self._L.fdfd_helm2d_invalidate(self._h)
+        """Called by `SlabComm.close()`: a sharded operator owns ghost-row buffers in the communicator's
+        peer-mapped heap (and, on the NCCL fallback path, a captured graph that pins the communicator), so
+        it is closed together with it; using it afterwards raises instead of touching freed memory."""
+        self.close()
+
+    def _handle(self):
+        if getattr(self, "_h", None) is None or not self._h.value:
+            raise _lib.FdfdError("operator is closed (its communicator was closed or close() was called)")
+        return self._h
 
     def __del__(self):
         try:
@@ -121,7 +126,7 @@ class HelmholtzOperator2D:
         if out is None:
             out = torch.empty_like(x)
         with torch.cuda.device(self.device):
-            _lib.check(self._L.fdfd_helm2d_apply(self._h, x.data_ptr(), out.data_ptr(), self._stream()))
+            _lib.check(self._L.fdfd_helm2d_apply(self._handle(), x.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
     def apply_host(self, x, out=None):
@@ -135,7 +140,7 @@ class HelmholtzOperator2D:
         if y.dtype != ndt or y.size != self.n or not y.flags.c_contiguous:
             raise ValueError("out must be a C-contiguous array of the operator dtype and size")
         with _torch().cuda.device(self.device):
-            _lib.check(self._L.fdfd_helm2d_apply_host(self._h, x.ctypes.data, y.ctypes.data))
+            _lib.check(self._L.fdfd_helm2d_apply_host(self._handle(), x.ctypes.data, y.ctypes.data))
         return y
 
     __matmul__ = lambda self, x: self.apply(x) if not isinstance(x, np.ndarray) else self.apply_host(x)
@@ -155,13 +160,13 @@ class HelmholtzOperator2D:
         if host:
             bh = np.ascontiguousarray(b, dtype=ndt).ravel()
             xh = np.zeros_like(bh) if x0 is None else np.ascontiguousarray(x0, dtype=ndt).ravel().copy()
-            st = self._L.fdfd_krylov_solve_host(self._h, C.byref(o), bh.ctypes.data, xh.ctypes.data, info)
+            st = self._L.fdfd_krylov_solve_host(self._handle(), C.byref(o), bh.ctypes.data, xh.ctypes.data, info)
             x = xh
         else:
             bd = b.to(device=self.device, dtype=self.tdtype).contiguous().reshape(-1)
             x = torch.zeros_like(bd) if x0 is None else x0.to(device=self.device, dtype=self.tdtype).reshape(-1).clone()
             with torch.cuda.device(self.device):
-                st = self._L.fdfd_krylov_solve(self._h, C.byref(o), bd.data_ptr(), x.data_ptr(), info, self._stream())
+                st = self._L.fdfd_krylov_solve(self._handle(), C.byref(o), bd.data_ptr(), x.data_ptr(), info, self._stream())
         d = dict(iterations=int(info[0]), relres=float(info[1]), applies=int(info[2]),
                  precond_applies=int(info[3]), seconds=float(info[4]), breakdowns=int(info[5]),
                  method=method, precond=precond, converged=(st == _lib.FDFD_OK))
@@ -178,7 +183,7 @@ class HelmholtzOperator2D:
         v = v.to(device=self.device, dtype=self.tdtype).contiguous().reshape(-1)
         z = torch.empty_like(v)
         with torch.cuda.device(self.device):
-            _lib.check(self._L.fdfd_precond_apply(self._h, C.byref(o), v.data_ptr(), z.data_ptr(), self._stream()))
+            _lib.check(self._L.fdfd_precond_apply(self._handle(), C.byref(o), v.data_ptr(), z.data_ptr(), self._stream()))
         return z
 
 
@@ -342,6 +347,12 @@ class SlabComm:
     def _register(self, op):
         self._dependants.add(op)
 
+    @property
+    def peer_mapped(self):
+        """True when ghost rows / small collectives travel over NVLink peer memory (CUDA IPC heap), False on
+        the NCCL fallback path."""
+        return bool(self.handle and self.handle.value and self._L.fdfd_comm_peer_mapped(self.handle))
+
     def close(self):
         """Destroy the communicator.  Operators created with it drop their cached preconditioners
         first: a captured multigrid cycle references the communicator (NCCL keeps a persistent
@@ -354,6 +365,12 @@ class SlabComm:
                 torch.cuda.synchronize()
             self._L.fdfd_comm_destroy(self.handle)
             self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def slab_rows(Ny, world_size, rank):

@@ -77,6 +77,14 @@ class FDFD2DScatteringSolver:
         self.comm = comm
         if comm is not None and comm.world_size > 1:
             from .operators import slab_rows
+            if self.Ny % comm.world_size:
+                # the sharded multigrid preconditioner (the default) keeps one equal slab per rank on every level
+                raise ValueError(f"Ny={self.Ny} is not divisible by the {comm.world_size} ranks of the communicator: "
+                                 "y-slab sharding of FDFD2DScatteringSolver needs equal slabs")
+            if (self.Ny // comm.world_size) % 2:
+                import warnings
+                warnings.warn(f"{self.Ny // comm.world_size} rows per rank is odd: the multigrid hierarchy cannot "
+                              "coarsen such slabs and the solve will converge slowly; use an even number of rows per rank")
             self._rows = slab_rows(self.Ny, comm.world_size, comm.rank)
         else:
             self._rows = None

@@ -210,6 +210,10 @@ int fdfd_precond_apply(fdfd_helm2d_t* A, const fdfd_krylov_opts* opts, const voi
  * ------------------------------------------------------------------------------------------ */
 int fdfd_comm_unique_id(void* id128);
 int fdfd_comm_create(fdfd_comm_t** out, int nranks, int rank, const void* id128);
+/* 1 when the data path of the communicator is NVLink peer memory (every rank mapped every other rank's
+ * symmetric heap with CUDA IPC: ghost rows are pushed by the stencil kernel itself, small all-gathers and
+ * inner-product reductions are flag-based kernels), 0 when it fell back to NCCL (or FDFD_P2P=0). */
+int fdfd_comm_peer_mapped(const fdfd_comm_t*);
 /* Destroy (or fdfd_helm2d_invalidate) every sharded operator created with the communicator first: a
  * cached multigrid preconditioner holds a CUDA graph with captured NCCL kernels, and NCCL does not
  * release a communicator while such a graph exists (ncclCommDestroy would block). */

@@ -20,6 +20,10 @@ def main():
     import datetime
     dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     comm = fdfd_b200.SlabComm()
+    expect = os.environ.get("FDFD_EXPECT_PATH")
+    if expect and comm.peer_mapped != (expect == "p2p"):
+        print(f"rank {rank}: data path is {'p2p' if comm.peer_mapped else 'nccl'}, expected {expect}", flush=True)
+        sys.exit(1)
     rng = np.random.default_rng(42)           # same stream on every rank -> same global arrays
     failures = []
     for (Nx, Ny), pol, bc in [((96, 70), "TE", (0, 0)), ((96, 70), "TM", (0, 0)), ((64, 64), "TE", (1, 1)),
@@ -119,6 +123,14 @@ def main():
     if failures:
         print(f"rank {rank} FAILURES:", failures, flush=True)
     comm.close()
+    # operators of a closed communicator refuse to run instead of touching freed peer memory
+    try:
+        op_closed = sim.operator("TM"); op_closed.apply(torch.zeros(op_closed.n, dtype=torch.complex128, device=dev))
+        failures.append("apply on a closed sharded operator did not raise")
+    except (fdfd_b200.FdfdError, ValueError, KeyError):
+        pass
+    if failures:
+        flag += 1
     dist.destroy_process_group()
     if flag.item():
         sys.exit(1)
