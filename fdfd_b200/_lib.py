@@ -76,6 +76,19 @@ _PROTOTYPES = {
                                       C.c_void_p, C.c_void_p]),
     "fdfd_blas_multi_axpy": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                        C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "fdfd_band_max_nx": (C.c_int, []),
+    "fdfd_band_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int,
+                                   C.c_void_p]),
+    "fdfd_band_destroy": (None, [C.c_void_p]),
+    "fdfd_band_set_start": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdfd_band_set_active": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "fdfd_band_cycle": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "fdfd_band_restart": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "fdfd_band_ritz": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                 C.c_void_p]),
+    "fdfd_band_vectors": (C.c_void_p, [C.c_void_p]),
+    "fdfd_band_apply_shifted": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdfd_csr_product_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]),
     "fdfd_csr_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

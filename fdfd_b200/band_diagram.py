@@ -22,6 +22,7 @@ from typing import Callable, Iterable, Sequence
 
 import numpy as np
 
+from . import _lib
 from . import eigs as _eigs
 from .operators import HelmholtzOperator2D
 
@@ -263,6 +264,11 @@ class BandDiagramSolver2D:
             dev, tdt = A0.device, A0.tdtype
             Mdev = torch.from_numpy(M).to(dev).to(tdt).reshape(-1)
             cdev = (-sigma) * Mdev.reshape(self.Ny, self.Nx)
+            if inner in ("auto", "block") and self._block_path_ok(ca, cb, M, sigma, num_bands, inner == "block"):
+                info["inner"] = "block-lu"
+                self._sweep_device(kind, A0, Mdev, beta_path, num_bands, sigma, tol, delta, pol, eigenvalues,
+                                   frequencies, info)
+                continue
             if dense:
                 self._sweep_batched(kind, A0, cdev, Mdev, beta_path, num_bands, sigma, tol, delta, pol,
                                     eigenvalues, frequencies, info, batch)
@@ -294,6 +300,119 @@ class BandDiagramSolver2D:
                                      frequencies=frequencies, eigenvalues=eigenvalues)
         self._results = result
         return result
+
+    def _block_path_ok(self, ca, cb, M, sigma, num_bands, explicit):
+        """The one-CTA-per-path-point kernels (csrc/band.cu) need Bloch walls on both axes, a cell whose block
+        factorisation fits in shared memory and a Hermitian positive definite shifted operator (real positive
+        materials, shift left of the spectrum)."""
+        L = _lib.lib()
+        ok = (tuple(int(b) for b in self.boundary_conditions) == (1, 1) and 3 <= self.Nx <= L.fdfd_band_max_nx()
+              and self.Ny >= 3 and (3 * self.Nx * self.Ny + 2 * self.Nx + 41) * 16 <= 220 * 1024
+              and np.imag(sigma) == 0 and np.real(sigma) < 0 and 2 * num_bands + 1 <= 40
+              and all(np.all(np.imag(a) == 0) and np.all(np.real(a) > 0) for a in (ca, cb, M)))
+        if explicit and not ok:
+            raise ValueError("inner='block' needs Bloch walls on both axes, real positive materials, a shift left of "
+                             "the spectrum and a cell that fits the shared-memory block factorisation")
+        return ok
+
+    def _sweep_device(self, kind, A0, Mdev, beta_path, num_bands, sigma, tol, delta, pol, eigenvalues, frequencies,
+                      info, max_restarts=100, seed=0):
+        """All path points of one polarisation in lock-step on this library's own kernels (csrc/band.cu, C-ABI
+        fdfd_band_*): block LU of the cyclic block-tridiagonal shifted operator, Arnoldi cycles and Krylov-Schur
+        restarts on the device, one CTA per path point; the host only decomposes the (ncv+1) x ncv projected
+        matrices (same restart logic as `eigs.krylov_schur_batched`)."""
+        import ctypes as C
+        import time
+        import scipy.linalg as sla
+        import torch
+        L = _lib.lib()
+        n, P, k = self.Nx * self.Ny, beta_path.shape[1], int(num_bands)
+        dev, tdt = A0.device, A0.tdtype
+        ncv = int(min(max(2 * k + 1, 20), n, 40))
+        keep = min(ncv - 1, k + max(1, (ncv - k) // 2))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def lap(key, t0):
+            torch.cuda.synchronize(dev)
+            info[key] = info.get(key, 0.0) + time.perf_counter() - t0
+            return time.perf_counter()
+
+        t = time.perf_counter()
+        ph = np.array([self._phases(beta_path[:, i]) for i in range(P)])
+        phases = np.ascontiguousarray(np.stack([ph[:, 0].real, ph[:, 0].imag, ph[:, 1].real, ph[:, 1].imag], axis=1))
+        Mc = Mdev.to(torch.complex128).contiguous()
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(L.fdfd_band_create(C.byref(h), {"TE": _lib.POL_TE, "TM": _lib.POL_TM}[kind], self.Nx, self.Ny, P,
+                                          A0.ca.data_ptr(), A0.cb.data_ptr(), Mc.data_ptr(), A0.sx, A0.sy, float(sigma),
+                                          phases.ctypes.data, ncv, k, stream))
+        try:
+            g = torch.Generator(device="cpu").manual_seed(int(seed))
+            v0 = torch.view_as_complex(torch.rand((P, n, 2), generator=g, dtype=torch.float64) * 2 - 1).to(dev)
+            v0 = (v0 / torch.linalg.vector_norm(v0, dim=1, keepdim=True)).contiguous()
+            _lib.check(L.fdfd_band_set_start(h, v0.data_ptr(), stream))
+            t = lap("t_factor", t)
+            Hh = np.zeros((P, ncv + 1, ncv), dtype=np.complex128)
+            active = np.arange(P, dtype=np.int32)
+            lam_out = np.zeros((P, k), dtype=np.complex128)
+            res_out = np.zeros((P, k))
+            p0, restarts = 0, 0
+            while True:
+                _lib.check(L.fdfd_band_cycle(h, p0, ncv, Hh.ctypes.data, stream))
+                t = lap("t_krylov", t)
+                Pa = len(active)
+                done = np.zeros(Pa, dtype=bool)
+                Sk = np.zeros((Pa, k, ncv), dtype=np.complex128)
+                Qk = np.zeros((Pa, keep, ncv), dtype=np.complex128)
+                Tn = np.zeros((Pa, ncv + 1, ncv), dtype=np.complex128)
+                mus = np.zeros((Pa, k), dtype=np.complex128)
+                for a, p in enumerate(active):
+                    Hm, b = Hh[p, :ncv, :ncv], Hh[p, ncv, :ncv]
+                    mu, S = np.linalg.eig(Hm)
+                    order = np.argsort(-np.abs(mu))
+                    mu, S = mu[order], S[:, order]
+                    S = S / np.linalg.norm(S, axis=0, keepdims=True)
+                    res = np.abs(b @ S)
+                    done[a] = np.all(res[:k] <= tol * np.abs(mu[:k])) or restarts >= max_restarts
+                    mus[a] = mu[:k]
+                    Sk[a] = S[:, :k].T
+                    if not done[a]:
+                        thr = np.sort(np.abs(mu))[::-1][keep - 1]
+                        T, Q, _ = sla.schur(Hm, output="complex", sort=lambda x: abs(x) >= thr * (1 - 1e-12))
+                        Qk[a] = Q[:, :keep].T
+                        Tn[a, :keep, :keep] = T[:keep, :keep]
+                        Tn[a, keep, :keep] = b @ Q[:, :keep]
+                t = lap("t_host_projected", t)
+                fin = np.flatnonzero(done)
+                if fin.size:
+                    idx = np.ascontiguousarray(active[fin], dtype=np.int32)
+                    lam = np.ascontiguousarray(sigma + 1.0 / mus[fin])
+                    res = np.zeros((fin.size, k))
+                    Sf = np.ascontiguousarray(Sk[fin])
+                    _lib.check(L.fdfd_band_ritz(h, idx.ctypes.data, int(fin.size), Sf.ctypes.data, lam.ctypes.data, k,
+                                                res.ctypes.data, stream))
+                    lam_out[idx], res_out[idx] = lam, res
+                go = np.flatnonzero(~done)
+                t = lap("t_post", t)
+                if go.size == 0:
+                    break
+                active = np.ascontiguousarray(active[go], dtype=np.int32)
+                _lib.check(L.fdfd_band_set_active(h, active.ctypes.data, int(active.size), stream))
+                Qg, Tg = np.ascontiguousarray(Qk[go]), np.ascontiguousarray(Tn[go])
+                _lib.check(L.fdfd_band_restart(h, Qg.ctypes.data, Tg.ctypes.data, keep, stream))
+                p0 = keep
+                restarts += 1
+        finally:
+            L.fdfd_band_destroy(h)
+        for i in range(P):
+            order = np.argsort(np.real(lam_out[i]))
+            vals = lam_out[i][order][:k]
+            eigenvalues[pol][:, i] = vals
+            frequencies[pol][:, i] = self._normalise_eigenvalues(vals)
+            info["max_residual"] = max(info["max_residual"],
+                                       float(np.max(res_out[i][np.abs(lam_out[i]) > 1e-6 * delta], initial=0.0)))
+        info["restarts"] += restarts
+        info["eigensolves"] += P
 
     def _sweep_batched(self, kind, A0, cdev, Mdev, beta_path, num_bands, sigma, tol, delta, pol, eigenvalues,
                        frequencies, info, batch):

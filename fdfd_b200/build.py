@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 # FDFD_COARSE_TRACE=1 builds an instrumented copy next to the product library (load it with FDFD_B200_LIB=...)
 LIB = os.path.join(HERE, "libfdfd_b200_trace.so" if os.environ.get("FDFD_COARSE_TRACE") else "libfdfd_b200.so")
-SOURCES = ["api.cu", "yee_assemble.cu", "helm2d.cu", "blas1.cu", "krylov.cu", "comm.cu", "p2p.cu", "mg.cu", "csr_ops.cu"]
+SOURCES = ["api.cu", "yee_assemble.cu", "helm2d.cu", "blas1.cu", "krylov.cu", "comm.cu", "p2p.cu", "mg.cu", "csr_ops.cu", "band.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

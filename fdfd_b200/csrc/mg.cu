@@ -811,9 +811,10 @@ struct MGPrecond : Precond {
     int coarse_grid = 0;
     bool coarse_ready = false;
     static size_t coarse_smem_bytes(const Level<C>& lv) {
-        const int len = std::max(lv.ylines.nl ? lv.ylines.len : 0, lv.xlines.nl ? lv.xlines.len : 0);
-        return (line_smem_elems<C>(lv.ylines.nl, lv.ylines.len, lv.ylines.Ptot) +
-                line_smem_elems<C>(lv.xlines.nl, lv.xlines.len, lv.xlines.Ptot) + (size_t)len) * sizeof(C);
+        const int len = std::max(lv.ylines.nl ? line_pad_len(lv.ylines.len, lv.ylines.m) : 0,
+                                 lv.xlines.nl ? line_pad_len(lv.xlines.len, lv.xlines.m) : 0);
+        return (line_smem_elems<C>(lv.ylines.nl, lv.ylines.len, lv.ylines.m, lv.ylines.Ptot) +
+                line_smem_elems<C>(lv.xlines.nl, lv.xlines.len, lv.xlines.m, lv.xlines.Ptot) + (size_t)len) * sizeof(C);
     }
     // shape limits of the persistent kernel; anything else keeps the launch chain of mode 1
     bool coarse_persistent_shape_ok(const Level<C>& lv) const {

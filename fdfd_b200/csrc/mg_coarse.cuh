@@ -84,15 +84,16 @@ __device__ __forceinline__ void coarse_barrier(unsigned int* bar, unsigned int c
     __syncthreads();
     if (threadIdx.x == 0) {
         ++gen;
-        __threadfence();
-        const unsigned int prev = atomicAdd(&bar[0], 1u);
+        // release on arrival (cumulative over the CTA's writes ordered by the bar.sync above), acquire on
+        // departure: no separate full fences
+        unsigned int prev;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(prev) : "l"(bar) : "memory");
         if (prev == count - 1) {
-            bar[0] = 0;
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar), "r"(0u) : "memory");
             st_release_u32(&bar[1], gen);
         } else {
             while (ld_acquire_u32(&bar[1]) != gen) { }
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -146,19 +147,26 @@ __device__ __forceinline__ void coarse_grid_total(const double* partials, double
 template <typename C>
 struct LineSmem { C *fl, *fc, *ip, *sv, *sw, *rinv; };
 
+// Lines live in shared memory with one padding element per chunk (position t -> t + t / m): the chunk
+// recurrences run one thread per chunk, and without the padding all chunk heads fall into the same bank
+// (m = 16 elements of 8 bytes = 128 bytes: a 32-way conflict on every access, measured 4.9 us per solve).
+__host__ __device__ inline int line_pad_len(int len, int m) { return len + (m > 0 ? (len + m - 1) / m : 0) + 1; }
+
 template <typename C>
-__host__ __device__ inline size_t line_smem_elems(int nl, int len, int Ptot) {
+__host__ __device__ inline size_t line_smem_elems(int nl, int len, int m, int Ptot) {
     if (nl == 0) return 0;
-    return (size_t)3 * len + (Ptot > 1 ? (size_t)2 * len + (size_t)4 * Ptot * Ptot : 0);
+    const size_t pl = (size_t)line_pad_len(len, m);
+    return 3 * pl + (Ptot > 1 ? 2 * pl + (size_t)4 * Ptot * Ptot : 0);
 }
 
 template <typename C>
 __device__ LineSmem<C> line_smem_carve(C*& cursor, const LineView<C>& v) {
     LineSmem<C> s{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (v.nl == 0) return s;
-    s.fl = cursor; s.fc = s.fl + v.len; s.ip = s.fc + v.len; cursor = s.ip + v.len;
+    const int pl = line_pad_len(v.len, v.m);
+    s.fl = cursor; s.fc = s.fl + pl; s.ip = s.fc + pl; cursor = s.ip + pl;
     if (v.Ptot > 1) {
-        s.sv = cursor; s.sw = s.sv + v.len; s.rinv = s.sw + v.len;
+        s.sv = cursor; s.sw = s.sv + pl; s.rinv = s.sw + pl;
         cursor = s.rinv + 4 * v.Ptot * v.Ptot;
     }
     return s;
@@ -168,8 +176,9 @@ template <typename C>
 __device__ void line_smem_load(const LineSmem<C>& s, const LineView<C>& v, int l) {
     const int64_t nl = v.nl;
     for (int t = threadIdx.x; t < v.len; t += kCoarseThreads) {
-        s.fl[t] = v.fl[t * nl + l]; s.fc[t] = v.fc[t * nl + l]; s.ip[t] = v.fip[t * nl + l];
-        if (v.Ptot > 1) { s.sv[t] = v.sv[t * nl + l]; s.sw[t] = v.sw[t * nl + l]; }
+        const int pt = t + t / v.m;
+        s.fl[pt] = v.fl[t * nl + l]; s.fc[pt] = v.fc[t * nl + l]; s.ip[pt] = v.fip[t * nl + l];
+        if (v.Ptot > 1) { s.sv[pt] = v.sv[t * nl + l]; s.sw[pt] = v.sw[t * nl + l]; }
     }
     if (v.Ptot > 1) {
         const int nn = 4 * v.Ptot * v.Ptot;
@@ -178,53 +187,99 @@ __device__ void line_smem_load(const LineSmem<C>& s, const LineView<C>& v, int l
     }
 }
 
-// tridiagonal solve of the line whose right-hand side sits in sl[0..len): chunk-local recurrences, interface
-// mat-vec, spike correction; the solution replaces sl.  Same arithmetic as line_fused_kernel.
+// -DFDFD_COARSE_TRACE: CTA 0 prints the time (ns) between the phase boundaries of the second iteration
+#ifdef FDFD_COARSE_TRACE
+__device__ unsigned int g_coarse_trace_count = 0;
+__device__ __forceinline__ unsigned long long coarse_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ unsigned long long g_line_tr[16];
+#define COARSE_MARK(k) do { if (it == 1 && blockIdx.x == 0 && threadIdx.x == 0) tr[k] = coarse_now(); } while (0)
+#define COARSE_LMARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_line_tr[k] = coarse_now(); } while (0)
+#else
+#define COARSE_MARK(k) do { } while (0)
+#define COARSE_LMARK(k) do { } while (0)
+#endif
+
+// tridiagonal solve of the line whose right-hand side sits in sl (padded positions): chunk-local recurrences,
+// interface mat-vec, spike correction; the solution replaces sl.  Same algorithm as line_fused_kernel.
 template <typename C>
-__device__ void coarse_line_solve(const LineView<C>& v, const LineSmem<C>& s, C* sl, C* sg, C* su) {
+__device__ void coarse_line_solve(const LineView<C>& v, const LineSmem<C>& s, C* sl, C* sg, C* su, int lm = 0) {
+    using R = typename real_of<C>::type;
     const int len = v.len;
+    COARSE_LMARK(lm);
     if ((int)threadIdx.x < v.P) {
         const int k = threadIdx.x;
         const int t0 = k * v.m, t1 = min(len, t0 + v.m);
         if (t0 < t1) {
-            C y = sl[t0];
-            for (int t = t0 + 1; t < t1; ++t) { y = csub(sl[t], cmul(s.fl[t], y)); sl[t] = y; }
-            C e = cmul(y, s.ip[t1 - 1]);
-            sl[t1 - 1] = e;
+            const int p0 = t0 + k, cnt = t1 - t0;           // padded position of the chunk head
+            // operands of four steps are fetched ahead of the dependent chain
+            C y = sl[p0];
+            for (int q0 = 1; q0 < cnt; q0 += 4) {
+                C rs[4], cf[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = min(q0 + u, cnt - 1);
+                    rs[u] = sl[p0 + q]; cf[u] = s.fl[p0 + q];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (q0 + u < cnt) { y = csub(rs[u], cmul(cf[u], y)); sl[p0 + q0 + u] = y; }
+                }
+            }
+            C e = cmul(y, s.ip[p0 + cnt - 1]);
+            sl[p0 + cnt - 1] = e;
             const C e_last = e;
-            for (int t = t1 - 2; t >= t0; --t) { e = cmul(csub(sl[t], cmul(s.fc[t], e)), s.ip[t]); sl[t] = e; }
+            for (int q0 = cnt - 2; q0 >= 0; q0 -= 4) {
+                C rs[4], cf[4], ci[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int q = max(q0 - u, 0);
+                    rs[u] = sl[p0 + q]; cf[u] = s.fc[p0 + q]; ci[u] = s.ip[p0 + q];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (q0 - u >= 0) { e = cmul(csub(rs[u], cmul(cf[u], e)), ci[u]); sl[p0 + q0 - u] = e; }
+                }
+            }
             sg[2 * k] = e; sg[2 * k + 1] = e_last;
         }
     }
     __syncthreads();
+    COARSE_LMARK(lm + 1);
     if (v.Ptot > 1) {
+        // interface mat-vec u = R^-1 g with every thread busy: `segs` adjacent lanes share a row
         const int n = 2 * v.Ptot;
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int row = warp; row < n; row += kCoarseWarps) {
+        int segs = 32;
+        while (segs > 1 && segs * n > kCoarseThreads) segs >>= 1;
+        const int row = threadIdx.x / segs, seg = threadIdx.x % segs;
+        R ax = 0, ay = 0;
+        if (row < n) {
             const C* Ri = s.rinv + row * n;
-            double ax = 0.0, ay = 0.0;
-            for (int q = lane; q < n; q += 32) {
+            for (int q = seg; q < n; q += segs) {
                 const C rv = Ri[q], g = sg[q];
-                ax += (double)rv.x * g.x - (double)rv.y * g.y;
-                ay += (double)rv.x * g.y + (double)rv.y * g.x;
+                ax += rv.x * g.x - rv.y * g.y;
+                ay += rv.x * g.y + rv.y * g.x;
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                ax += __shfl_down_sync(0xffffffffu, ax, off);
-                ay += __shfl_down_sync(0xffffffffu, ay, off);
-            }
-            if (lane == 0) su[row] = mk<C>((typename real_of<C>::type)ax, (typename real_of<C>::type)ay);
         }
+        for (int off = segs >> 1; off > 0; off >>= 1) {
+            ax += __shfl_xor_sync(0xffffffffu, ax, off);
+            ay += __shfl_xor_sync(0xffffffffu, ay, off);
+        }
+        if (row < n && seg == 0) su[row] = mk<C>(ax, ay);
         __syncthreads();
         for (int t = threadIdx.x; t < len; t += kCoarseThreads) {
-            C e = sl[t];
-            const int kg = t / v.m;
-            if (kg > 0) e = csub(e, cmul(s.sv[t], su[2 * (kg - 1) + 1]));
-            if (kg < v.Ptot - 1) e = csub(e, cmul(s.sw[t], su[2 * (kg + 1)]));
-            sl[t] = e;
+            const int kg = t / v.m, pt = t + kg;
+            C e = sl[pt];
+            if (kg > 0) e = csub(e, cmul(s.sv[pt], su[2 * (kg - 1) + 1]));
+            if (kg < v.Ptot - 1) e = csub(e, cmul(s.sw[pt], su[2 * (kg + 1)]));
+            sl[pt] = e;
         }
         __syncthreads();
     }
+    COARSE_LMARK(lm + 2);
 }
 
 // M x at one point from the five values (out-of-range neighbours have zero coefficients)
@@ -298,17 +353,20 @@ __device__ void coarse_line_phases(CoarseCtx<C>& c, C* z, const C* rhs) {
     const CoarseArgs<C>& a = c.a;
     const int l = blockIdx.x;
     if (l >= a.owners) return;
+    COARSE_LMARK(0);
     if (a.yl.nl > 0) {
         if (l < a.yl.nl) {
             const LineView<C>& v = a.yl;
-            for (int t = threadIdx.x; t < v.len; t += kCoarseThreads) c.sl[t] = ldv(&v.g[(int64_t)t * v.nl + l]);
+            for (int t = threadIdx.x; t < v.len; t += kCoarseThreads) c.sl[t + t / v.m] = ldv(&v.g[(int64_t)t * v.nl + l]);
             __syncthreads();
-            coarse_line_solve<C>(v, c.ys, c.sl, c.sg, c.su);
+            coarse_line_solve<C>(v, c.ys, c.sl, c.sg, c.su, 1);
             const int col = l < v.lo ? l : v.Nx - v.hi + (l - v.lo);
             for (int t = threadIdx.x; t < v.len; t += kCoarseThreads)
-                z[(int64_t)t * v.Nx + col] = cscale(a.omega, c.sl[t]);      // the column was zero
+                z[(int64_t)t * v.Nx + col] = cscale(a.omega, c.sl[t + t / v.m]);      // the column was zero
         }
+        COARSE_LMARK(4);
         if (a.xl.nl > 0) coarse_barrier(a.bar + 2, (unsigned)a.owners, c.gen_own);
+        COARSE_LMARK(5);
     }
     if (a.xl.nl > 0 && l < a.xl.nl) {
         const LineView<C>& v = a.xl;
@@ -321,11 +379,12 @@ __device__ void coarse_line_phases(CoarseCtx<C>& c, C* z, const C* rhs) {
             const C ze = i < a.Nx - 1 ? ldv(&z[pn + 1]) : czero<C>();
             const C zs = j > 0 ? ldv(&z[pn - a.Nx]) : czero<C>();
             const C zn = j < a.Ny - 1 ? ldv(&z[pn + a.Nx]) : czero<C>();
-            c.sl[i] = csub(ldv(&rhs[pn]), coarse_stencil5<C>(pc, zc, zw, ze, zs, zn));
+            c.sl[i + i / v.m] = csub(ldv(&rhs[pn]), coarse_stencil5<C>(pc, zc, zw, ze, zs, zn));
         }
         __syncthreads();
-        coarse_line_solve<C>(v, c.xs, c.sl, c.sg, c.su);
-        for (int i = threadIdx.x; i < v.len; i += kCoarseThreads) v.g[(int64_t)i * v.nl + l] = c.sl[i];
+        coarse_line_solve<C>(v, c.xs, c.sl, c.sg, c.su, 6);
+        for (int i = threadIdx.x; i < v.len; i += kCoarseThreads) v.g[(int64_t)i * v.nl + l] = c.sl[i + i / v.m];
+        COARSE_LMARK(9);
     }
 }
 
@@ -387,19 +446,6 @@ __device__ __forceinline__ void coarse_apply_phase(const CoarseArgs<C>& a, const
         }
     }
 }
-
-// -DFDFD_COARSE_TRACE: CTA 0 prints the time (ns) between the phase boundaries of the second iteration
-#ifdef FDFD_COARSE_TRACE
-__device__ unsigned int g_coarse_trace_count = 0;
-__device__ __forceinline__ unsigned long long coarse_now() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-#define COARSE_MARK(k) do { if (it == 1 && blockIdx.x == 0 && threadIdx.x == 0) tr[k] = coarse_now(); } while (0)
-#else
-#define COARSE_MARK(k) do { } while (0)
-#endif
 
 template <typename C, bool TM>
 __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(CoarseArgs<C> a) {
@@ -571,6 +617,11 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
                    tr[1] - tr[0], tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5], tr[7] - tr[6],
                    tr[8] - tr[7], tr[9] - tr[8], tr[10] - tr[9], tr[11] - tr[10], tr[12] - tr[11], tr[13] - tr[12],
                    tr[14] - tr[13], tr[14] - tr[0]);
+        if (it == 1 && blockIdx.x == 0 && threadIdx.x == 0)
+            printf("[coarse line ns] y: load %llu local %llu interface+spike %llu store %llu | owner bar %llu | x: resid %llu local %llu interface+spike %llu store %llu\n",
+                   g_line_tr[1] - g_line_tr[0], g_line_tr[2] - g_line_tr[1], g_line_tr[3] - g_line_tr[2], g_line_tr[4] - g_line_tr[3],
+                   g_line_tr[5] - g_line_tr[4], g_line_tr[6] - g_line_tr[5], g_line_tr[7] - g_line_tr[6], g_line_tr[8] - g_line_tr[7],
+                   g_line_tr[9] - g_line_tr[8]);
 #endif
     }
 }

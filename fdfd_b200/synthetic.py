@@ -73,22 +73,46 @@ def slab_problem(Nx, Ny, j0, j1, pol="TE", angle_deg=45.0, mask=80, device="cuda
 
 
 def sharded_scattering_solve(Nx, Ny, pol="TE", comm=None, rank=0, world=1, device="cuda", pml=40, mask=80,
-                             solver=None, **kw):
+                             solver=None, repeat=False, **kw):
     """Solve the synthetic scattering problem on `world` y-slabs (one per rank).  Returns
     (x_local (rows, Nx) device tensor, info dict)."""
+    import time
+    import torch
     from .operators import HelmholtzOperator2D, slab_rows
 
+    def lap(t0):
+        torch.cuda.synchronize(device)
+        return time.perf_counter() - t0
+
     j0, j1 = slab_rows(Ny, world, rank)
+    t0 = time.perf_counter()
     ca, cb, cd, sx, sy, src, q = slab_problem(Nx, Ny, j0, j1, pol=pol, mask=mask, device=device, pml=pml, **kw)
+    t_inputs = lap(t0)
+    t0 = time.perf_counter()
     A = HelmholtzOperator2D(pol, Nx, Ny, ca, cb, cd, sx, sy, device=device,
                             rows=(j0, j1) if world > 1 else None, comm=comm)
     s = src.reshape(-1)
     qf = q.reshape(-1)
     b = qf * A.apply(s) - A.apply(qf * s)           # (Q A - A Q) src with two sharded stencil applies
-    opts = dict(method="fgmres", precond="mg", rtol=1e-8, maxit=20000, restart=40 if pol.upper() == "TE" else 30,
-                mg_single=1, basis_single=1,
+    del src, q, s, qf
+    t_operator = lap(t0)
+    lam0 = C0 / kw.get("f0", 10e9)
+    from .scattering import FDFD2DScatteringSolver
+    amp = FDFD2DScatteringSolver.AMPLIFICATION_PER_SQRT_WAVELENGTH * math.sqrt(max(max(Nx, Ny) * (lam0 / 50.0) / lam0, 1.0))
+    opts = dict(method="fgmres", precond="mg", rtol=min(1e-8, 1e-6 / (1.25 * amp)), maxit=20000,
+                restart=40 if pol.upper() == "TE" else 30, mg_single=1, basis_single=1,
                 line_x_lo=pml, line_x_hi=pml, line_y_lo=pml, line_y_hi=pml)
     opts.update(solver or {})
+    t0 = time.perf_counter()
     x, info = A.solve(b, raise_on_noconv=False, **opts)
+    info["solve_wall_s"] = lap(t0)               # preconditioner set-up + Krylov solve
+    info["precond_setup_s"] = info["solve_wall_s"] - info["seconds"]
+    info["inputs_s"], info["operator_rhs_s"], info["rtol"] = t_inputs, t_operator, opts["rtol"]
+    if repeat:
+        # second right-hand side with the cached preconditioner / Krylov arena (angle sweeps)
+        t0 = time.perf_counter()
+        x2, info2 = A.solve(b, raise_on_noconv=False, **opts)
+        info["repeat_wall_s"], info["repeat_device_s"] = lap(t0), info2["seconds"]
+        del x2
     A.close()
     return x.reshape(j1 - j0, Nx), info

@@ -178,6 +178,42 @@ int fdfd_blas_multi_axpy(fdfd_blas_t*, int dtype, int64_t n, int k, const void* 
                          void* w, const double* h_host, double sign, double* nrm2_host, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K6b  batched shift-invert Arnoldi for the Bloch sweep of a unit cell — replaces, for ALL path points at
+ *      once, the per-point operator rebuild + `eigs(A, M, k, sigma)` (ARPACK mode 3 + SuperLU) of
+ *      Band_Diagram_Solver.py:302-323.  One CTA per path point: bordered block LU of the cyclic
+ *      block-tridiagonal A - sigma M in shared memory (never assembled densely), Arnoldi recurrence of
+ *      (A - sigma M)^-1 M with the block substitutions and two-pass Gram-Schmidt inside one kernel per
+ *      restart cycle; only the (ncv+1) x ncv projected matrices travel to the host.
+ *   kind = FDFD_POL_TE / FDFD_POL_TM operator type of K2 with Bloch walls on both axes;
+ *   ca, cb, m: device (Ny, Nx) complex128 (m = diagonal of M, real positive); sx, sy as in fdfd_helm2d_create;
+ *   sigma: real shift LEFT of the spectrum (A - sigma M Hermitian positive definite: no pivoting);
+ *   phases_host: [P][4] = (phx_re, phx_im, phy_re, phy_im) per path point, exp(-1j*k*N*d) as yeeder2d.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct fdfd_band fdfd_band_t;
+int fdfd_band_max_nx(void);      /* widest cell (Nx) whose block factorisation fits in shared memory */
+int fdfd_band_create(fdfd_band_t** out, int kind, int Nx, int Ny, int P, const void* ca, const void* cb,
+                     const void* m, double sx, double sy, double sigma, const double* phases_host,
+                     int ncv, int kmax, void* stream);
+void fdfd_band_destroy(fdfd_band_t*);
+/* v0: device [P][n] unit start vectors */
+int fdfd_band_set_start(fdfd_band_t*, const void* v0, void* stream);
+/* path points that are still iterating (host int array) */
+int fdfd_band_set_active(fdfd_band_t*, const int* idx_host, int count, void* stream);
+/* Arnoldi steps j0 .. j1-1 for the active points; H_host (optional, [P][ncv+1][ncv] complex128) receives the
+ * projected matrices of all points (synchronises) */
+int fdfd_band_cycle(fdfd_band_t*, int j0, int j1, void* H_host, void* stream);
+/* Krylov-Schur restart of the active points (host arrays in active order): V[:keep] = Q V[:ncv],
+ * V[keep] = V[ncv], H <- Hnew;  Q: [Pa][keep][ncv], Hnew: [Pa][ncv+1][ncv] */
+int fdfd_band_restart(fdfd_band_t*, const void* Q_host, const void* Hnew_host, int keep, void* stream);
+/* Ritz vectors (unit rows) of the listed points, S_host: [count][k][ncv], and their true residuals
+ * ||A x - lam M x|| / (||A x|| + |lam| ||M x||) for lam_host [count][k] -> res_host [count][k] */
+int fdfd_band_ritz(fdfd_band_t*, const int* idx_host, int count, const void* S_host, const void* lam_host,
+                   int k, double* res_host, void* stream);
+const void* fdfd_band_vectors(fdfd_band_t*);      /* device [P][kmax][n] */
+/* y = (A - sigma M) x of path point p with the entries the factorisation uses (validation hook) */
+int fdfd_band_apply_shifted(fdfd_band_t*, int p, const void* x, void* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K2b  full-vector mode-solver operator  Omega = P Q  kept as two device CSR matrices
  *      — replaces the explicit product P_reduced @ Q_reduced and eigs' SuperLU solve
  *        (Mode_Solver_2D/Mode_Solver_2D.py:771-780).
