@@ -58,6 +58,10 @@ _PROTOTYPES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdfd_yee2d_csr_fill_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdfd_stagger_csr_fill": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdfd_stagger_csr_fill_host": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdfd_helm2d_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.POINTER(C.c_double), C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]),

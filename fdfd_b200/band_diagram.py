@@ -323,7 +323,6 @@ class BandDiagramSolver2D:
         matrices (same restart logic as `eigs.krylov_schur_batched`)."""
         import ctypes as C
         import time
-        import scipy.linalg as sla
         import torch
         L = _lib.lib()
         n, P, k = self.Nx * self.Ny, beta_path.shape[1], int(num_bands)
@@ -360,28 +359,26 @@ class BandDiagramSolver2D:
             while True:
                 _lib.check(L.fdfd_band_cycle(h, p0, ncv, Hh.ctypes.data, stream))
                 t = lap("t_krylov", t)
+                # projected problems of all active points at once (stacked LAPACK calls).  The operator is
+                # self-adjoint in the M inner product, so its Ritz vectors are well conditioned and the thick
+                # restart keeps the span of the `keep` dominant ones, orthonormalised by QR (the same subspace
+                # an ordered Schur form would keep): A (V Q) = (V Q)(Q^H H Q) + v (b Q).
                 Pa = len(active)
-                done = np.zeros(Pa, dtype=bool)
-                Sk = np.zeros((Pa, k, ncv), dtype=np.complex128)
-                Qk = np.zeros((Pa, keep, ncv), dtype=np.complex128)
+                Hm, b = Hh[active, :ncv, :ncv], Hh[active, ncv, :ncv]
+                mu, S = np.linalg.eig(Hm)
+                order = np.argsort(-np.abs(mu), axis=1)
+                mu = np.take_along_axis(mu, order, axis=1)
+                S = np.take_along_axis(S, order[:, None, :], axis=2)
+                S = S / np.linalg.norm(S, axis=1, keepdims=True)
+                res = np.abs(np.einsum("pc,pck->pk", b, S))
+                done = np.all(res[:, :k] <= tol * np.abs(mu[:, :k]), axis=1) | (restarts >= max_restarts)
+                mus = mu[:, :k]
+                Sk = np.ascontiguousarray(S[:, :, :k].transpose(0, 2, 1))
+                Q, _ = np.linalg.qr(S[:, :, :keep])
                 Tn = np.zeros((Pa, ncv + 1, ncv), dtype=np.complex128)
-                mus = np.zeros((Pa, k), dtype=np.complex128)
-                for a, p in enumerate(active):
-                    Hm, b = Hh[p, :ncv, :ncv], Hh[p, ncv, :ncv]
-                    mu, S = np.linalg.eig(Hm)
-                    order = np.argsort(-np.abs(mu))
-                    mu, S = mu[order], S[:, order]
-                    S = S / np.linalg.norm(S, axis=0, keepdims=True)
-                    res = np.abs(b @ S)
-                    done[a] = np.all(res[:k] <= tol * np.abs(mu[:k])) or restarts >= max_restarts
-                    mus[a] = mu[:k]
-                    Sk[a] = S[:, :k].T
-                    if not done[a]:
-                        thr = np.sort(np.abs(mu))[::-1][keep - 1]
-                        T, Q, _ = sla.schur(Hm, output="complex", sort=lambda x: abs(x) >= thr * (1 - 1e-12))
-                        Qk[a] = Q[:, :keep].T
-                        Tn[a, :keep, :keep] = T[:keep, :keep]
-                        Tn[a, keep, :keep] = b @ Q[:, :keep]
+                Tn[:, :keep, :keep] = np.conj(Q.transpose(0, 2, 1)) @ Hm @ Q
+                Tn[:, keep, :keep] = np.einsum("pc,pck->pk", b, Q)
+                Qk = np.ascontiguousarray(Q.transpose(0, 2, 1))
                 t = lap("t_host_projected", t)
                 fin = np.flatnonzero(done)
                 if fin.size:

@@ -8,8 +8,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-# FDFD_COARSE_TRACE=1 builds an instrumented copy next to the product library (load it with FDFD_B200_LIB=...)
-LIB = os.path.join(HERE, "libfdfd_b200_trace.so" if os.environ.get("FDFD_COARSE_TRACE") else "libfdfd_b200.so")
+# Experiment builds live next to the product library and are loaded with FDFD_B200_LIB=<path>:
+#   FDFD_COARSE_TRACE=1                 -> libfdfd_b200_trace.so   (phase timings of the persistent coarse solver)
+#   FDFD_BUILD_VARIANT="name:-DFLAG=1"  -> libfdfd_b200_<name>.so  (kernel tuning experiments)
+_VARIANT = os.environ.get("FDFD_BUILD_VARIANT", "")
+_VNAME = "trace" if os.environ.get("FDFD_COARSE_TRACE") else (_VARIANT.split(":", 1)[0] if _VARIANT else "")
+LIB = os.path.join(HERE, f"libfdfd_b200_{_VNAME}.so" if _VNAME else "libfdfd_b200.so")
 SOURCES = ["api.cu", "yee_assemble.cu", "helm2d.cu", "blas1.cu", "krylov.cu", "comm.cu", "p2p.cu", "mg.cu", "csr_ops.cu", "band.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
@@ -20,6 +24,8 @@ NVCC_FLAGS = [
 ]
 
 
+if _VARIANT and ":" in _VARIANT:
+    NVCC_FLAGS.extend(_VARIANT.split(":", 1)[1].split())
 if os.environ.get("FDFD_COARSE_TRACE"):
     NVCC_FLAGS.append("-DFDFD_COARSE_TRACE")      # phase timings of the persistent coarse solver (debug)
 
@@ -51,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == fp:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objdir = os.path.join(HERE, "build_trace" if os.environ.get("FDFD_COARSE_TRACE") else "build")
+    objdir = os.path.join(HERE, f"build_{_VNAME}" if _VNAME else "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []

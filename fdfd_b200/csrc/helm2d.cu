@@ -27,8 +27,14 @@ namespace fdfd {
 // Register budget: the loop needs ~70 registers (c128) to keep all seven loads of a row in flight;
 // capping it lower makes ptxas serialise the loads into 3-4 dependent round trips per row
 // (measured: 56 regs / 9 CTAs per SM = 5.3 TB/s, 70 regs / 7 CTAs = 6.35 TB/s at 4096^2).
+#ifndef FDFD_C64_SMOOTH_MINB
+#define FDFD_C64_SMOOTH_MINB 8
+#endif
+#ifndef FDFD_C64_AX_MINB
+#define FDFD_C64_AX_MINB 9
+#endif
 template <typename C> __host__ __device__ constexpr int default_min_blocks(int mode) {
-    return sizeof(C) == 16 ? (mode >= APPLY_JACOBI ? 6 : 7) : (mode >= APPLY_JACOBI ? 8 : 9);
+    return sizeof(C) == 16 ? (mode >= APPLY_JACOBI ? 6 : 7) : (mode >= APPLY_JACOBI ? FDFD_C64_SMOOTH_MINB : FDFD_C64_AX_MINB);
 }
 
 // load an element of the input vector, stored as X (complex64 input of a complex128 operator: the

@@ -126,9 +126,95 @@ int yee2d_fill(int Nx, int Ny, int axis, int bc, const double vals[6], int32_t* 
     return FDFD_OK;
 }
 
+// K1b — staggered-grid operators with two entries per row (rectangular forward differences between the
+// staggered grids of the mode solvers, periodic z difference / forward average of the 3-D solver).
+// Row (i, j, k) of the output grid: (self column, v_self) and (forward column, v_fwd), stored in ascending
+// column order as scipy's coo -> csr leaves them (the periodic wrap puts the forward column first on the
+// last plane).  indptr = 2 * row: closed form, no scan.
+struct StaggerArgs {
+    int inx, iny, inz, onx, ony, onz, axis;
+    double v_self, v_fwd;
+    int32_t* indptr; int32_t* indices; double* data; double* h_data;
+};
+
+__global__ void __launch_bounds__(256) stagger_fill_kernel(StaggerArgs a) {
+    const int64_t rows = (int64_t)a.onx * a.ony * a.onz;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r <= rows; r += stride) {
+        a.indptr[r] = (int32_t)(2 * r);
+        if (r == rows) break;
+        const int i = (int)(r % a.onx);
+        const int64_t q = r / a.onx;
+        const int j = (int)(q % a.ony), k = (int)(q / a.ony);
+        int fi = i, fj = j, fk = k;
+        if (a.axis == 0) ++fi; else if (a.axis == 1) ++fj; else fk = (k + 1) % a.inz;
+        const int64_t cs = i + (int64_t)a.inx * (j + (int64_t)a.iny * k);
+        const int64_t cf = fi + (int64_t)a.inx * (fj + (int64_t)a.iny * fk);
+        const bool self_first = cs < cf;
+        a.indices[2 * r] = (int32_t)(self_first ? cs : cf);
+        a.indices[2 * r + 1] = (int32_t)(self_first ? cf : cs);
+        const double d0 = self_first ? a.v_self : a.v_fwd, d1 = self_first ? a.v_fwd : a.v_self;
+        a.data[2 * r] = d0; a.data[2 * r + 1] = d1;
+        if (a.h_data) { a.h_data[2 * r] = -d0; a.h_data[2 * r + 1] = -d1; }
+    }
+}
+
+int stagger_fill(const int in_shape[3], const int out_shape[3], int axis, double v_self, double v_fwd,
+                 int32_t* indptr, int32_t* indices, double* data, double* h_data, cudaStream_t stream) {
+    FDFD_CHECK_ARG(in_shape && out_shape && indptr && indices && data, "null pointer");
+    FDFD_CHECK_ARG(axis >= 0 && axis <= 2, "axis must be 0, 1 or 2");
+    for (int d = 0; d < 3; ++d) FDFD_CHECK_ARG(in_shape[d] >= 1 && out_shape[d] >= 1, "grid extents must be >= 1");
+    // every forward neighbour must exist: the input grid is one larger along a difference axis (x, y),
+    // equal along the periodic axis (z) and at least as large elsewhere
+    for (int d = 0; d < 3; ++d) {
+        if (d == axis && axis < 2) FDFD_CHECK_ARG(in_shape[d] >= out_shape[d] + 1, "input grid must be one larger along the difference axis");
+        else FDFD_CHECK_ARG(in_shape[d] >= out_shape[d], "input grid smaller than the output grid");
+    }
+    if (axis == 2) FDFD_CHECK_ARG(in_shape[2] == out_shape[2] && in_shape[2] >= 2, "periodic z operator needs equal grids with nz >= 2");
+    const int64_t rows = (int64_t)out_shape[0] * out_shape[1] * out_shape[2];
+    const int64_t cols = (int64_t)in_shape[0] * in_shape[1] * in_shape[2];
+    FDFD_CHECK_ARG(2 * rows < (int64_t)INT32_MAX && cols < (int64_t)INT32_MAX, "operator exceeds the int32 index range");
+    StaggerArgs a{in_shape[0], in_shape[1], in_shape[2], out_shape[0], out_shape[1], out_shape[2], axis, v_self, v_fwd,
+                  indptr, indices, data, h_data};
+    int blocks = (int)((rows + 1 + 255) / 256);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    stagger_fill_kernel<<<blocks, 256, 0, stream>>>(a);
+    FDFD_CUDA(cudaGetLastError());
+    return FDFD_OK;
+}
+
 }  // namespace fdfd
 
 using namespace fdfd;
+
+extern "C" int fdfd_stagger_csr_fill(const int in_shape[3], const int out_shape[3], int axis, double v_self, double v_fwd,
+                                     int32_t* indptr, int32_t* indices, double* data, double* h_data, void* stream) {
+    return stagger_fill(in_shape, out_shape, axis, v_self, v_fwd, indptr, indices, data, h_data, (cudaStream_t)stream);
+}
+
+extern "C" int fdfd_stagger_csr_fill_host(const int in_shape[3], const int out_shape[3], int axis, double v_self,
+                                          double v_fwd, int32_t* indptr, int32_t* indices, double* data, double* h_data) {
+    FDFD_CHECK_ARG(in_shape && out_shape && indptr && indices && data, "null pointer");
+    for (int d = 0; d < 3; ++d) FDFD_CHECK_ARG(out_shape[d] >= 1, "grid extents must be >= 1");
+    const int64_t rows = (int64_t)out_shape[0] * out_shape[1] * out_shape[2];
+    int32_t *d_ptr = nullptr, *d_idx = nullptr;
+    double *d_e = nullptr, *d_h = nullptr;
+    int st = FDFD_OK;
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_ptr, (rows + 1) * 4)) != cudaSuccess || (e = cudaMalloc(&d_idx, 2 * rows * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&d_e, 2 * rows * 8)) != cudaSuccess || (h_data && (e = cudaMalloc(&d_h, 2 * rows * 8)) != cudaSuccess))
+        st = cuda_fail(e, "cudaMalloc (stagger host fill)", __FILE__, __LINE__);
+    if (st == FDFD_OK) st = stagger_fill(in_shape, out_shape, axis, v_self, v_fwd, d_ptr, d_idx, d_e, d_h, 0);
+    if (st == FDFD_OK) {
+        if ((e = cudaMemcpy(indptr, d_ptr, (rows + 1) * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+            (e = cudaMemcpy(indices, d_idx, 2 * rows * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+            (e = cudaMemcpy(data, d_e, 2 * rows * 8, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+            (h_data && (e = cudaMemcpy(h_data, d_h, 2 * rows * 8, cudaMemcpyDeviceToHost)) != cudaSuccess))
+            st = cuda_fail(e, "cudaMemcpy D2H (stagger host fill)", __FILE__, __LINE__);
+    }
+    cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_e); cudaFree(d_h);
+    return st;
+}
 
 extern "C" int fdfd_yee2d_csr_nnz(int Nx, int Ny, int bcx, int bcy, int64_t* nnz_dex,
                                   int64_t* nnz_dey, int* dex_is_complex, int* dey_is_complex) {

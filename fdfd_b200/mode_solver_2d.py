@@ -407,30 +407,19 @@ class ModeSolver2D:
 
     # ---- staggered difference operators (Mode_Solver_2D.py:482-544) ---------------------------------------
     @staticmethod
-    def _difference(in_shape, out_shape, scale, axis):
-        onx, ony = out_shape
-        inx, iny = in_shape
-        i = np.tile(np.arange(onx), ony)
-        j = np.repeat(np.arange(ony), onx)
-        row = i + j * onx
-        r, c, v = [], [], []
-        for di, dj, val in ((1 - axis, axis, 1.0), (0, 0, -1.0)):
-            ci, cj = i + di, j + dj
-            ok = (ci < inx) & (cj < iny)
-            r.append(row[ok]); c.append((ci + cj * inx)[ok]); v.append(np.full(int(ok.sum()), val / scale))
-        return sp.coo_matrix((np.concatenate(v), (np.concatenate(r), np.concatenate(c))),
-                             shape=(onx * ony, inx * iny)).tocsr()
+    def _difference(in_shape, out_shape, scale, axis, with_h=True):
+        """Rectangular forward difference between two staggered grids and its H-field counterpart -D^H,
+        assembled by the K1b kernel (csrc/yee_assemble.cu: stagger_fill_kernel); byte-identical to the
+        reference's Python double loop + coo -> csr (Mode_Solver_2D.py:482-514)."""
+        from . import stagger
+        return stagger.difference(in_shape, out_shape, scale, axis, with_h=with_h)
 
     def _yeeder2d(self):
         dx, dy = self.dx_normalized, self.dy_normalized
-        self.DEX_EZ_TO_EX = self._difference(self.shape_ez, self.shape_ex, dx, 0)
-        self.DEY_EZ_TO_EY = self._difference(self.shape_ez, self.shape_ey, dy, 1)
-        self.DEX_EY_TO_HZ = self._difference(self.shape_ey, self.shape_hz, dx, 0)
-        self.DEY_EX_TO_HZ = self._difference(self.shape_ex, self.shape_hz, dy, 1)
-        self.DHX_HY_TO_EZ = -self.DEX_EZ_TO_EX.conj().T
-        self.DHY_HX_TO_EZ = -self.DEY_EZ_TO_EY.conj().T
-        self.DHX_HZ_TO_HX = -self.DEX_EY_TO_HZ.conj().T
-        self.DHY_HZ_TO_HY = -self.DEY_EX_TO_HZ.conj().T
+        self.DEX_EZ_TO_EX, self.DHX_HY_TO_EZ = self._difference(self.shape_ez, self.shape_ex, dx, 0)
+        self.DEY_EZ_TO_EY, self.DHY_HX_TO_EZ = self._difference(self.shape_ez, self.shape_ey, dy, 1)
+        self.DEX_EY_TO_HZ, self.DHX_HZ_TO_HX = self._difference(self.shape_ey, self.shape_hz, dx, 0)
+        self.DEY_EX_TO_HZ, self.DHY_HZ_TO_HY = self._difference(self.shape_ex, self.shape_hz, dy, 1)
         self.DEX, self.DEY, self.DHX, self.DHY = (self.DEX_EY_TO_HZ, self.DEY_EX_TO_HZ, self.DHX_HY_TO_EZ,
                                                   self.DHY_HX_TO_EZ)
         return (self.DEX_EZ_TO_EX, self.DEY_EZ_TO_EY, self.DEX_EY_TO_HZ, self.DEY_EX_TO_HZ,

@@ -56,7 +56,6 @@ class PeriodicModeSolver3D:
         self.material_no_average_mask = np.zeros(self.shape_cell, dtype=bool)
         self._pec_regions, self._pmc_regions = [], []
         self.device = device
-        self._init_operators()
         self.update_component_materials()
         self.fields = {}
         self.eigenvalues = self.eigenvectors = None
@@ -67,52 +66,33 @@ class PeriodicModeSolver3D:
         self.eigenvalues = self.eigenvectors = None
         self.__dict__.pop("gammas", None)
 
-    # ---- operators (Periodic_Solver_3D.py:95-194), vectorised ---------------------------------------------
-    @staticmethod
-    def _ijk(shape):
-        nx, ny, nz = shape
-        i = np.tile(np.arange(nx), ny * nz)
-        j = np.tile(np.repeat(np.arange(ny), nx), nz)
-        k = np.repeat(np.arange(nz), nx * ny)
-        return i, j, k
+    # ---- operators (Periodic_Solver_3D.py:95-194): GPU assembly ---------------------------------------------
+    _OPERATORS = ("DEX_EZ_TO_EX", "DEY_EZ_TO_EY", "DEX_EY_TO_HZ", "DEY_EX_TO_HZ", "DHX_HY_TO_EZ", "DHY_HX_TO_EZ",
+                  "DHX_HZ_TO_HX", "DHY_HZ_TO_HY", "DEZ_EX", "DEZ_EY", "DHZ_HX", "DHZ_HY", "AZ_EX", "AZ_EY", "AZ_HX", "AZ_HY")
 
-    @classmethod
-    def _difference(cls, in_shape, out_shape, scale, axis):
-        i, j, k = cls._ijk(out_shape)
-        row = i + out_shape[0] * (j + out_shape[1] * k)
-        r, c, v = [], [], []
-        for di, dj, val in ((1 - axis, axis, 1.0), (0, 0, -1.0)):
-            ci, cj = i + di, j + dj
-            ok = (ci < in_shape[0]) & (cj < in_shape[1]) & (k < in_shape[2])
-            r.append(row[ok]); c.append((ci + in_shape[0] * (cj + in_shape[1] * k))[ok])
-            v.append(np.full(int(ok.sum()), val / scale))
-        return sp.coo_matrix((np.concatenate(v), (np.concatenate(r), np.concatenate(c))),
-                             shape=(int(np.prod(out_shape)), int(np.prod(in_shape)))).tocsr()
-
-    @classmethod
-    def _periodic_z(cls, shape, forward_weight, self_weight):
-        i, j, k = cls._ijk(shape)
-        row = i + shape[0] * (j + shape[1] * k)
-        nxt = i + shape[0] * (j + shape[1] * ((k + 1) % shape[2]))
-        n = row.size
-        return sp.coo_matrix((np.concatenate([np.full(n, forward_weight), np.full(n, self_weight)]),
-                              (np.concatenate([row, row]), np.concatenate([nxt, row]))), shape=(n, n)).tocsr()
+    def __getattr__(self, name):
+        # the sixteen staggered operators are assembled on the GPU on first use (the reference builds them
+        # with Python triple loops in its constructor, Periodic_Solver_3D.py:95-194)
+        if name in type(self)._OPERATORS and "shape_ex" in self.__dict__:
+            self._init_operators()
+            return self.__dict__[name]
+        raise AttributeError(name)
 
     def _init_operators(self):
-        self.DEX_EZ_TO_EX = self._difference(self.shape_ez, self.shape_ex, self.dx, 0)
-        self.DEY_EZ_TO_EY = self._difference(self.shape_ez, self.shape_ey, self.dy, 1)
-        self.DEX_EY_TO_HZ = self._difference(self.shape_ey, self.shape_hz, self.dx, 0)
-        self.DEY_EX_TO_HZ = self._difference(self.shape_ex, self.shape_hz, self.dy, 1)
-        self.DHX_HY_TO_EZ = -self.DEX_EZ_TO_EX.conj().T
-        self.DHY_HX_TO_EZ = -self.DEY_EZ_TO_EY.conj().T
-        self.DHX_HZ_TO_HX = -self.DEX_EY_TO_HZ.conj().T
-        self.DHY_HZ_TO_HY = -self.DEY_EX_TO_HZ.conj().T
-        self.DEZ_EX = self._periodic_z(self.shape_ex, 1.0 / self.dz, -1.0 / self.dz)
-        self.DEZ_EY = self._periodic_z(self.shape_ey, 1.0 / self.dz, -1.0 / self.dz)
-        self.DHZ_HX = -self.DEZ_EY.conj().T
-        self.DHZ_HY = -self.DEZ_EX.conj().T
-        self.AZ_EX = self._periodic_z(self.shape_ex, 0.5, 0.5)
-        self.AZ_EY = self._periodic_z(self.shape_ey, 0.5, 0.5)
+        """K1b kernel (csrc/yee_assemble.cu: stagger_fill_kernel) through fdfd_b200.stagger: two entries per
+        row, byte-identical to the reference's loops + coo -> csr; H operators are the CSC reading of the same
+        index arrays with negated data (-D^H)."""
+        from . import stagger
+        d = stagger.difference
+        self.DEX_EZ_TO_EX, self.DHX_HY_TO_EZ = d(self.shape_ez, self.shape_ex, self.dx, 0, with_h=True)
+        self.DEY_EZ_TO_EY, self.DHY_HX_TO_EZ = d(self.shape_ez, self.shape_ey, self.dy, 1, with_h=True)
+        self.DEX_EY_TO_HZ, self.DHX_HZ_TO_HX = d(self.shape_ey, self.shape_hz, self.dx, 0, with_h=True)
+        self.DEY_EX_TO_HZ, self.DHY_HZ_TO_HY = d(self.shape_ex, self.shape_hz, self.dy, 1, with_h=True)
+        # periodic z difference: forward weight 1/dz, self weight -1/dz (no Bloch phase, :172)
+        self.DEZ_EX, self.DHZ_HY = stagger.stagger_csr(self.shape_ex, self.shape_ex, 2, -1.0 / self.dz, 1.0 / self.dz, with_h=True)
+        self.DEZ_EY, self.DHZ_HX = stagger.stagger_csr(self.shape_ey, self.shape_ey, 2, -1.0 / self.dz, 1.0 / self.dz, with_h=True)
+        self.AZ_EX = stagger.periodic_z(self.shape_ex, 0.5, 0.5)
+        self.AZ_EY = stagger.periodic_z(self.shape_ey, 0.5, 0.5)
         self.AZ_HX = self.AZ_EY.conj().T
         self.AZ_HY = self.AZ_EX.conj().T
 

@@ -77,6 +77,24 @@ int fdfd_yee2d_csr_fill_host(int Nx, int Ny, int axis, int bc, const double vals
                              int32_t* indptr, int32_t* indices, void* e_data, void* h_data);
 
 /* ------------------------------------------------------------------------------------------
+ * K1b  staggered-grid operators with two entries per row — replaces the Python loops of
+ *      Mode_Solver_2D/Mode_Solver_2D.py:482-544 (_difference_matrix_x/_y between the Ez / Ex / Ey / Hz grids)
+ *      and Periodic_Solver_3D/Periodic_Solver_3D.py:95-194 (_difference_matrix_x/_y, the periodic z difference
+ *      _periodic_difference_matrix_z and the forward average _periodic_forward_average_z).
+ *   Grids are (nx, ny, nz) with x fastest (2-D: nz = 1).  Row (i, j, k) of the OUTPUT grid holds
+ *       (column (i, j, k) of the input grid, v_self)   and
+ *       (column (i+1, j, k) | (i, j+1, k) | (i, j, (k+1) mod nz) for axis 0 | 1 | 2, v_fwd)
+ *   in ascending column order, exactly what scipy's coo -> csr conversion produces; int32 index arrays,
+ *   float64 data (2 per row).  v_self / v_fwd are evaluated by the caller with the reference's expressions
+ *   (-1/d, +1/d or 0.5, 0.5).  h_data (optional) = -data: the CSC arrays of -D^H share indptr / indices.
+ * ------------------------------------------------------------------------------------------ */
+int fdfd_stagger_csr_fill(const int in_shape[3], const int out_shape[3], int axis, double v_self, double v_fwd,
+                          int32_t* indptr, int32_t* indices, double* data, double* h_data, void* stream);
+/* same, HOST output buffers */
+int fdfd_stagger_csr_fill_host(const int in_shape[3], const int out_shape[3], int axis, double v_self, double v_fwd,
+                               int32_t* indptr, int32_t* indices, double* data, double* h_data);
+
+/* ------------------------------------------------------------------------------------------
  * K2  matrix-free complex Helmholtz / curl-curl operator on an Nx x Ny (slab of a) Yee grid
  *     — replaces the explicit sparse products of
  *       _build_A_TE / _build_A_TM   (Scattering_Solver_2D.py:176-188) and

@@ -118,10 +118,14 @@ def test_mode_host_logic_and_oracle(case):
     for n in names:
         assert np.array_equal(getattr(ref, n), getattr(mine, n), equal_nan=True), n
     assert ref._resolve_eigs_guess(None) == mine._resolve_eigs_guess(None)
-    for a, b in zip(ref._yeeder2d(), mine._yeeder2d()):
-        assert a.shape == b.shape and a.format == b.format
-        assert a.indptr.tobytes() == b.indptr.tobytes() and a.indices.tobytes() == b.indices.tobytes()
-        assert a.data.tobytes() == b.data.tobytes()
+    # the eight staggered operators: the product assembles them on the GPU (K1b; tests/test_stagger_gpu.py
+    # byte-compares it with this oracle), here the oracle is pinned against the reference
+    D = mo.operators(ref.Nx, ref.Ny, ref.dx_normalized, ref.dy_normalized)
+    for a, name in zip(ref._yeeder2d(), ("d_ez_ex", "d_ez_ey", "d_ey_hz", "d_ex_hz", "d_hy_ez", "d_hx_ez", "d_hz_hx", "d_hz_hy")):
+        b = D[name]
+        assert a.shape == b.shape and a.format == b.format, name
+        assert a.indptr.tobytes() == b.indptr.tobytes() and a.indices.tobytes() == b.indices.tobytes(), name
+        assert a.data.tobytes() == b.data.tobytes(), name
     rm, mm = ref._effective_materials_and_masks(), mine._effective_materials_and_masks()
     for k in rm[0]:
         assert np.array_equal(rm[0][k], mm[0][k]), k
@@ -137,10 +141,8 @@ def test_mode_host_logic_and_oracle(case):
                  ref.num_modes, ref._resolve_eigs_guess(None), ref._has_lossy_material())
     assert np.max(np.abs(o["eigenvalues"] - ref.eigenvalues)) <= 1e-10 * np.abs(ref.eigenvalues).max()
     assert np.max(np.abs(o["neff"] - ref.neff)) <= 1e-10
-    # the factored operator the GPU path uses equals the reference's Omega
-    f = mine._factors()
-    Om = (f["P_e"] @ f["Q_e"])
-    assert abs(Om - o["Omega"]).max() <= 1e-12 * abs(o["Omega"]).max()
+    # (the factored operator the GPU path uses, P_e Q_e = Omega, is checked in tests/test_stagger_gpu.py: its
+    # staggered operators come from the GPU assembly kernel)
 
 
 def _p3d_cases():
@@ -171,13 +173,14 @@ def test_periodic3d_host_logic_and_oracle(case):
     D = po.operators(ref.Nx, ref.Ny, ref.Nz, ref.dx, ref.dy, ref.dz)
     for name in ops:
         r = getattr(ref, name)
-        for other in (getattr(mine, name), D[name]):
-            assert r.shape == other.shape and r.format == other.format, name
-            assert r.indptr.tobytes() == other.indptr.tobytes() and r.indices.tobytes() == other.indices.tobytes(), name
-            assert r.data.tobytes() == other.data.tobytes(), name
+        other = D[name]         # the product's GPU-assembled operators: tests/test_stagger_gpu.py
+        assert r.shape == other.shape and r.format == other.format, name
+        assert r.indptr.tobytes() == other.indptr.tobytes() and r.indices.tobytes() == other.indices.tobytes(), name
+        assert r.data.tobytes() == other.data.tobytes(), name
     Ar, Br = ref._build_eigen_matrices()
-    Am, Bm = mine._build_eigen_matrices()
-    assert (Ar != Am).nnz == 0 and (Br != Bm).nnz == 0
+    cell_o = {k: getattr(ref, f"cell_{k[0].upper()}{k[1:]}_3D") for k in ("erxx", "eryy", "erzz", "mrxx", "mryy", "mrzz")}
+    Ao, Bo = po.pencil(po.materials_on_fields(cell_o, ref.material_no_average_mask), D, ref.omega)
+    assert abs(Ar - Ao).max() <= 1e-12 * abs(Ar).max() and abs(Br - Bo).max() == 0
     if case != "tiny":
         return
     ref.solve(**kw)
