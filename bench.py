@@ -5,8 +5,15 @@ Metric (BASELINE.json): Yee-operator GB/s against the HBM roofline, plus time-to
 4096^2 scattering problem.  One *step* = one matrix-free application y = A x of the complex128
 TE (Ez) scattering operator on this rank's 4096 x 4096 y-slab (SURVEY.md §8d inputs: 50 cells
 per wavelength, eps_r = -1e6 cylinder, UPML 40).  N ranks hold a 4096 x (4096 N) global grid
-(weak scaling; one halo row per neighbour per step over NCCL).  Algorithmic bytes per step and
-rank: 80 B/point (x, y, ca, cb, cd once each).
+(weak scaling; the stencil kernel pushes its two edge rows into the neighbours' peer-mapped
+receive buffers over NVLink, no collective call).  Algorithmic bytes per step and rank:
+80 B/point (x, y, ca, cb, cd once each).
+
+The line also carries `solve`: STRONG scaling of the time-to-solution — the same problems at every N,
+solved through the same code path (inputs built on the device per y-slab, sharded multigrid-
+preconditioned FGMRES), set-up and solve reported separately:
+  * 4096^2 TE (BASELINE metric), residual tolerance derived from the 1e-6 field bar;
+  * 16384^2 (BASELINE configs[4]) — see SOLVE_LARGE below.
 
   python bench.py --gpus N --steps K --warmup W           # this repository's CUDA path
   python bench.py --impl reference ...                    # the reference's scipy CPU path
@@ -33,7 +40,7 @@ NX = 4096
 ROWS_PER_RANK = 4096
 POL = "TE"
 BYTES_PER_POINT = 80
-CPU_SAMPLE_ROWS = 1024
+CPU_SAMPLE_ROWS = 4096          # the whole grid: the reference arm runs the same configuration
 
 
 def measured_peak():
@@ -80,9 +87,9 @@ def run_reference(args):
     if rank != 0:
         return
     r = cpu_spmv_sample(max(args.steps, 1), max(args.warmup, 1))
-    sample = (f"{NX}x{CPU_SAMPLE_ROWS} slab of the {NX}x{ROWS_PER_RANK} scattering grid (same materials), "
-              f"A assembled with scipy sparse products as the reference does (nnz {r['nnz']}), "
-              f"{max(args.steps, 1)} x `A @ x` (scipy CSR/CSC SpMV, complex128)")
+    sample = (f"the full {NX}x{CPU_SAMPLE_ROWS} scattering grid, A assembled with scipy sparse products as the "
+              f"reference does ({r['build_s']:.0f} s, nnz {r['nnz']}), {max(args.steps, 1)} x `A @ x` "
+              f"(scipy CSR/CSC SpMV, complex128, {r['seconds_per_step'] * 1e3:.0f} ms each)")
     line = {
         "impl": "reference", "metric": "yee_operator_GBps", "value": round(r["value"], 3), "unit": "GB/s",
         "n_gpus": args.gpus, "steps": max(args.steps, 1), "warmup": max(args.warmup, 1),
@@ -257,68 +264,75 @@ def run_ours(args):
                      "kernel": "helm2d_march_kernel<double2, TE, APPLY_AX>",
                      "algorithmic_bytes_per_launch": bytes_rank},
     }
-    if world > 1 and not args.no_solve:
-        # strong scaling of the time-to-solution: the SAME 4096^2 TE problem split into `world` y-slabs
-        # (inputs generated on the device per slab; sharded multigrid-preconditioned FGMRES)
-        N = args.solve_size
-        barrier()
-        t0 = time.perf_counter()
-        xs, info = synthetic.sharded_scattering_solve(N, N, pol="TE", comm=comm, rank=rank, world=world, device=dev)
-        torch.cuda.synchronize(dev)
-        tt = torch.tensor([time.perf_counter() - t0, info["seconds"]], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        line["solve"] = {"grid": f"{N}x{N}", "pol": "TE", "scaling": "strong", "n_gpus": world,
-                         "time_to_solution_s": round(float(tt[0]), 3), "device_solve_s": round(float(tt[1]), 3),
-                         "iterations": info["iterations"], "relres": info["relres"], "converged": info["converged"],
-                         "inputs": "synthetic, generated on the device per y-slab"}
-        del xs
-    if world == 1 and rank == 0:
-        if not args.no_solve:
-            line["solve"] = time_to_solution(args)
-        if not args.no_cpu:
-            r = cpu_spmv_sample(10, 2)
-            line["cpu_baseline"] = {
-                "value": round(r["value"], 3), "unit": "GB/s", "cores": 1, "kind": "port",
-                "sample": f"{NX}x{CPU_SAMPLE_ROWS} slab of the workload, scipy sparse-product assembly "
-                          f"({r['build_s']:.1f} s) + 10 x CSR SpMV `A @ x` ({r['seconds_per_step'] * 1e3:.1f} ms each)",
-                "host_cores": r["host_threads_available"]}
+    # release the apply benchmark's arrays before the solves (the 16384^2 problem needs the memory)
+    A.close()
+    del A, ca, cb, cd, x, y, xh, yh, xn, yn
+    torch.cuda.empty_cache()
+    if not args.no_solve:
+        line["solve"] = [solve_record(N, pol, opts, comm, rank, world, dev, barrier) if world >= need else
+                         {"grid": f"{N}x{N}", "pol": pol, "n_gpus": world, "skipped":
+                          f"needs >= {need} GPUs: FGMRES({opts.get('restart')}) basis + corrections do not fit 180 GB"}
+                         for N, pol, opts, need in solve_plan(args, world)]
+    if world == 1 and rank == 0 and not args.no_cpu:
+        r = cpu_spmv_sample(5, 1)
+        line["cpu_baseline"] = {
+            "value": round(r["value"], 3), "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"the full {NX}x{CPU_SAMPLE_ROWS} workload grid: scipy sparse-product assembly "
+                      f"({r['build_s']:.1f} s) + 5 x CSR SpMV `A @ x` ({r['seconds_per_step'] * 1e3:.1f} ms each)",
+            "host_cores": r["host_threads_available"]}
     if rank == 0:
         print(json.dumps(line), file=_OUT, flush=True)
     if comm is not None:
-        A.close()
         comm.close()
         dist.destroy_process_group()
 
 
-def time_to_solution(args):
-    """Time-to-solution of the 4096^2 TE scattering problem through the drop-in class (host numpy in,
-    host numpy out): BASELINE.json's second headline number."""
+# Strong-scaling time-to-solution.  Same code path at every N (fdfd_b200.synthetic.sharded_scattering_solve:
+# inputs built on the device for this rank's y-slab, FGMRES + mixed-precision multigrid, complex64 basis), the
+# same solver options at every N, set-up and solve timed separately (max over ranks).
+#   4096^2 TE : BASELINE.json's "time-to-solution at 4096^2 grid, 1-8 GPUs".
+#   16384^2   : BASELINE.json configs[4] (2.7e8 unknowns).  TM (Hz) converges with FGMRES(10) and fits one GPU, so it
+#               is the curve with an N = 1 point.  TE (Ez; configs[4] says "TEz") needs FGMRES(40) — with restart 24,
+#               the longest whose Krylov vectors fit beside the operator in 180 GB, it stagnates at 1e-3 (measured,
+#               12 300 iterations) — i.e. 174 GB of basis + corrections: it is solved from N = 2 up and its strong
+#               scaling is read relative to N = 2.
+SOLVE_LARGE = [dict(N=16384, pol="TM", opts=dict(restart=10), min_gpus=1),
+               dict(N=16384, pol="TE", opts=dict(restart=40), min_gpus=2)]
+
+
+def solve_plan(args, world):
+    if args.solve_size:
+        return [(args.solve_size, args.solve_pol, {}, 1)]
+    plan = [(4096, "TE", {}, 1)]
+    if args.solve_large != "off":
+        plan += [(c["N"], c["pol"], dict(c["opts"]), c["min_gpus"]) for c in SOLVE_LARGE]
+    return plan
+
+
+def solve_record(N, pol, opts, comm, rank, world, dev, barrier):
     import torch
-    import fdfd_b200
-    N = args.solve_size
-    f0 = 10e9
-    lam = 299792458 / f0
+    import torch.distributed as dist
+    from fdfd_b200 import synthetic
+    barrier()
     t0 = time.perf_counter()
-    sim = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N)
-    sim.add_object(-1e6, 1.0, (sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
-    sim.add_UPML(pml_width=40, sigma_max=10)
-    sim.add_mask(80)
-    sim.add_source("plane_wave", angle_deg=45.0, polarization="TE")
-    t1 = time.perf_counter()
-    try:
-        F = sim.solve_total_field_TE()
-        info = sim.solver_info["TE"]
-        ok = True
-    except fdfd_b200.NoConvergence as e:
-        info, ok = (e.info or {}), False
-    torch.cuda.synchronize()
-    t2 = time.perf_counter()
-    return {"grid": f"{N}x{N}", "pol": "TE", "host_setup_s": round(t1 - t0, 3),
-            "time_to_solution_s": round(t2 - t1, 3), "device_solve_s": round(info.get("seconds", float("nan")), 3),
-            "iterations": info.get("iterations"), "relres": info.get("relres"), "converged": ok,
-            "method": info.get("method"), "precond": info.get("precond"),
-            "reference": "scipy SuperLU direct solve is infeasible at this size (LU ~3.7e9 nnz > RAM, SURVEY.md §6); "
-                         "2048^2 takes 259 s on 8 cores"}
+    xs, info = synthetic.sharded_scattering_solve(N, N, pol=pol, comm=comm, rank=rank, world=world, device=dev,
+                                                  solver=opts)
+    torch.cuda.synchronize(dev)
+    keys = ("inputs_s", "operator_rhs_s", "precond_setup_s", "seconds")
+    tt = torch.tensor([time.perf_counter() - t0] + [float(info[k]) for k in keys], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    del xs
+    torch.cuda.empty_cache()
+    tt = [float(v) for v in tt]
+    return {"grid": f"{N}x{N}", "pol": pol, "scaling": "strong", "n_gpus": world,
+            "time_to_solution_s": round(tt[0], 3),
+            "setup_s": {"inputs_on_device": round(tt[1], 3), "operator_and_rhs": round(tt[2], 3),
+                        "preconditioner": round(tt[3], 3)},
+            "device_solve_s": round(tt[4], 3), "iterations": info["iterations"], "relres": info["relres"],
+            "rtol": info["rtol"], "converged": info["converged"], "options": opts,
+            "data_path": "nvlink-peer-memory" if (comm is not None and comm.peer_mapped) else ("nccl" if world > 1 else "single"),
+            "inputs": "synthetic, generated on the device per y-slab"}
 
 
 def _quiet_stdout():
@@ -338,7 +352,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--solve-size", type=int, default=4096)
+    ap.add_argument("--solve-size", type=int, default=0, help="solve only this grid size (default: the plan above)")
+    ap.add_argument("--solve-pol", default="TE")
+    ap.add_argument("--solve-large", default="on", choices=["on", "off"], help="include the 16384^2 solves")
     args = ap.parse_args()
     global _OUT
     _OUT = _quiet_stdout()

@@ -237,7 +237,7 @@ extern "C" void fdfd_krylov_default_opts(fdfd_krylov_opts* o) {
     o->mg_omega = 0.7;
     o->mg_cycle = 1;
     o->mg_coarse_its = 0;          /* 0 = automatic from k*h of the coarsest level */
-    o->mg_coarse_mode = 1;
+    o->mg_coarse_mode = 2;         /* persistent kernel where the level fits it, launch chain otherwise */
     o->mg_graph = 1;
     o->mg_coarse_replicate = -1;
     o->mg_single = 0;

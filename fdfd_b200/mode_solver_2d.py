@@ -19,7 +19,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import eigs as _eigs
-from .operators import CsrProductOperator
+from .operators import CsrOperator, CsrProductOperator
 
 _COMPS = ("xx", "yy", "zz")
 
@@ -490,27 +490,37 @@ class ModeSolver2D:
                                                          dtype=torch.complex128)
         self.solver_info = dict(restarts=restarts, residuals=res, n=n_free, sigma=sigma, **stats)
         eigenvalues = lam
-        vec_red = X.T.cpu().numpy()
-        eigenvectors = np.zeros((self.n_e, self.num_modes), dtype=complex)
-        eigenvectors[f["free_e"], :] = vec_red
         order = np.argsort(np.real(eigenvalues))
         self.eigenvalues = eigenvalues[order]
-        Exy = eigenvectors[:, order]
-        self.eigenvectors = Exy
         self.neff = self._passive_positive_neff(-self.eigenvalues)
         self.propagation_constant = np.real(self.neff)
         self.attenuation_constant = np.imag(self.neff)
         root = np.sqrt(self.eigenvalues)
         if np.any(np.abs(root) < 1e-300):
             raise ValueError("Encountered a near-zero eigenvalue while reconstructing magnetic fields.")
-        # field reconstruction (Mode_Solver_2D.py:792-805), host side
+        # field reconstruction (Mode_Solver_2D.py:792-805) on the device: H = Q E / sqrt(lambda) and the two curls
+        # are sparse mat-vecs with the device CSR kernel on the Ritz vectors where the eigen-solver left them;
+        # the six fields come back to the host once
+        dev, k = Om.device, self.num_modes
         d_ey_hz, d_ex_hz, d_hy_ez, d_hx_ez = f["ops"]
+        idx = lambda mask: torch.from_numpy(np.flatnonzero(mask)).to(dev)  # noqa: E731
+        Exy_d = torch.zeros((k, self.n_e), dtype=torch.complex128, device=dev)
+        Exy_d[:, idx(f["free_e"])] = X[torch.from_numpy(order.copy()).to(dev)]
+        inv_root = torch.from_numpy(1.0 / root).to(dev).unsqueeze(1)
+        Hxy_d = torch.zeros((k, self.n_h), dtype=torch.complex128, device=dev)
+        Hxy_d[:, idx(f["free_h"])] = CsrOperator(f["Q_red"], device=dev).apply_rows(Exy_d) * inv_root
+        ex_d, ey_d = Exy_d[:, :self.n_ex].contiguous(), Exy_d[:, self.n_ex:].contiguous()
+        hx_d, hy_d = Hxy_d[:, :self.n_hx].contiguous(), Hxy_d[:, self.n_hx:].contiguous()
+        dvec = lambda D: torch.from_numpy(np.ascontiguousarray(D.diagonal(), dtype=np.complex128)).to(dev)  # noqa: E731
+        op = lambda D: CsrOperator(D, device=dev)  # noqa: E731
+        ez_d = dvec(f["ezi"]) * (op(d_hy_ez).apply_rows(hy_d) - op(d_hx_ez).apply_rows(hx_d))
+        hz_d = dvec(f["mzi"]) * (op(d_ey_hz).apply_rows(ey_d) - op(d_ex_hz).apply_rows(ex_d))
+        host = lambda t: np.ascontiguousarray(t.cpu().numpy().T)  # noqa: E731  -> (n, k) as the reference stores them
+        Exy, Hxy = host(Exy_d), host(Hxy_d)
+        self.eigenvectors = Exy
         ex, ey = Exy[:self.n_ex, :], Exy[self.n_ex:, :]
-        Hxy = np.zeros((self.n_h, self.num_modes), dtype=complex)
-        Hxy[f["free_h"], :] = (f["Q_red"] @ Exy) @ np.diag(1.0 / root)
         hx, hy = Hxy[:self.n_hx, :], Hxy[self.n_hx:, :]
-        ez = np.asarray(f["ezi"] @ (d_hy_ez @ hy - d_hx_ez @ hx), dtype=complex)
-        hz = np.asarray(f["mzi"] @ (d_ey_hz @ ey - d_ex_hz @ ex), dtype=complex)
+        ez, hz = host(ez_d), host(hz_d)
         # NB: copies — in the reference `Ex`/`Ey` are *views* of `eigenvectors` (Mode_Solver_2D.py:797-798,
         # 807-808), so its most-real rotation (:711-725) hits them twice and leaves Ex, Ey and the
         # eigenvectors with a run-dependent phase; here all six fields share one consistent phase.

@@ -266,7 +266,7 @@ class CsrProductOperator:
 
 
 class CsrOperator:
-    """y = A x (+ shift x) for one square scipy CSR matrix uploaded to the device."""
+    """y = A x (+ shift x) for one scipy CSR matrix uploaded to the device (rectangular allowed when shift = 0)."""
 
     def __init__(self, A, shift=0.0, device=None):
         torch = _torch()
@@ -274,9 +274,11 @@ class CsrOperator:
         self._L = _lib.lib()
         self.device = torch.device(device or "cuda")
         A = A.tocsr()
-        if A.shape[0] != A.shape[1]:
-            raise ValueError("square matrix expected")
-        self.n = A.shape[0]
+        self.shape = tuple(int(v) for v in A.shape)
+        if A.shape[0] != A.shape[1] and complex(shift) != 0:
+            raise ValueError("a shift needs a square matrix")
+        self.n = A.shape[1]            # input length
+        self.nrows = A.shape[0]
         self.tdtype = torch.complex128
 
         def up(a, dt):
@@ -285,8 +287,12 @@ class CsrOperator:
         self._h = C.c_void_p()
         sh = complex(shift)
         with torch.cuda.device(self.device):
-            _lib.check(self._L.fdfd_csr_create(C.byref(self._h), _lib.C128, self.n, *[t.data_ptr() for t in self._keep],
-                                               sh.real, sh.imag))
+            if self.shape[0] == self.shape[1]:
+                _lib.check(self._L.fdfd_csr_create(C.byref(self._h), _lib.C128, self.n, *[t.data_ptr() for t in self._keep],
+                                                   sh.real, sh.imag))
+            else:
+                _lib.check(self._L.fdfd_csr_create_rect(C.byref(self._h), _lib.C128, self.nrows, self.n,
+                                                        *[t.data_ptr() for t in self._keep]))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -305,16 +311,16 @@ class CsrOperator:
         if x.numel() != self.n:
             raise ValueError("x has the wrong number of elements")
         if out is None:
-            out = torch.empty_like(x)
+            out = torch.empty(self.nrows, dtype=self.tdtype, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self._L.fdfd_linop_apply(self._h, x.data_ptr(), out.data_ptr(),
                                                 torch.cuda.current_stream(self.device).cuda_stream))
         return out
 
     def apply_rows(self, V):
-        """A applied to every row of V (m, n) -> (m, n): the SpMM of the refined extraction."""
+        """A applied to every row of V (m, n) -> (m, nrows): the SpMM of the refined extraction."""
         torch = _torch()
-        out = torch.empty_like(V)
+        out = torch.empty((V.shape[0], self.nrows), dtype=self.tdtype, device=self.device)
         for i in range(V.shape[0]):
             self.apply(V[i], out=out[i])
         return out

@@ -155,8 +155,10 @@ typedef struct {
     int mg_min_n;     /* stop coarsening when min(Nx, Ny) of the next level would drop below this */
     int reorth;       /* FGMRES: 1 = second Gram-Schmidt pass                                   */
     int mg_coarse_mode; /* coarsest level: 0 = mg_coarse_its smoothing sweeps, 1 = mg_coarse_its
-                         * iterations of BiCGSTAB preconditioned by one smoothing sweep, 2 = the same
-                         * iterations inside one persistent cooperative kernel (experimental, opt-in) */
+                         * iterations of BiCGSTAB preconditioned by one smoothing sweep (a chain of ~30
+                         * launches per iteration), 2 (default) = the same iterations inside ONE persistent
+                         * kernel (csrc/mg_coarse.cuh) whenever the level is unsharded and its relaxation
+                         * lines fit in shared memory, else as 1 */
     int mg_coarse_replicate; /* sharded grids: 1 = every rank solves the whole coarsest level, 0 = distributed,
                               * -1 = automatic (replicate while the coarse grid has <= 2^20 points)        */
     int mg_single;    /* 1 = run the multigrid cycle in complex64 inside a complex128 solve (mixed precision) */
@@ -248,6 +250,11 @@ int fdfd_csr_product_create(fdfd_linop_t** out, int dtype, int n, int m,
  * Periodic_Solver_3D.py:478-533 and the SpMV / SpMM of refined_shift_invert_arnoldi.py:74-75,96-97) */
 int fdfd_csr_create(fdfd_linop_t** out, int dtype, int n, const int32_t* indptr, const int32_t* indices,
                     const void* data, double shift_re, double shift_im);
+/* y = A x for a rectangular device CSR matrix (nrows x ncols; x has ncols, y nrows elements): the field
+ * reconstruction of the mode solver, H = Q E / sqrt(lambda), Ez / Hz from the curls
+ * (Mode_Solver_2D.py:792-805), runs on the device with these */
+int fdfd_csr_create_rect(fdfd_linop_t** out, int dtype, int nrows, int ncols, const int32_t* indptr,
+                         const int32_t* indices, const void* data);
 void fdfd_linop_destroy(fdfd_linop_t*);
 int fdfd_linop_apply(fdfd_linop_t*, const void* x, void* y, void* stream);
 int fdfd_linop_solve(fdfd_linop_t*, const fdfd_krylov_opts* opts, const void* dinv, const void* b,
