@@ -153,6 +153,8 @@ int bicgstab_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x
     int it = 0;
     double best = rr;
     int since_best = 0;
+    double last_true = -1.0;      // true residual of the previous failed confirmation
+    int floor_hits = 0;           // confirmations that failed without halving it: the attainable accuracy is reached
     while (rr > target2 && it < o.maxit) {
         ++it;
         // beta, p = r + beta (p - omega v)
@@ -211,6 +213,12 @@ int bicgstab_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x
             FDFD_TRY(allreduce_slots(comm, sc, S_TMP0, 1, stream));
             FDFD_TRY(read_slots(sc, S_TMP0, 1, h, stream));
             if (h[0].x > target2 && it < o.maxit) {
+                // the recurrence says converged, the true residual does not: rebuild the recurrences.  When that
+                // keeps happening without progress the rounding floor of b - A x has been reached: stop instead
+                // of burning maxit iterations (the caller sees the true residual and FDFD_ERR_NOCONV).
+                if (last_true > 0 && h[0].x > 0.25 * last_true) ++floor_hits; else floor_hits = 0;
+                last_true = h[0].x;
+                if (floor_hits >= 3) { rr = h[0].x; break; }
                 FDFD_TRY(restart());
                 FDFD_TRY(read_slots(sc, S_RR, 1, h, stream));
                 rr = h[0].x; best = rr;

@@ -18,6 +18,7 @@ from __future__ import annotations
 import numpy as np
 import scipy.sparse as sp
 
+from . import _lib
 from . import eigs as _eigs
 from .operators import CsrOperator, CsrProductOperator
 
@@ -481,9 +482,14 @@ class ModeSolver2D:
         stats = dict(inner_solves=0, inner_iterations=0)
 
         def shifted(r):
-            x, info = Oms.solve(r, method="bicgstab", rtol=inner_rtol, maxit=50000)
+            # the inner tolerance sits close to the rounding floor of b - (Omega - sigma) x: a solve that stalls
+            # within two digits of it is as accurate as this operator allows and is accepted (recorded below)
+            x, info = Oms.solve(r, method="bicgstab", rtol=inner_rtol, maxit=50000, raise_on_noconv=False)
+            if not info["converged"] and not info["relres"] <= 100 * inner_rtol:
+                raise _lib.NoConvergence(f"inner BiCGSTAB stalled at relres {info['relres']:.3e}", info)
             stats["inner_solves"] += 1
             stats["inner_iterations"] += info["iterations"]
+            stats["inner_max_relres"] = max(stats.get("inner_max_relres", 0.0), info["relres"])
             return x
         lam, X, res, restarts = _eigs.eigs_shift_invert(Om.apply, lambda v: v, shifted, n_free, self.num_modes,
                                                          complex(sigma), tol=tol, device=Om.device,
