@@ -41,6 +41,39 @@ def main():
         dist.all_gather(gathered, t)
         assert all(torch.equal(g, gathered[0]) for g in gathered)
         assert gathered[0].any()
+    # 3) replica distribution of the sweep drivers (fdfd_b200/sweeps.py): slices tile the sweep in rank order and
+    #    the gathered rows equal the single-process list; the drivers themselves are exercised with stand-in
+    #    solvers (the real ones need a GPU: tests/mgpu_worker.py)
+    from fdfd_b200 import sweeps
+    import numpy as np
+    for n in (1, 2, 5, 20):
+        lo, hi = sweeps.replica_slice(n)
+        got = sweeps.gather_replicas(list(range(lo, hi)))
+        assert got == list(range(n)), (n, got)
+
+    class FakeMode:
+        def __init__(self, f):
+            self.f = f
+        def solve(self):
+            self.propagation_constant = np.array([self.f * 1e-9, 2.0])
+            self.attenuation_constant = np.array([0.0, 0.5])
+    freqs = np.arange(10e9, 17e9, 1e9)
+    rows = sweeps.modal_2d_dispersion(freqs, FakeMode, 3)
+    assert [r["frequency_GHz"] for r in rows] == [f / 1e9 for f in freqs]
+    assert all(abs(r["Mode 1 beta"] - r["frequency_GHz"]) < 1e-9 and np.isnan(r["Mode 3 beta"]) for r in rows)
+
+    class Fake3D:
+        def __init__(self, f, sigma):
+            self.f, self.sigma = f, sigma
+            self.refined_residuals, self.refined_restarts = None, 0
+        def solve(self):
+            if self.f == 23e9:
+                raise RuntimeError("boom")
+            self.gammas = np.array([1j * self.f * 1e-10]); self.eigenvalues = self.gammas * 3
+    recs = sweeps.periodic_3d_dispersion(np.arange(21e9, 26e9, 1e9), Fake3D, guess_func=lambda f: -1j)
+    assert [r["frequency"] for r in recs] == [21e9, 22e9, 23e9, 24e9, 25e9] and "error" in recs[2]
+    # a chain starts from guess_func and continues with last_gamma * k0
+    assert recs[0]["sigma_guess"] == -1j
     dist.destroy_process_group()
     if rank == 0:
         print("GLOO_OK nccl_id=%d" % okt.item(), flush=True)

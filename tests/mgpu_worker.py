@@ -118,6 +118,19 @@ def main():
     err = np.linalg.norm(fields[1] - fields[0]) / np.linalg.norm(fields[0])
     if fields[1].shape != (N, N) or err > 1e-6:
         failures.append(f"sharded FDFD2DScatteringSolver: rel diff {err}")
+    # replica distribution of a Bloch sweep (fdfd_b200.sweeps): every rank solves a slice of the path on its own
+    # GPU; the gathered band structure equals the single-process one (independent eigen-problems)
+    bs = fdfd_b200.BandDiagramSolver2D(a=1.0, Nx=16, background_er=9.0)
+    bs.device = dev
+    bs.add_circular_inclusion(radius=0.3, er=1.0)
+    bp = np.array([[0.2, 1.0, 2.0, 3.0, 0.7], [0.1, 0.0, 1.5, 3.1, 2.2]])
+    with torch.cuda.device(dev):
+        single = bs.compute_band_structure(bp, num_bands=3)
+        spread = fdfd_b200.sweeps.band_structure_sweep(bs, bp, num_bands=3)
+    for pol in ("TE", "TM"):
+        d = np.max(np.abs(single.eigenvalues[pol] - spread.eigenvalues[pol]))
+        if spread.eigenvalues[pol].shape != (3, 5) or d > 1e-9 * np.max(np.abs(single.eigenvalues[pol])):
+            failures.append(f"distributed Bloch sweep {pol}: max diff {d}")
     flag = torch.tensor([len(failures)], device=dev)
     dist.all_reduce(flag)
     if failures:
