@@ -656,6 +656,10 @@ struct MGPrecond : Precond {
         cudaFree(zero_buf);
         cudaFree(coarse_partials); cudaFree(coarse_bar); cudaFree(coarse_extra[0]); cudaFree(coarse_extra[1]);
         cudaFree(coarse_k5); cudaFree(coarse_relax);
+        if (coarse_sh.seq) {
+            cudaFree(coarse_sh.seq); cudaFree(coarse_tx_table);
+            for (int q = 0; q < 6; ++q) p2p_free(coarse_comm, coarse_offs[q]);
+        }
         if (gstream) cudaStreamDestroy(gstream);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_out) cudaEventDestroy(ev_out);
@@ -809,6 +813,7 @@ struct MGPrecond : Precond {
     C* coarse_extra[2] = {nullptr, nullptr};
     C *coarse_k5 = nullptr, *coarse_relax = nullptr;
     int coarse_grid = 0;
+    size_t coarse_smem_launch = 0;
     bool coarse_ready = false;
     static size_t coarse_smem_bytes(const Level<C>& lv) {
         const int len = std::max(lv.ylines.nl ? line_pad_len(lv.ylines.len, lv.ylines.m) : 0,
@@ -817,18 +822,69 @@ struct MGPrecond : Precond {
                 line_smem_elems<C>(lv.xlines.nl, lv.xlines.len, lv.xlines.m, lv.xlines.Ptot) + (size_t)len) * sizeof(C);
     }
     // shape limits of the persistent kernel; anything else keeps the launch chain of mode 1
+    // (every condition is the same on all ranks of a sharded level: equal slabs, global strip widths)
     bool coarse_persistent_shape_ok(const Level<C>& lv) const {
         if (o.mg_coarse_mode != 2) return false;
-        if (lv.op.Ny != lv.op.Ny_global) return false;                    // unsharded level only
+        const bool sharded = lv.op.Ny != lv.op.Ny_global;
+        if (sharded && !(lv.op.comm && p2p_enabled(lv.op.comm))) return false;   // needs the peer-mapped heap
         if ((int64_t)lv.op.Nx * lv.op.Ny >= ((int64_t)1 << 31)) return false;
-        if (lv.ylines.nl && lv.ylines.nranks != 1) return false;
+        if (lv.ylines.nl && lv.ylines.nranks != (sharded ? lv.op.comm->nranks : 1)) return false;
         if (lv.xlines.nl && lv.xlines.nranks != 1) return false;
+        if (lv.ylines.Ptot > kMaxChunks || lv.xlines.Ptot > kMaxChunks) return false;
         if (std::max(lv.ylines.P, lv.xlines.P) > kCoarseThreads) return false;
-        return coarse_smem_bytes(lv) <= (size_t)200 * 1024;
+        // shared memory is sized for the widest line sets any rank of the level has (x-lines exist on the first
+        // and last rank only, with the global strip widths)
+        const size_t worst = (line_smem_elems<C>(1, lv.ylines.len, std::max(lv.ylines.m, 1), std::max(lv.ylines.Ptot, 1)) +
+                              line_smem_elems<C>(1, lv.op.Nx, std::max((lv.op.Nx + kMaxChunks - 1) / kMaxChunks, 1), kMaxChunks) +
+                              (size_t)line_pad_len(std::max(lv.op.Nx, lv.ylines.len), 1)) * sizeof(C);
+        return (sharded ? worst : coarse_smem_bytes(lv)) <= (size_t)216 * 1024;
     }
     bool coarse_persistent_ok(const Level<C>& lv) const { return coarse_ready && coarse_persistent_shape_ok(lv); }
+    // sharded level: message buffers in the symmetric heap
+    CoarseShard<C> coarse_sh;
+    size_t coarse_offs[6] = {0, 0, 0, 0, 0, 0};
+    Comm* coarse_comm = nullptr;
+    void** coarse_tx_table = nullptr;
+    int coarse_setup_sharded(const Level<C>& lv, cudaStream_t st) {
+        Comm* comm = lv.op.comm;
+        const int P = comm->nranks, me = comm->rank, G = coarse_grid;
+        const size_t nl = std::max(lv.ylines.nl, 1), nloc = 2 * (size_t)std::max(lv.ylines.P, 1);
+        const size_t bytes[6] = {
+            (size_t)2 * 2 * lv.op.Nx * sizeof(C),                    // ghost rows
+            (size_t)2 * 2 * G * sizeof(unsigned int),                // their flags
+            (size_t)2 * P * kCoarseVals * sizeof(double),            // reduction slots
+            (size_t)2 * P * sizeof(unsigned int),
+            (size_t)2 * P * nl * nloc * sizeof(C),                   // interface values of the y-lines
+            (size_t)2 * P * nl * sizeof(unsigned int)};
+        coarse_comm = comm;
+        for (int q = 0; q < 6; ++q) FDFD_TRY(p2p_alloc(comm, bytes[q], &coarse_offs[q]));
+        void* ptrs[6 * kP2PMaxRanks];
+        FDFD_TRY(p2p_exchange(comm, coarse_offs, 6, ptrs, st));
+        CoarseShard<C>& sh = coarse_sh;
+        sh.nranks = P; sh.rank = me;
+        sh.open_s = !lv.first; sh.open_n = !lv.last;
+        sh.ghost_rx = (C*)ptrs[6 * me + 0]; sh.gflag_rx = (unsigned int*)ptrs[6 * me + 1];
+        sh.red_rx = (double*)ptrs[6 * me + 2]; sh.rflag_rx = (unsigned int*)ptrs[6 * me + 3];
+        sh.ifg_rx = (C*)ptrs[6 * me + 4]; sh.iflag_rx = (unsigned int*)ptrs[6 * me + 5];
+        if (me > 0) { sh.ghost_tx_s = (C*)ptrs[6 * (me - 1) + 0]; sh.gflag_tx_s = (unsigned int*)ptrs[6 * (me - 1) + 1]; }
+        if (me < P - 1) { sh.ghost_tx_n = (C*)ptrs[6 * (me + 1) + 0]; sh.gflag_tx_n = (unsigned int*)ptrs[6 * (me + 1) + 1]; }
+        void* table[4][kP2PMaxRanks] = {};
+        for (int r = 0; r < P; ++r)
+            for (int q = 0; q < 4; ++q) table[q][r] = ptrs[6 * r + 2 + q];
+        FDFD_CUDA(cudaMalloc(&coarse_tx_table, sizeof(table)));
+        FDFD_CUDA(cudaMemcpy(coarse_tx_table, table, sizeof(table), cudaMemcpyHostToDevice));
+        sh.red_tx = (double* const*)(coarse_tx_table + 0 * kP2PMaxRanks);
+        sh.rflag_tx = (unsigned int* const*)(coarse_tx_table + 1 * kP2PMaxRanks);
+        sh.ifg_tx = (C* const*)(coarse_tx_table + 2 * kP2PMaxRanks);
+        sh.iflag_tx = (unsigned int* const*)(coarse_tx_table + 3 * kP2PMaxRanks);
+        FDFD_CUDA(cudaMalloc(&sh.seq, 4 * sizeof(unsigned int)));
+        FDFD_CUDA(cudaMemset(sh.seq, 0, 4 * sizeof(unsigned int)));
+        return FDFD_OK;
+    }
+
     int coarse_setup(const Level<C>& lv) {
-        const size_t smem = coarse_smem_bytes(lv);
+        const bool sharded = lv.op.Ny != lv.op.Ny_global;
+        const size_t smem = sharded ? (size_t)216 * 1024 : coarse_smem_bytes(lv);
         auto kern = TM() ? coarse_bicgstab_kernel<C, true> : coarse_bicgstab_kernel<C, false>;
         FDFD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, dev = 0, sms = 0, coop = 0;
@@ -837,9 +893,11 @@ struct MGPrecond : Precond {
         FDFD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         FDFD_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
         const int owners = std::max(lv.ylines.nl, lv.xlines.nl);
-        if (per_sm < 1 || !coop || owners > sms) return FDFD_OK;        // stays on the launch chain
+        // (sharded: the decision must be the same on every rank — all B200s of a box, same kernel, same smem)
+        if (per_sm < 1 || !coop || (sharded ? std::max(lv.ylines.nl, kMaxChunks) : owners) > sms) return FDFD_OK;   // launch chain
         const int64_t want = ((int64_t)lv.op.Nx * lv.op.Ny + kCoarseThreads - 1) / kCoarseThreads;
-        coarse_grid = (int)std::max<int64_t>(owners, std::min<int64_t>(sms, want));   // one CTA per SM at most
+        coarse_grid = sharded ? sms : (int)std::max<int64_t>(owners, std::min<int64_t>(sms, want));   // one CTA per SM at most
+        coarse_smem_launch = smem;
         const size_t bytes = (size_t)lv.op.n_local() * sizeof(C);
         FDFD_CUDA(cudaMalloc(&coarse_partials, (size_t)coarse_grid * kCoarseVals * sizeof(double)));
         FDFD_CUDA(cudaMalloc(&coarse_bar, 4 * sizeof(unsigned int)));
@@ -852,10 +910,11 @@ struct MGPrecond : Precond {
             using R = typename real_of<C>::type;
             const int64_t n = lv.op.n_local();
             const int blocks = (int)((n + 255) / 256);
-            if (TM()) coarse_coefs_kernel<C, true><<<blocks, 256>>>(lv.op.Nx, lv.op.Ny, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), (R)o.mg_omega, coarse_k5, coarse_relax);
-            else coarse_coefs_kernel<C, false><<<blocks, 256>>>(lv.op.Nx, lv.op.Ny, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), (R)o.mg_omega, coarse_k5, coarse_relax);
+            if (TM()) coarse_coefs_kernel<C, true><<<blocks, 256>>>(lv.op.Nx, lv.op.Ny, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), (R)o.mg_omega, coarse_k5, coarse_relax, lv.edge());
+            else coarse_coefs_kernel<C, false><<<blocks, 256>>>(lv.op.Nx, lv.op.Ny, lv.ca, lv.cb, lv.cd, (R)lv.op.sx, (R)lv.op.sy, shift(), (R)o.mg_omega, coarse_k5, coarse_relax, lv.edge());
             FDFD_CUDA(cudaGetLastError());
         }
+        if (sharded) FDFD_TRY(coarse_setup_sharded(lv, 0));
         coarse_ready = true;
         return FDFD_OK;
     }
@@ -877,10 +936,11 @@ struct MGPrecond : Precond {
         a.partials = coarse_partials;
         a.bar = coarse_bar;
         a.owners = std::max(lv.ylines.nl, lv.xlines.nl);
+        if (lv.op.Ny != lv.op.Ny_global) a.shard = coarse_sh;
         void* args[] = {&a};
         const void* kern = TM() ? (const void*)coarse_bicgstab_kernel<C, true> : (const void*)coarse_bicgstab_kernel<C, false>;
         // cooperative launch: the runtime guarantees that all CTAs are co-resident (the barriers need it)
-        FDFD_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coarse_grid), dim3(kCoarseThreads), args, coarse_smem_bytes(lv), st));
+        FDFD_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coarse_grid), dim3(kCoarseThreads), args, coarse_smem_launch, st));
         return FDFD_OK;
     }
 

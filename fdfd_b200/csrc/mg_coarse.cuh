@@ -37,6 +37,33 @@ constexpr int kCoarseThreads = 512;
 constexpr int kCoarseWarps = kCoarseThreads / 32;
 constexpr int kCoarseVals = 8;          // doubles per CTA in the partials array
 
+// y-slab sharded level: every rank runs this kernel on its slab; ghost rows of the swept vector, the inner
+// products and the interface values of the y-lines (which run through all ranks) travel through peer-mapped
+// buffers (p2p.cuh) with one flag per message.  Messages of one kind are numbered by a sequence that every CTA
+// of every rank advances in lock-step (same control flow everywhere); buffers and flags are double buffered by
+// its parity — between two messages of equal parity lies at least one all-rank reduction, so a rank cannot
+// overwrite data a peer has not consumed.
+template <typename C>
+struct CoarseShard {
+    int nranks = 1, rank = 0;
+    int open_s = 0, open_n = 0;            // a neighbour slab exists below / above
+    C* ghost_rx = nullptr;                 // [2 parity][2 sides: 0 = row below my slab, 1 = row above][Nx]
+    C* ghost_tx_s = nullptr;               // the south neighbour's ghost_rx (I fill its side 1)
+    C* ghost_tx_n = nullptr;               // the north neighbour's ghost_rx (I fill its side 0)
+    unsigned int *gflag_rx = nullptr, *gflag_tx_s = nullptr, *gflag_tx_n = nullptr;   // [2][2][gridDim.x]
+    double* red_rx = nullptr;              // [2][nranks][kCoarseVals]
+    unsigned int* rflag_rx = nullptr;      // [2][nranks]
+    C* ifg_rx = nullptr;                   // [2][nranks][nl][2 P]
+    unsigned int* iflag_rx = nullptr;      // [2][nranks][nl]
+    // the same buffers of every rank as mapped into this process: tables in device memory (indexed by rank at
+    // run time; arrays inside the kernel parameter block would be copied to local memory for that)
+    double* const* red_tx = nullptr;
+    unsigned int* const* rflag_tx = nullptr;
+    C* const* ifg_tx = nullptr;
+    unsigned int* const* iflag_tx = nullptr;
+    unsigned int* seq = nullptr;           // local, persistent: sequence numbers {ghost, reduction, line}
+};
+
 template <typename C>
 struct CoarseArgs {
     int Nx, Ny;
@@ -54,7 +81,17 @@ struct CoarseArgs {
     double* partials;                    // [gridDim.x][kCoarseVals]
     unsigned int* bar;                   // {count, generation} of the grid barrier, {count, generation} of the owners'
     int owners;                          // CTAs that own at least one line
+    CoarseShard<C> shard;                // shard.nranks == 1: unsharded level
 };
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ double2 cs_div(double2 a, double2 b) {     // as blas1.cu safe_div
     const double d = b.x * b.x + b.y * b.y;
@@ -142,6 +179,35 @@ __device__ __forceinline__ void coarse_grid_total(const double* partials, double
     __syncthreads();
 }
 
+// sharded level: the totals of all ranks, summed in rank order on every rank (identical bits everywhere).
+// CTA 0 sends this rank's totals to every peer; every CTA waits for the peers' messages itself (no extra
+// grid barrier).
+template <int K, typename C>
+__device__ __forceinline__ void coarse_rank_total(const CoarseShard<C>& sh, double (&tot)[K], double* sm, unsigned int seq_r) {
+    if (sh.nranks <= 1) return;
+    const unsigned int par = seq_r & 1u;
+    const int me = sh.rank, P = sh.nranks, t = threadIdx.x;
+    if (t < P && t != me) {
+        if (blockIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) sh.red_tx[t][((size_t)par * P + me) * kCoarseVals + k] = tot[k];
+            __threadfence_system();
+            st_release_sys(sh.rflag_tx[t] + (size_t)par * P + me, seq_r);
+        }
+        while (ld_acquire_sys(sh.rflag_rx + (size_t)par * P + t) != seq_r) { }
+    }
+    __syncthreads();
+    if (t < K) {
+        double s = 0.0;
+        for (int r = 0; r < P; ++r) s += (r == me) ? tot[t] : __ldcg(&sh.red_rx[((size_t)par * P + r) * kCoarseVals + t]);
+        sm[t] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) tot[k] = sm[k];
+    __syncthreads();
+}
+
 // shared-memory image of one relaxation line: factors (and, for partitioned lines, spikes + the inverse
 // of the interface system), resident for the whole solve
 template <typename C>
@@ -156,7 +222,7 @@ template <typename C>
 __host__ __device__ inline size_t line_smem_elems(int nl, int len, int m, int Ptot) {
     if (nl == 0) return 0;
     const size_t pl = (size_t)line_pad_len(len, m);
-    return 3 * pl + (Ptot > 1 ? 2 * pl + (size_t)4 * Ptot * Ptot : 0);
+    return 3 * pl + (Ptot > 1 ? (size_t)4 * Ptot * Ptot : 0);       // the spikes are read from L2 (two loads per point)
 }
 
 template <typename C>
@@ -166,7 +232,7 @@ __device__ LineSmem<C> line_smem_carve(C*& cursor, const LineView<C>& v) {
     const int pl = line_pad_len(v.len, v.m);
     s.fl = cursor; s.fc = s.fl + pl; s.ip = s.fc + pl; cursor = s.ip + pl;
     if (v.Ptot > 1) {
-        s.sv = cursor; s.sw = s.sv + pl; s.rinv = s.sw + pl;
+        s.rinv = cursor;
         cursor = s.rinv + 4 * v.Ptot * v.Ptot;
     }
     return s;
@@ -178,7 +244,6 @@ __device__ void line_smem_load(const LineSmem<C>& s, const LineView<C>& v, int l
     for (int t = threadIdx.x; t < v.len; t += kCoarseThreads) {
         const int pt = t + t / v.m;
         s.fl[pt] = v.fl[t * nl + l]; s.fc[pt] = v.fc[t * nl + l]; s.ip[pt] = v.fip[t * nl + l];
-        if (v.Ptot > 1) { s.sv[pt] = v.sv[t * nl + l]; s.sw[pt] = v.sw[t * nl + l]; }
     }
     if (v.Ptot > 1) {
         const int nn = 4 * v.Ptot * v.Ptot;
@@ -206,7 +271,8 @@ __device__ unsigned long long g_line_tr[16];
 // tridiagonal solve of the line whose right-hand side sits in sl (padded positions): chunk-local recurrences,
 // interface mat-vec, spike correction; the solution replaces sl.  Same algorithm as line_fused_kernel.
 template <typename C>
-__device__ void coarse_line_solve(const LineView<C>& v, const LineSmem<C>& s, C* sl, C* sg, C* su, int lm = 0) {
+__device__ void coarse_line_solve(const LineView<C>& v, const LineSmem<C>& s, C* sl, C* sg, C* su, int l,
+                                  const CoarseShard<C>& sh, unsigned int seq_l, int lm = 0) {
     using R = typename real_of<C>::type;
     const int len = v.len;
     COARSE_LMARK(lm);
@@ -244,10 +310,33 @@ __device__ void coarse_line_solve(const LineView<C>& v, const LineSmem<C>& s, C*
                     if (q0 - u >= 0) { e = cmul(csub(rs[u], cmul(cf[u], e)), ci[u]); sl[p0 + q0 - u] = e; }
                 }
             }
-            sg[2 * k] = e; sg[2 * k + 1] = e_last;
+            sg[2 * (v.k0 + k)] = e; sg[2 * (v.k0 + k) + 1] = e_last;
         }
     }
     __syncthreads();
+    if (v.nranks > 1) {
+        // the line runs through every rank: exchange the interface values of the local chunks (peer memory),
+        // every rank then holds all 2 Ptot of them and applies the replicated interface inverse
+        const unsigned int par = seq_l & 1u;
+        const int nloc = 2 * v.P, me = sh.rank, P = sh.nranks;
+        for (int e = threadIdx.x; e < nloc * P; e += kCoarseThreads) {
+            const int r = e / nloc, q = e - r * nloc;
+            if (r != me) sh.ifg_tx[r][(((size_t)par * P + me) * v.nl + l) * nloc + q] = sg[2 * v.k0 + q];
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < P && (int)threadIdx.x != me) {
+            const int r = threadIdx.x;
+            __threadfence_system();
+            st_release_sys(sh.iflag_tx[r] + ((size_t)par * P + me) * v.nl + l, seq_l);
+            while (ld_acquire_sys(sh.iflag_rx + ((size_t)par * P + r) * v.nl + l) != seq_l) { }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < nloc * P; e += kCoarseThreads) {
+            const int r = e / nloc, q = e - r * nloc;
+            if (r != me) sg[2 * r * v.P + q] = __ldcg(&sh.ifg_rx[(((size_t)par * P + r) * v.nl + l) * nloc + q]);
+        }
+        __syncthreads();
+    }
     COARSE_LMARK(lm + 1);
     if (v.Ptot > 1) {
         // interface mat-vec u = R^-1 g with every thread busy: `segs` adjacent lanes share a row
@@ -271,10 +360,10 @@ __device__ void coarse_line_solve(const LineView<C>& v, const LineSmem<C>& s, C*
         if (row < n && seg == 0) su[row] = mk<C>(ax, ay);
         __syncthreads();
         for (int t = threadIdx.x; t < len; t += kCoarseThreads) {
-            const int kg = t / v.m, pt = t + kg;
+            const int kl = t / v.m, pt = t + kl, kg = v.k0 + kl;
             C e = sl[pt];
-            if (kg > 0) e = csub(e, cmul(s.sv[pt], su[2 * (kg - 1) + 1]));
-            if (kg < v.Ptot - 1) e = csub(e, cmul(s.sw[pt], su[2 * (kg + 1)]));
+            if (kg > 0) e = csub(e, cmul(v.sv[(int64_t)t * v.nl + l], su[2 * (kg - 1) + 1]));
+            if (kg < v.Ptot - 1) e = csub(e, cmul(v.sw[(int64_t)t * v.nl + l], su[2 * (kg + 1)]));
             sl[pt] = e;
         }
         __syncthreads();
@@ -295,11 +384,11 @@ __device__ __forceinline__ C coarse_stencil5(const PointCoefs<C>& pc, C xc, C xw
 
 template <typename C>
 struct CoarseCtx {
-    CoarseArgs<C> a;
     LineSmem<C> ys, xs;
     C *sl, *sg, *su;
     double* red;
     unsigned int gen_all, gen_own;
+    unsigned int seq_g, seq_r, seq_l;     // message sequences of the sharded exchanges (ghost rows, sums, lines)
 };
 
 // pointwise part of the zero-guess smoothing sweep for the value `val` at point (i, j): returns the swept
@@ -328,12 +417,12 @@ __device__ __forceinline__ PointCoefs<C> coarse_coefs(const CoarseArgs<C>& a, in
 template <typename C, bool TM>
 __global__ void coarse_coefs_kernel(int Nx, int Ny, const C* ca, const C* cb, const C* cd,
         typename real_of<C>::type sx, typename real_of<C>::type sy, C shift, typename real_of<C>::type omega,
-        C* k5, C* relax) {
+        C* k5, C* relax, SlabEdge<C> edge) {
     const int64_t n = (int64_t)Nx * Ny;
     const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= n) return;
     const int j = (int)(q / Nx), i = (int)(q - (int64_t)j * Nx);
-    const PointCoefs<C> p = point_coefs<C, TM>(ca, cb, cd, Nx, Ny, sx, sy, shift, i, j);
+    const PointCoefs<C> p = point_coefs<C, TM>(ca, cb, cd, Nx, Ny, sx, sy, shift, i, j, edge);
     k5[q] = p.kw; k5[n + q] = p.ke; k5[2 * n + q] = p.ks; k5[3 * n + q] = p.kn; k5[4 * n + q] = p.dg;
     relax[q] = cscale(omega, cdiv(mk<C>(1, 0), p.dg));
 }
@@ -349,9 +438,9 @@ template <typename C> struct CoarseBatch {
 // and 0 inside; yl.g holds the strip-column right-hand sides.  On return (after the caller's grid barrier)
 // z is final except for the rows of the x-lines, whose correction e sits in xl.g (applied by coarse_zfin).
 template <typename C, bool TM>
-__device__ void coarse_line_phases(CoarseCtx<C>& c, C* z, const C* rhs) {
-    const CoarseArgs<C>& a = c.a;
+__device__ void coarse_line_phases(const CoarseArgs<C>& a, CoarseCtx<C>& c, C* z, const C* rhs) {
     const int l = blockIdx.x;
+    if (a.yl.nl > 0 && a.yl.nranks > 1) ++c.seq_l;        // (every CTA keeps the count, owners or not)
     if (l >= a.owners) return;
     COARSE_LMARK(0);
     if (a.yl.nl > 0) {
@@ -359,7 +448,7 @@ __device__ void coarse_line_phases(CoarseCtx<C>& c, C* z, const C* rhs) {
             const LineView<C>& v = a.yl;
             for (int t = threadIdx.x; t < v.len; t += kCoarseThreads) c.sl[t + t / v.m] = ldv(&v.g[(int64_t)t * v.nl + l]);
             __syncthreads();
-            coarse_line_solve<C>(v, c.ys, c.sl, c.sg, c.su, 1);
+            coarse_line_solve<C>(v, c.ys, c.sl, c.sg, c.su, l, a.shard, c.seq_l, 1);
             const int col = l < v.lo ? l : v.Nx - v.hi + (l - v.lo);
             for (int t = threadIdx.x; t < v.len; t += kCoarseThreads)
                 z[(int64_t)t * v.Nx + col] = cscale(a.omega, c.sl[t + t / v.m]);      // the column was zero
@@ -382,7 +471,7 @@ __device__ void coarse_line_phases(CoarseCtx<C>& c, C* z, const C* rhs) {
             c.sl[i + i / v.m] = csub(ldv(&rhs[pn]), coarse_stencil5<C>(pc, zc, zw, ze, zs, zn));
         }
         __syncthreads();
-        coarse_line_solve<C>(v, c.xs, c.sl, c.sg, c.su, 6);
+        coarse_line_solve<C>(v, c.xs, c.sl, c.sg, c.su, l, a.shard, 0u, 6);
         for (int i = threadIdx.x; i < v.len; i += kCoarseThreads) v.g[(int64_t)i * v.nl + l] = c.sl[i + i / v.m];
         COARSE_LMARK(9);
     }
@@ -402,10 +491,38 @@ __device__ __forceinline__ C coarse_zfin(const CoarseArgs<C>& a, const C* z, int
 
 // out = M zfin at the thread's points, zfin stored to zf; MODE 0: acc = (rh, out);
 // MODE 1: acc = (out, s), (out, out), (rh, s), (rh, out) with s = a.r
+// ghost value of the swept vector in the row below (side 0) / above (side 1) the slab
+template <typename C>
+__device__ __forceinline__ C coarse_ghost(const CoarseShard<C>& sh, int Nx, int side, int i, unsigned int seq_g) {
+    const unsigned int par = seq_g & 1u;
+    const int chunk = (Nx + (int)gridDim.x - 1) / (int)gridDim.x;
+    const unsigned int* f = sh.gflag_rx + ((size_t)par * 2 + side) * gridDim.x + i / chunk;
+    while (ld_acquire_sys(f) != seq_g) { }
+    return __ldcg(&sh.ghost_rx[((size_t)par * 2 + side) * Nx + i]);
+}
+
 template <typename C, bool TM, int MODE>
 __device__ __forceinline__ void coarse_apply_phase(const CoarseArgs<C>& a, const C* z, C* zf, C* out, double* acc,
-                                                   int tid, int stride, int n) {
+                                                   int tid, int stride, int n, unsigned int seq_g) {
     constexpr int U = CoarseBatch<C>::US;
+    const CoarseShard<C>& sh = a.shard;
+    if (sh.nranks > 1) {
+        // push this rank's edge rows of the swept vector into the neighbours' ghost rows: CTA c owns the
+        // columns [c chunk, (c+1) chunk) and raises flag c on the receiver
+        const unsigned int par = seq_g & 1u;
+        const int chunk = (a.Nx + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int i0 = blockIdx.x * chunk, i1 = min(a.Nx, i0 + chunk);
+        for (int i = i0 + threadIdx.x; i < i1; i += kCoarseThreads) {
+            if (sh.open_n) sh.ghost_tx_n[((size_t)par * 2 + 0) * a.Nx + i] = coarse_zfin<C>(a, z, i, a.Ny - 1, (int64_t)(a.Ny - 1) * a.Nx + i);
+            if (sh.open_s) sh.ghost_tx_s[((size_t)par * 2 + 1) * a.Nx + i] = coarse_zfin<C>(a, z, i, 0, i);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && i0 < i1) {
+            __threadfence_system();
+            if (sh.open_n) st_release_sys(sh.gflag_tx_n + ((size_t)par * 2 + 0) * gridDim.x + blockIdx.x, seq_g);
+            if (sh.open_s) st_release_sys(sh.gflag_tx_s + ((size_t)par * 2 + 1) * gridDim.x + blockIdx.x, seq_g);
+        }
+    }
     for (int base = tid; base < n; base += U * stride) {
         C o[U], zc[U], rhv[U], sv[U];
 #pragma unroll
@@ -417,8 +534,10 @@ __device__ __forceinline__ void coarse_apply_phase(const CoarseArgs<C>& a, const
                 zc[u] = coarse_zfin<C>(a, z, i, j, q);
                 const C zw = i > 0 ? coarse_zfin<C>(a, z, i - 1, j, q - 1) : czero<C>();
                 const C ze = i < a.Nx - 1 ? coarse_zfin<C>(a, z, i + 1, j, q + 1) : czero<C>();
-                const C zs = j > 0 ? coarse_zfin<C>(a, z, i, j - 1, q - a.Nx) : czero<C>();
-                const C zn = j < a.Ny - 1 ? coarse_zfin<C>(a, z, i, j + 1, q + a.Nx) : czero<C>();
+                const C zs = j > 0 ? coarse_zfin<C>(a, z, i, j - 1, q - a.Nx)
+                                   : (sh.open_s ? coarse_ghost<C>(sh, a.Nx, 0, i, seq_g) : czero<C>());
+                const C zn = j < a.Ny - 1 ? coarse_zfin<C>(a, z, i, j + 1, q + a.Nx)
+                                          : (sh.open_n ? coarse_ghost<C>(sh, a.Nx, 1, i, seq_g) : czero<C>());
                 o[u] = coarse_stencil5<C>(pc, zc[u], zw, ze, zs, zn);
                 rhv[u] = ldv(&a.rh[q]);
                 if (MODE == 1) sv[u] = ldv(&a.r[q]);
@@ -457,7 +576,6 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
     __shared__ C sg[2 * kMaxChunks], su[2 * kMaxChunks];
     __shared__ double red[kCoarseVals * kCoarseWarps];
     CoarseCtx<C> c;
-    c.a = a;
     C* cursor = reinterpret_cast<C*>(coarse_smem);
     c.ys = line_smem_carve<C>(cursor, a.yl);
     c.xs = line_smem_carve<C>(cursor, a.xl);
@@ -466,6 +584,8 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
     if (threadIdx.x == 0) { sg[0] = czero<C>(); }
     c.gen_all = ld_acquire_u32(&a.bar[1]);
     c.gen_own = ld_acquire_u32(&a.bar[3]);
+    c.seq_g = c.seq_r = c.seq_l = 0;
+    if (a.shard.nranks > 1) { c.seq_g = a.shard.seq[0]; c.seq_r = a.shard.seq[1]; c.seq_l = a.shard.seq[2]; }
     const int n = a.Nx * a.Ny;                       // < 2^31 (checked on the host)
     const int tid = blockIdx.x * kCoarseThreads + threadIdx.x;
     const int stride = gridDim.x * kCoarseThreads;
@@ -506,24 +626,26 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
     coarse_barrier(a.bar, nblk, c.gen_all);
     double tot2[2];
     coarse_grid_total<2>(a.partials, tot2, red);
+    coarse_rank_total<2, C>(a.shard, tot2, red, ++c.seq_r);
     double2 rho = make_double2(tot2[0], 0.0);
     double2 alpha = make_double2(1.0, 0.0), omega = make_double2(1.0, 0.0);
 
     for (int it = 0; it < a.its; ++it) {
         // (p^0 and the y-line right-hand sides of this iteration were written by the previous phase)
         COARSE_MARK(0);
-        coarse_line_phases<C, TM>(c, a.ph, a.p);
+        coarse_line_phases<C, TM>(a, c, a.ph, a.p);
         COARSE_MARK(1);
         coarse_barrier(a.bar, nblk, c.gen_all);
         COARSE_MARK(2);
         // V: v = M p^, (r^, v)
         double accv[2] = {0.0, 0.0};
-        coarse_apply_phase<C, TM, 0>(a, a.ph, a.phf, a.v, accv, tid, stride, n);
+        coarse_apply_phase<C, TM, 0>(a, a.ph, a.phf, a.v, accv, tid, stride, n, ++c.seq_g);
         COARSE_MARK(3);
         coarse_block_reduce<2>(accv, prow, red);
         coarse_barrier(a.bar, nblk, c.gen_all);
         COARSE_MARK(4);
         coarse_grid_total<2>(a.partials, tot2, red);
+        coarse_rank_total<2, C>(a.shard, tot2, red, ++c.seq_r);
         COARSE_MARK(5);
         alpha = cs_div(rho, make_double2(tot2[0], tot2[1]));
         // S: s = r - alpha v (in r), s^0 pointwise
@@ -553,19 +675,20 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
         COARSE_MARK(6);
         coarse_barrier(a.bar, nblk, c.gen_all);
         COARSE_MARK(7);
-        coarse_line_phases<C, TM>(c, a.sh, a.r);
+        coarse_line_phases<C, TM>(a, c, a.sh, a.r);
         COARSE_MARK(8);
         coarse_barrier(a.bar, nblk, c.gen_all);
         COARSE_MARK(9);
         // T: t = M s^, (t, s), (t, t), (r^, s), (r^, t)
         double acct[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        coarse_apply_phase<C, TM, 1>(a, a.sh, a.shf, a.t, acct, tid, stride, n);
+        coarse_apply_phase<C, TM, 1>(a, a.sh, a.shf, a.t, acct, tid, stride, n, ++c.seq_g);
         COARSE_MARK(10);
         coarse_block_reduce<8>(acct, prow, red);
         coarse_barrier(a.bar, nblk, c.gen_all);
         COARSE_MARK(11);
         double tot8[8];
         coarse_grid_total<8>(a.partials, tot8, red);
+        coarse_rank_total<8, C>(a.shard, tot8, red, ++c.seq_r);
         COARSE_MARK(12);
         omega = cs_div(make_double2(tot8[0], tot8[1]), make_double2(tot8[2], 0.0));
         // rho_new = (r^, s - omega t)
@@ -623,5 +746,9 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
                    g_line_tr[5] - g_line_tr[4], g_line_tr[6] - g_line_tr[5], g_line_tr[7] - g_line_tr[6], g_line_tr[8] - g_line_tr[7],
                    g_line_tr[9] - g_line_tr[8]);
 #endif
+    }
+    // (every CTA read the sequence numbers before the first barrier of this launch)
+    if (a.shard.nranks > 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+        a.shard.seq[0] = c.seq_g; a.shard.seq[1] = c.seq_r; a.shard.seq[2] = c.seq_l;
     }
 }

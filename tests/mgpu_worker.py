@@ -80,10 +80,20 @@ def main():
         zf = full.precond_apply(torch.from_numpy(v).to(dev), precond="mg", **lines).reshape(N, N)
         part = fdfd_b200.HelmholtzOperator2D(pol, N, N, ca[j0:j1], cb[j0:j1], cd[j0:j1], sx, sy, device=dev,
                                              rows=(j0, j1), comm=comm)
-        zp = part.precond_apply(torch.from_numpy(np.ascontiguousarray(v[j0:j1])).to(dev), precond="mg", **lines)
-        err = (torch.linalg.vector_norm(zp.reshape(-1) - zf[j0:j1].reshape(-1)) / torch.linalg.vector_norm(zf[j0:j1])).item()
-        if not err <= 1e-7:
-            failures.append(f"mg precond {pol}: sharded vs full rel diff {err}")
+        # coarsest level replicated on every rank (default for small coarse grids) and distributed (what large
+        # grids use: with a peer-mapped heap the coarse solve is ONE persistent kernel per rank exchanging ghost
+        # rows, inner products and line interface values over NVLink; on the NCCL path a launch chain)
+        for rep in (-1, 0):
+            zp = part.precond_apply(torch.from_numpy(np.ascontiguousarray(v[j0:j1])).to(dev), precond="mg",
+                                    mg_coarse_replicate=rep, **lines)
+            err = (torch.linalg.vector_norm(zp.reshape(-1) - zf[j0:j1].reshape(-1)) / torch.linalg.vector_norm(zf[j0:j1])).item()
+            if not err <= 1e-7:
+                failures.append(f"mg precond {pol} (coarse_replicate={rep}): sharded vs full rel diff {err}")
+        xd, inf_d = part.solve(torch.from_numpy(np.ascontiguousarray(so.rhs(so.build_A(p, pol), p).reshape(N, N)[j0:j1])).to(dev).reshape(-1),
+                               method="fgmres", precond="mg", rtol=1e-9, maxit=400, mg_coarse_replicate=0, mg_single=1,
+                               line_x_lo=pw, line_x_hi=pw, line_y_lo=pw, line_y_hi=pw)
+        if inf_d["relres"] > 1e-9:
+            failures.append(f"mg solve {pol} with the distributed coarse level: relres {inf_d['relres']}")
         # solve
         A = so.build_A(p, pol)
         b = so.rhs(A, p).reshape(N, N)
