@@ -455,13 +455,14 @@ int helm2d_apply_x32(Helm2D& op, const float2* x, double2* y, cudaStream_t strea
     a.rows_per_cta = v.ry;
     dim3 grid(ceil_div(op.Nx, bx), ceil_div(op.Ny, v.ry));
     FDFD_CHECK_ARG(grid.y <= 65535, "too many row tiles for one launch");
+    // (the widening loads cost this variant two registers more than the 72 that 7 CTAs per SM allow: 6 CTAs)
     if (p2p) {
-        if (op.pol == FDFD_POL_TM) helm2d_march_kernel<C, true, APPLY_AX, float2, true><<<grid, bx, 0, stream>>>(a);
-        else helm2d_march_kernel<C, false, APPLY_AX, float2, true><<<grid, bx, 0, stream>>>(a);
+        if (op.pol == FDFD_POL_TM) helm2d_march_kernel<C, true, APPLY_AX, float2, true, 6><<<grid, bx, 0, stream>>>(a);
+        else helm2d_march_kernel<C, false, APPLY_AX, float2, true, 6><<<grid, bx, 0, stream>>>(a);
     } else {
         a.halo = HaloP2P();
-        if (op.pol == FDFD_POL_TM) helm2d_march_kernel<C, true, APPLY_AX, float2><<<grid, bx, 0, stream>>>(a);
-        else helm2d_march_kernel<C, false, APPLY_AX, float2><<<grid, bx, 0, stream>>>(a);
+        if (op.pol == FDFD_POL_TM) helm2d_march_kernel<C, true, APPLY_AX, float2, false, 6><<<grid, bx, 0, stream>>>(a);
+        else helm2d_march_kernel<C, false, APPLY_AX, float2, false, 6><<<grid, bx, 0, stream>>>(a);
     }
     FDFD_CUDA(cudaGetLastError());
     return FDFD_OK;
