@@ -273,6 +273,8 @@ def run_ours(args):
                          {"grid": f"{N}x{N}", "pol": pol, "n_gpus": world, "skipped":
                           f"needs >= {need} GPUs: FGMRES({opts.get('restart')}) basis + corrections do not fit 180 GB"}
                          for N, pol, opts, need in solve_plan(args, world)]
+    if world == 1 and rank == 0 and not args.no_solve:
+        line["solve_dropin"] = dropin_time_to_solution()
     if world == 1 and rank == 0 and not args.no_cpu:
         r = cpu_spmv_sample(5, 1)
         line["cpu_baseline"] = {
@@ -333,6 +335,37 @@ def solve_record(N, pol, opts, comm, rank, world, dev, barrier):
             "rtol": info["rtol"], "converged": info["converged"], "options": opts,
             "data_path": "nvlink-peer-memory" if (comm is not None and comm.peer_mapped) else ("nccl" if world > 1 else "single"),
             "inputs": "synthetic, generated on the device per y-slab"}
+
+
+def dropin_time_to_solution(N=4096):
+    """The same 4096^2 TE problem through the reference-facing class (host call in, (Ny, Nx) numpy field out):
+    wall clock of everything a user waits for — geometry calls, device set-up, preconditioner, solve, download."""
+    import torch
+    import fdfd_b200
+    f0 = 10e9
+    lam = 299792458 / f0
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sim = fdfd_b200.FDFD2DScatteringSolver(f0, N / 50 * lam, N / 50 * lam, N, N)
+    sim.add_object(-1e6, 1.0, (sim.X ** 2 + sim.Y ** 2) <= (0.5 * lam) ** 2)
+    sim.add_UPML(pml_width=40, sigma_max=10)
+    sim.add_mask(80)
+    sim.add_source("plane_wave", angle_deg=45.0, polarization="TE")
+    t1 = time.perf_counter()
+    try:
+        F = sim.solve_total_field_TE()
+        info, ok = sim.solver_info["TE"], True
+    except fdfd_b200.NoConvergence as e:
+        F, info, ok = None, (e.info or {}), False
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    sim.close()
+    return {"grid": f"{N}x{N}", "pol": "TE", "api": "FDFD2DScatteringSolver.solve_total_field_TE (host in, host out)",
+            "geometry_calls_s": round(t1 - t0, 3), "time_to_solution_s": round(t2 - t0, 3),
+            "device_solve_s": round(info.get("seconds", float("nan")), 3), "iterations": info.get("iterations"),
+            "relres": info.get("relres"), "rtol": info.get("rtol"), "converged": ok,
+            "field_bytes_to_host": 0 if F is None else int(F.nbytes),
+            "reference": "scipy SuperLU is infeasible at this size (LU ~3.7e9 nnz > RAM, SURVEY.md §6); 2048^2 takes it 228 s"}
 
 
 def _quiet_stdout():

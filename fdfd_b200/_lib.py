@@ -58,6 +58,8 @@ _PROTOTYPES = {
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdfd_yee2d_csr_fill_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fdfd_scatter_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p]),
     "fdfd_stagger_csr_fill": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fdfd_stagger_csr_fill_host": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double,

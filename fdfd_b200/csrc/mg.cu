@@ -814,12 +814,13 @@ struct MGPrecond : Precond {
     C *coarse_k5 = nullptr, *coarse_relax = nullptr;
     int coarse_grid = 0;
     size_t coarse_smem_launch = 0;
+    bool coarse_spikes = false;
     bool coarse_ready = false;
-    static size_t coarse_smem_bytes(const Level<C>& lv) {
+    static size_t coarse_smem_bytes(const Level<C>& lv, bool spikes) {
         const int len = std::max(lv.ylines.nl ? line_pad_len(lv.ylines.len, lv.ylines.m) : 0,
                                  lv.xlines.nl ? line_pad_len(lv.xlines.len, lv.xlines.m) : 0);
-        return (line_smem_elems<C>(lv.ylines.nl, lv.ylines.len, lv.ylines.m, lv.ylines.Ptot) +
-                line_smem_elems<C>(lv.xlines.nl, lv.xlines.len, lv.xlines.m, lv.xlines.Ptot) + (size_t)len) * sizeof(C);
+        return (line_smem_elems<C>(lv.ylines.nl, lv.ylines.len, lv.ylines.m, lv.ylines.Ptot, spikes) +
+                line_smem_elems<C>(lv.xlines.nl, lv.xlines.len, lv.xlines.m, lv.xlines.Ptot, spikes) + (size_t)len) * sizeof(C);
     }
     // shape limits of the persistent kernel; anything else keeps the launch chain of mode 1
     // (every condition is the same on all ranks of a sharded level: equal slabs, global strip widths)
@@ -834,10 +835,10 @@ struct MGPrecond : Precond {
         if (std::max(lv.ylines.P, lv.xlines.P) > kCoarseThreads) return false;
         // shared memory is sized for the widest line sets any rank of the level has (x-lines exist on the first
         // and last rank only, with the global strip widths)
-        const size_t worst = (line_smem_elems<C>(1, lv.ylines.len, std::max(lv.ylines.m, 1), std::max(lv.ylines.Ptot, 1)) +
-                              line_smem_elems<C>(1, lv.op.Nx, std::max((lv.op.Nx + kMaxChunks - 1) / kMaxChunks, 1), kMaxChunks) +
+        const size_t worst = (line_smem_elems<C>(1, lv.ylines.len, std::max(lv.ylines.m, 1), std::max(lv.ylines.Ptot, 1), false) +
+                              line_smem_elems<C>(1, lv.op.Nx, std::max((lv.op.Nx + kMaxChunks - 1) / kMaxChunks, 1), kMaxChunks, false) +
                               (size_t)line_pad_len(std::max(lv.op.Nx, lv.ylines.len), 1)) * sizeof(C);
-        return (sharded ? worst : coarse_smem_bytes(lv)) <= (size_t)216 * 1024;
+        return (sharded ? worst : coarse_smem_bytes(lv, false)) <= (size_t)216 * 1024;
     }
     bool coarse_persistent_ok(const Level<C>& lv) const { return coarse_ready && coarse_persistent_shape_ok(lv); }
     // sharded level: message buffers in the symmetric heap
@@ -882,10 +883,17 @@ struct MGPrecond : Precond {
         return FDFD_OK;
     }
 
+    using CoarseKernel = void (*)(CoarseArgs<C>);
+    CoarseKernel coarse_kernel(bool sharded) const {
+        if (sharded) return TM() ? coarse_bicgstab_kernel<C, true, true> : coarse_bicgstab_kernel<C, false, true>;
+        return TM() ? coarse_bicgstab_kernel<C, true, false> : coarse_bicgstab_kernel<C, false, false>;
+    }
+
     int coarse_setup(const Level<C>& lv) {
         const bool sharded = lv.op.Ny != lv.op.Ny_global;
-        const size_t smem = sharded ? (size_t)216 * 1024 : coarse_smem_bytes(lv);
-        auto kern = TM() ? coarse_bicgstab_kernel<C, true> : coarse_bicgstab_kernel<C, false>;
+        coarse_spikes = !sharded && coarse_smem_bytes(lv, true) <= (size_t)216 * 1024;
+        const size_t smem = sharded ? (size_t)216 * 1024 : coarse_smem_bytes(lv, coarse_spikes);
+        auto kern = coarse_kernel(sharded);
         FDFD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0, dev = 0, sms = 0, coop = 0;
         FDFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCoarseThreads, smem));
@@ -936,9 +944,10 @@ struct MGPrecond : Precond {
         a.partials = coarse_partials;
         a.bar = coarse_bar;
         a.owners = std::max(lv.ylines.nl, lv.xlines.nl);
+        a.spikes_in_smem = coarse_spikes ? 1 : 0;
         if (lv.op.Ny != lv.op.Ny_global) a.shard = coarse_sh;
         void* args[] = {&a};
-        const void* kern = TM() ? (const void*)coarse_bicgstab_kernel<C, true> : (const void*)coarse_bicgstab_kernel<C, false>;
+        const void* kern = (const void*)coarse_kernel(lv.op.Ny != lv.op.Ny_global);
         // cooperative launch: the runtime guarantees that all CTAs are co-resident (the barriers need it)
         FDFD_CUDA(cudaLaunchCooperativeKernel(kern, dim3(coarse_grid), dim3(kCoarseThreads), args, coarse_smem_launch, st));
         return FDFD_OK;

@@ -81,6 +81,7 @@ struct CoarseArgs {
     double* partials;                    // [gridDim.x][kCoarseVals]
     unsigned int* bar;                   // {count, generation} of the grid barrier, {count, generation} of the owners'
     int owners;                          // CTAs that own at least one line
+    int spikes_in_smem;                  // the spike arrays of the lines fit in shared memory as well
     CoarseShard<C> shard;                // shard.nranks == 1: unsharded level
 };
 
@@ -218,20 +219,23 @@ struct LineSmem { C *fl, *fc, *ip, *sv, *sw, *rinv; };
 // (m = 16 elements of 8 bytes = 128 bytes: a 32-way conflict on every access, measured 4.9 us per solve).
 __host__ __device__ inline int line_pad_len(int len, int m) { return len + (m > 0 ? (len + m - 1) / m : 0) + 1; }
 
+// `spikes`: keep the two spike arrays in shared memory too (else they are read from L2, two loads per point:
+// long lines / sharded levels, where shared memory is short)
 template <typename C>
-__host__ __device__ inline size_t line_smem_elems(int nl, int len, int m, int Ptot) {
+__host__ __device__ inline size_t line_smem_elems(int nl, int len, int m, int Ptot, bool spikes) {
     if (nl == 0) return 0;
     const size_t pl = (size_t)line_pad_len(len, m);
-    return 3 * pl + (Ptot > 1 ? (size_t)4 * Ptot * Ptot : 0);       // the spikes are read from L2 (two loads per point)
+    return 3 * pl + (Ptot > 1 ? (spikes ? 2 * pl : 0) + (size_t)4 * Ptot * Ptot : 0);
 }
 
 template <typename C>
-__device__ LineSmem<C> line_smem_carve(C*& cursor, const LineView<C>& v) {
+__device__ LineSmem<C> line_smem_carve(C*& cursor, const LineView<C>& v, bool spikes) {
     LineSmem<C> s{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (v.nl == 0) return s;
     const int pl = line_pad_len(v.len, v.m);
     s.fl = cursor; s.fc = s.fl + pl; s.ip = s.fc + pl; cursor = s.ip + pl;
     if (v.Ptot > 1) {
+        if (spikes) { s.sv = cursor; s.sw = s.sv + pl; cursor = s.sw + pl; }
         s.rinv = cursor;
         cursor = s.rinv + 4 * v.Ptot * v.Ptot;
     }
@@ -244,6 +248,7 @@ __device__ void line_smem_load(const LineSmem<C>& s, const LineView<C>& v, int l
     for (int t = threadIdx.x; t < v.len; t += kCoarseThreads) {
         const int pt = t + t / v.m;
         s.fl[pt] = v.fl[t * nl + l]; s.fc[pt] = v.fc[t * nl + l]; s.ip[pt] = v.fip[t * nl + l];
+        if (s.sv) { s.sv[pt] = v.sv[t * nl + l]; s.sw[pt] = v.sw[t * nl + l]; }
     }
     if (v.Ptot > 1) {
         const int nn = 4 * v.Ptot * v.Ptot;
@@ -270,7 +275,7 @@ __device__ unsigned long long g_line_tr[16];
 
 // tridiagonal solve of the line whose right-hand side sits in sl (padded positions): chunk-local recurrences,
 // interface mat-vec, spike correction; the solution replaces sl.  Same algorithm as line_fused_kernel.
-template <typename C>
+template <typename C, bool SH>
 __device__ void coarse_line_solve(const LineView<C>& v, const LineSmem<C>& s, C* sl, C* sg, C* su, int l,
                                   const CoarseShard<C>& sh, unsigned int seq_l, int lm = 0) {
     using R = typename real_of<C>::type;
@@ -314,7 +319,7 @@ __device__ void coarse_line_solve(const LineView<C>& v, const LineSmem<C>& s, C*
         }
     }
     __syncthreads();
-    if (v.nranks > 1) {
+    if (SH && v.nranks > 1) {
         // the line runs through every rank: exchange the interface values of the local chunks (peer memory),
         // every rank then holds all 2 Ptot of them and applies the replicated interface inverse
         const unsigned int par = seq_l & 1u;
@@ -362,8 +367,8 @@ __device__ void coarse_line_solve(const LineView<C>& v, const LineSmem<C>& s, C*
         for (int t = threadIdx.x; t < len; t += kCoarseThreads) {
             const int kl = t / v.m, pt = t + kl, kg = v.k0 + kl;
             C e = sl[pt];
-            if (kg > 0) e = csub(e, cmul(v.sv[(int64_t)t * v.nl + l], su[2 * (kg - 1) + 1]));
-            if (kg < v.Ptot - 1) e = csub(e, cmul(v.sw[(int64_t)t * v.nl + l], su[2 * (kg + 1)]));
+            if (kg > 0) e = csub(e, cmul(s.sv ? s.sv[pt] : v.sv[(int64_t)t * v.nl + l], su[2 * (kg - 1) + 1]));
+            if (kg < v.Ptot - 1) e = csub(e, cmul(s.sw ? s.sw[pt] : v.sw[(int64_t)t * v.nl + l], su[2 * (kg + 1)]));
             sl[pt] = e;
         }
         __syncthreads();
@@ -437,10 +442,10 @@ template <typename C> struct CoarseBatch {
 // line phases of one smoothing sweep from a zero guess.  z holds omega D^-1 rhs outside the strip columns
 // and 0 inside; yl.g holds the strip-column right-hand sides.  On return (after the caller's grid barrier)
 // z is final except for the rows of the x-lines, whose correction e sits in xl.g (applied by coarse_zfin).
-template <typename C, bool TM>
+template <typename C, bool TM, bool SH>
 __device__ void coarse_line_phases(const CoarseArgs<C>& a, CoarseCtx<C>& c, C* z, const C* rhs) {
     const int l = blockIdx.x;
-    if (a.yl.nl > 0 && a.yl.nranks > 1) ++c.seq_l;        // (every CTA keeps the count, owners or not)
+    if (SH && a.yl.nl > 0 && a.yl.nranks > 1) ++c.seq_l;        // (every CTA keeps the count, owners or not)
     if (l >= a.owners) return;
     COARSE_LMARK(0);
     if (a.yl.nl > 0) {
@@ -448,7 +453,7 @@ __device__ void coarse_line_phases(const CoarseArgs<C>& a, CoarseCtx<C>& c, C* z
             const LineView<C>& v = a.yl;
             for (int t = threadIdx.x; t < v.len; t += kCoarseThreads) c.sl[t + t / v.m] = ldv(&v.g[(int64_t)t * v.nl + l]);
             __syncthreads();
-            coarse_line_solve<C>(v, c.ys, c.sl, c.sg, c.su, l, a.shard, c.seq_l, 1);
+            coarse_line_solve<C, SH>(v, c.ys, c.sl, c.sg, c.su, l, a.shard, c.seq_l, 1);
             const int col = l < v.lo ? l : v.Nx - v.hi + (l - v.lo);
             for (int t = threadIdx.x; t < v.len; t += kCoarseThreads)
                 z[(int64_t)t * v.Nx + col] = cscale(a.omega, c.sl[t + t / v.m]);      // the column was zero
@@ -471,7 +476,7 @@ __device__ void coarse_line_phases(const CoarseArgs<C>& a, CoarseCtx<C>& c, C* z
             c.sl[i + i / v.m] = csub(ldv(&rhs[pn]), coarse_stencil5<C>(pc, zc, zw, ze, zs, zn));
         }
         __syncthreads();
-        coarse_line_solve<C>(v, c.xs, c.sl, c.sg, c.su, l, a.shard, 0u, 6);
+        coarse_line_solve<C, false>(v, c.xs, c.sl, c.sg, c.su, l, a.shard, 0u, 6);
         for (int i = threadIdx.x; i < v.len; i += kCoarseThreads) v.g[(int64_t)i * v.nl + l] = c.sl[i + i / v.m];
         COARSE_LMARK(9);
     }
@@ -501,12 +506,12 @@ __device__ __forceinline__ C coarse_ghost(const CoarseShard<C>& sh, int Nx, int 
     return __ldcg(&sh.ghost_rx[((size_t)par * 2 + side) * Nx + i]);
 }
 
-template <typename C, bool TM, int MODE>
+template <typename C, bool TM, int MODE, bool SH>
 __device__ __forceinline__ void coarse_apply_phase(const CoarseArgs<C>& a, const C* z, C* zf, C* out, double* acc,
                                                    int tid, int stride, int n, unsigned int seq_g) {
     constexpr int U = CoarseBatch<C>::US;
     const CoarseShard<C>& sh = a.shard;
-    if (sh.nranks > 1) {
+    if (SH) {
         // push this rank's edge rows of the swept vector into the neighbours' ghost rows: CTA c owns the
         // columns [c chunk, (c+1) chunk) and raises flag c on the receiver
         const unsigned int par = seq_g & 1u;
@@ -535,9 +540,9 @@ __device__ __forceinline__ void coarse_apply_phase(const CoarseArgs<C>& a, const
                 const C zw = i > 0 ? coarse_zfin<C>(a, z, i - 1, j, q - 1) : czero<C>();
                 const C ze = i < a.Nx - 1 ? coarse_zfin<C>(a, z, i + 1, j, q + 1) : czero<C>();
                 const C zs = j > 0 ? coarse_zfin<C>(a, z, i, j - 1, q - a.Nx)
-                                   : (sh.open_s ? coarse_ghost<C>(sh, a.Nx, 0, i, seq_g) : czero<C>());
+                                   : (SH && sh.open_s ? coarse_ghost<C>(sh, a.Nx, 0, i, seq_g) : czero<C>());
                 const C zn = j < a.Ny - 1 ? coarse_zfin<C>(a, z, i, j + 1, q + a.Nx)
-                                          : (sh.open_n ? coarse_ghost<C>(sh, a.Nx, 1, i, seq_g) : czero<C>());
+                                          : (SH && sh.open_n ? coarse_ghost<C>(sh, a.Nx, 1, i, seq_g) : czero<C>());
                 o[u] = coarse_stencil5<C>(pc, zc[u], zw, ze, zs, zn);
                 rhv[u] = ldv(&a.rh[q]);
                 if (MODE == 1) sv[u] = ldv(&a.r[q]);
@@ -566,7 +571,7 @@ __device__ __forceinline__ void coarse_apply_phase(const CoarseArgs<C>& a, const
     }
 }
 
-template <typename C, bool TM>
+template <typename C, bool TM, bool SH>
 __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(CoarseArgs<C> a) {
 #ifdef FDFD_COARSE_TRACE
     unsigned long long tr[16];
@@ -577,15 +582,15 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
     __shared__ double red[kCoarseVals * kCoarseWarps];
     CoarseCtx<C> c;
     C* cursor = reinterpret_cast<C*>(coarse_smem);
-    c.ys = line_smem_carve<C>(cursor, a.yl);
-    c.xs = line_smem_carve<C>(cursor, a.xl);
+    c.ys = line_smem_carve<C>(cursor, a.yl, a.spikes_in_smem != 0);
+    c.xs = line_smem_carve<C>(cursor, a.xl, a.spikes_in_smem != 0);
     c.sl = cursor;
     c.sg = sg; c.su = su; c.red = red;
     if (threadIdx.x == 0) { sg[0] = czero<C>(); }
     c.gen_all = ld_acquire_u32(&a.bar[1]);
     c.gen_own = ld_acquire_u32(&a.bar[3]);
     c.seq_g = c.seq_r = c.seq_l = 0;
-    if (a.shard.nranks > 1) { c.seq_g = a.shard.seq[0]; c.seq_r = a.shard.seq[1]; c.seq_l = a.shard.seq[2]; }
+    if (SH) { c.seq_g = a.shard.seq[0]; c.seq_r = a.shard.seq[1]; c.seq_l = a.shard.seq[2]; }
     const int n = a.Nx * a.Ny;                       // < 2^31 (checked on the host)
     const int tid = blockIdx.x * kCoarseThreads + threadIdx.x;
     const int stride = gridDim.x * kCoarseThreads;
@@ -626,26 +631,26 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
     coarse_barrier(a.bar, nblk, c.gen_all);
     double tot2[2];
     coarse_grid_total<2>(a.partials, tot2, red);
-    coarse_rank_total<2, C>(a.shard, tot2, red, ++c.seq_r);
+    if (SH) coarse_rank_total<2, C>(a.shard, tot2, red, ++c.seq_r);
     double2 rho = make_double2(tot2[0], 0.0);
     double2 alpha = make_double2(1.0, 0.0), omega = make_double2(1.0, 0.0);
 
     for (int it = 0; it < a.its; ++it) {
         // (p^0 and the y-line right-hand sides of this iteration were written by the previous phase)
         COARSE_MARK(0);
-        coarse_line_phases<C, TM>(a, c, a.ph, a.p);
+        coarse_line_phases<C, TM, SH>(a, c, a.ph, a.p);
         COARSE_MARK(1);
         coarse_barrier(a.bar, nblk, c.gen_all);
         COARSE_MARK(2);
         // V: v = M p^, (r^, v)
         double accv[2] = {0.0, 0.0};
-        coarse_apply_phase<C, TM, 0>(a, a.ph, a.phf, a.v, accv, tid, stride, n, ++c.seq_g);
+        coarse_apply_phase<C, TM, 0, SH>(a, a.ph, a.phf, a.v, accv, tid, stride, n, ++c.seq_g);
         COARSE_MARK(3);
         coarse_block_reduce<2>(accv, prow, red);
         coarse_barrier(a.bar, nblk, c.gen_all);
         COARSE_MARK(4);
         coarse_grid_total<2>(a.partials, tot2, red);
-        coarse_rank_total<2, C>(a.shard, tot2, red, ++c.seq_r);
+        if (SH) coarse_rank_total<2, C>(a.shard, tot2, red, ++c.seq_r);
         COARSE_MARK(5);
         alpha = cs_div(rho, make_double2(tot2[0], tot2[1]));
         // S: s = r - alpha v (in r), s^0 pointwise
@@ -675,20 +680,20 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
         COARSE_MARK(6);
         coarse_barrier(a.bar, nblk, c.gen_all);
         COARSE_MARK(7);
-        coarse_line_phases<C, TM>(a, c, a.sh, a.r);
+        coarse_line_phases<C, TM, SH>(a, c, a.sh, a.r);
         COARSE_MARK(8);
         coarse_barrier(a.bar, nblk, c.gen_all);
         COARSE_MARK(9);
         // T: t = M s^, (t, s), (t, t), (r^, s), (r^, t)
         double acct[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        coarse_apply_phase<C, TM, 1>(a, a.sh, a.shf, a.t, acct, tid, stride, n, ++c.seq_g);
+        coarse_apply_phase<C, TM, 1, SH>(a, a.sh, a.shf, a.t, acct, tid, stride, n, ++c.seq_g);
         COARSE_MARK(10);
         coarse_block_reduce<8>(acct, prow, red);
         coarse_barrier(a.bar, nblk, c.gen_all);
         COARSE_MARK(11);
         double tot8[8];
         coarse_grid_total<8>(a.partials, tot8, red);
-        coarse_rank_total<8, C>(a.shard, tot8, red, ++c.seq_r);
+        if (SH) coarse_rank_total<8, C>(a.shard, tot8, red, ++c.seq_r);
         COARSE_MARK(12);
         omega = cs_div(make_double2(tot8[0], tot8[1]), make_double2(tot8[2], 0.0));
         // rho_new = (r^, s - omega t)
@@ -748,7 +753,7 @@ __global__ void __launch_bounds__(kCoarseThreads, 1) coarse_bicgstab_kernel(Coar
 #endif
     }
     // (every CTA read the sequence numbers before the first barrier of this launch)
-    if (a.shard.nranks > 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+    if (SH && blockIdx.x == 0 && threadIdx.x == 0) {
         a.shard.seq[0] = c.seq_g; a.shard.seq[1] = c.seq_r; a.shard.seq[2] = c.seq_l;
     }
 }

@@ -187,6 +187,41 @@ int stagger_fill(const int in_shape[3], const int out_shape[3], int axis, double
 
 using namespace fdfd;
 
+// §8f-2 — coefficient arrays of the scattering operator from an object-id map: out[q] = table[ids[q]] for the
+// three arrays at once (1 byte read, 48 bytes written per point).  No arithmetic on the values: the table is
+// evaluated by the caller with the reference's numpy expressions, which is what keeps the device set-up
+// bit-identical to Scattering_Solver_2D.py:72-153 + :176-188.
+namespace fdfd { namespace {
+__global__ void __launch_bounds__(256) scatter_fill_kernel(const uint8_t* __restrict__ ids, int64_t n, int ntab,
+        const double2* __restrict__ tab, double2* __restrict__ ca, double2* __restrict__ cb, double2* __restrict__ cd) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += stride) {
+        const int k = ids[q];
+        ca[q] = tab[k]; cb[q] = tab[ntab + k]; cd[q] = tab[2 * ntab + k];
+    }
+}
+} }
+
+extern "C" int fdfd_scatter_fill(const uint8_t* ids, int64_t n, int ntab, const double* table_host, void* ca, void* cb,
+                                 void* cd, void* stream) {
+    FDFD_CHECK_ARG(ids && table_host && ca && cb && cd, "null pointer");
+    FDFD_CHECK_ARG(n >= 1 && ntab >= 1 && ntab <= 256, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    double2* tab = nullptr;
+    FDFD_CUDA(cudaMalloc(&tab, sizeof(double2) * 3 * ntab));
+    cudaError_t e = cudaMemcpyAsync(tab, table_host, sizeof(double2) * 3 * ntab, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+        scatter_fill_kernel<<<blocks, 256, 0, st>>>(ids, n, ntab, tab, (double2*)ca, (double2*)cb, (double2*)cd);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(tab);
+    if (e != cudaSuccess) return cuda_fail(e, "fdfd_scatter_fill", __FILE__, __LINE__);
+    return FDFD_OK;
+}
+
 extern "C" int fdfd_stagger_csr_fill(const int in_shape[3], const int out_shape[3], int axis, double v_self, double v_fwd,
                                      int32_t* indptr, int32_t* indices, double* data, double* h_data, void* stream) {
     return stagger_fill(in_shape, out_shape, axis, v_self, v_fwd, indptr, indices, data, h_data, (cudaStream_t)stream);

@@ -95,6 +95,17 @@ int fdfd_stagger_csr_fill_host(const int in_shape[3], const int out_shape[3], in
                                int32_t* indptr, int32_t* indices, double* data, double* h_data);
 
 /* ------------------------------------------------------------------------------------------
+ * Set-up of the scattering operator on the device (reference: add_object / add_UPML /
+ * _build_A_* of Scattering_Solver_2D.py:72-153, :176-188): the three coefficient arrays from an object-id map,
+ *   ca[q] = table[0][ids[q]], cb[q] = table[1][ids[q]], cd[q] = table[2][ids[q]]
+ * ids: device uint8[n]; table_host: HOST complex128 [3][ntab] evaluated by the caller with the reference's
+ * numpy expressions (1/m_a, 1/m_b, diagonal term per object; entry 0 = background).  The UPML frame is
+ * overwritten afterwards by the caller with values computed on the O(perimeter) frame.  Synchronises.
+ * ------------------------------------------------------------------------------------------ */
+int fdfd_scatter_fill(const uint8_t* ids, int64_t n, int ntab, const double* table_host, void* ca, void* cb,
+                      void* cd, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K2  matrix-free complex Helmholtz / curl-curl operator on an Nx x Ny (slab of a) Yee grid
  *     — replaces the explicit sparse products of
  *       _build_A_TE / _build_A_TM   (Scattering_Solver_2D.py:176-188) and
