@@ -8,12 +8,14 @@ What changed underneath:
     sparse products (Band_Diagram_Solver.py:304-319); here the pencil is the matrix-free K2
     operator (only the two Bloch phases change between path points);
   * ``eigs(A, M=M, k, sigma)`` (ARPACK mode 3 + SuperLU, :313/:320) is replaced by the GPU
-    Krylov-Schur solver of ``fdfd_b200/eigs.py`` around a shifted solve on the device: a dense
-    LU of the (few thousand unknown) unit-cell operator, assembled on the GPU from five
-    phase-independent pieces, or the K3 Krylov solver for large cells.
-The shift actually used is ``eig_sigma - delta`` (delta > 0): the pencil's eigenvalues do not
-depend on it, and it keeps the shifted operator non-singular at Gamma where the reference's
-``sigma = 0`` is exactly singular (the reference relies on SuperLU surviving that).
+    one-CTA-per-path-point kernels of ``csrc/band.cu`` (block LU of the cyclic block-tridiagonal
+    shifted operator in shared memory + Arnoldi / Krylov-Schur cycles, all path points in lock-step);
+    cells those kernels do not cover fall back to the Krylov-Schur solver of ``fdfd_b200/eigs.py``
+    around a dense batched inverse or the K3 Krylov solver.
+For the reference's default ``eig_sigma = 0`` the shift actually used is ``-delta`` (delta > 0): the
+pencil's eigenvalues do not depend on it, and it keeps the shifted operator non-singular at Gamma where
+``sigma = 0`` is exactly singular (the reference relies on SuperLU surviving that).  A non-zero
+``eig_sigma`` is used as given.
 """
 from __future__ import annotations
 
@@ -253,8 +255,15 @@ class BandDiagramSolver2D:
         blas = _eigs.DeviceBlas(self.device)
         dense = inner == "lu" or (inner == "auto" and n <= self.DENSE_LIMIT)
         # effective shift: left of the (non-negative) spectrum when the requested shift is 0
+        # The reference's default shift sigma = 0 sits ON the spectrum at Gamma (A is singular there) and ARPACK
+        # survives it only through SuperLU's perturbed pivots; the shift actually used for sigma = 0 is -delta
+        # (left of the non-negative spectrum: same "k nearest" set).  A caller's non-zero shift is used as given,
+        # so that its nearest-eigenvalue set is the reference's eigs(sigma=eig_sigma).
         delta = (2 * np.pi * 0.05 / self.a) ** 2
-        sigma = float(np.real(eig_sigma)) - delta if np.imag(eig_sigma) == 0 else eig_sigma - delta
+        if eig_sigma == 0:
+            sigma = -delta
+        else:
+            sigma = float(np.real(eig_sigma)) if np.imag(eig_sigma) == 0 else complex(eig_sigma)
         info = dict(restarts=0, inner="lu" if dense else "krylov", eigensolves=0, max_residual=0.0)
         for pol in ("TM", "TE"):          # reference order inside the loop (:311-323)
             if pol not in polarisations:
