@@ -462,7 +462,7 @@ extern "C" int fdfd_linop_solve(fdfd_linop_t* h, const fdfd_krylov_opts* opts, c
     int s = FDFD_OK;
     bool done = false;
     // small factored operators: the whole solve in one persistent kernel (the launch chain is pure latency there)
-    static const bool no_persist = getenv("FDFD_NO_PERSISTENT_BICGSTAB") != nullptr;
+    const bool no_persist = getenv("FDFD_NO_PERSISTENT_BICGSTAB") != nullptr;   // read per solve: tests switch it
     CsrProductOp* prod = dynamic_cast<CsrProductOp*>(h->op);
     if (!no_persist && prod && A.dtype == FDFD_C128 && opts->method == FDFD_KRYLOV_BICGSTAB &&
         A.n_local() <= ((int64_t)1 << 22))
