@@ -271,7 +271,7 @@ def run_ours(args):
     if not args.no_solve:
         line["solve"] = [solve_record(N, pol, opts, comm, rank, world, dev, barrier) if world >= need else
                          {"grid": f"{N}x{N}", "pol": pol, "n_gpus": world, "skipped":
-                          f"needs >= {need} GPUs: FGMRES({opts.get('restart')}) basis + corrections do not fit 180 GB"}
+                          f"needs >= {need} GPUs: the FGMRES(40) basis + corrections do not fit 180 GB"}
                          for N, pol, opts, need in solve_plan(args, world)]
     if world == 1 and rank == 0 and not args.no_solve:
         line["solve_dropin"] = dropin_time_to_solution()
@@ -298,8 +298,8 @@ def run_ours(args):
 #               the longest whose Krylov vectors fit beside the operator in 180 GB, it stagnates at 1e-3 (measured,
 #               12 300 iterations) — i.e. 174 GB of basis + corrections: it is solved from N = 2 up and its strong
 #               scaling is read relative to N = 2.
-SOLVE_LARGE = [dict(N=16384, pol="TM", opts=dict(restart=10), min_gpus=1),
-               dict(N=16384, pol="TE", opts=dict(restart=40), min_gpus=2)]
+SOLVE_LARGE = [dict(N=16384, pol="TM", opts={}, min_gpus=1),       # polarisation defaults: FGMRES(8)
+               dict(N=16384, pol="TE", opts={}, min_gpus=2)]       # FGMRES(40), shift (1, 0.3)
 
 
 def solve_plan(args, world):

@@ -515,6 +515,19 @@ class FDFD2DScatteringSolver:
         amp = self.AMPLIFICATION_PER_SQRT_WAVELENGTH * np.sqrt(max(L, 1.0))
         return float(min(1e-8, field_tol / (1.25 * amp)))
 
+    @staticmethod
+    def polarisation_defaults(pol):
+        """Krylov / multigrid options that depend on the polarisation (measured at 4096^2, eps = -1e6 cylinder,
+        three incidence angles each, `scripts/bench_solve.py`; profiles/r02_solver_option_sweep.txt).
+        TE (Ez) needs a long recurrence — FGMRES(30) stagnates for one of the angles — and converges
+        more regularly with the smaller imaginary shift (437-461 iterations at (40, 0.3) against 480-597 at
+        (40, 0.4)).  TM is a near-fixed contraction under the multigrid cycle: iteration counts do not
+        depend on the restart length (335-357 for 4...30), so the shortest basis wins (0.83 s at 8 against
+        1.08 s at 30: the Gram-Schmidt traffic)."""
+        if pol.upper() == "TE":
+            return dict(restart=40, mg_shift_im=0.3)
+        return dict(restart=8)
+
     def _solve(self, pol, reuse_factorisation=True):
         A = self.operator(pol)
         if not reuse_factorisation:
@@ -525,9 +538,8 @@ class FDFD2DScatteringSolver:
         if opts.get("rtol") is None:
             # complex64 operators cannot resolve residuals below ~1e-5: their callers set rtol themselves
             opts["rtol"] = self.default_rtol(field_tol) if str(self.dtype).endswith("128") else 1e-4
-        # TE (Ez) with strongly negative eps needs a longer recurrence than TM (measured at 4096^2:
-        # FGMRES(20) stagnates, (30) 595 its, (40) 432 its; TM is fastest at 20-30)
-        opts.setdefault("restart", 40 if pol.upper() == "TE" else 30)
+        for k, v in self.polarisation_defaults(pol).items():
+            opts.setdefault(k, v)
         if opts.get("precond") == "mg":
             opts.setdefault("line_x_lo", self._pml["x"])
             opts.setdefault("line_x_hi", self._pml["x"])

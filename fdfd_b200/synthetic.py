@@ -100,8 +100,8 @@ def sharded_scattering_solve(Nx, Ny, pol="TE", comm=None, rank=0, world=1, devic
     from .scattering import FDFD2DScatteringSolver
     amp = FDFD2DScatteringSolver.AMPLIFICATION_PER_SQRT_WAVELENGTH * math.sqrt(max(max(Nx, Ny) * (lam0 / 50.0) / lam0, 1.0))
     opts = dict(method="fgmres", precond="mg", rtol=min(1e-8, 1e-6 / (1.25 * amp)), maxit=20000,
-                restart=40 if pol.upper() == "TE" else 30, mg_single=1, basis_single=1,
-                line_x_lo=pml, line_x_hi=pml, line_y_lo=pml, line_y_hi=pml)
+                mg_single=1, basis_single=1, line_x_lo=pml, line_x_hi=pml, line_y_lo=pml, line_y_hi=pml)
+    opts.update(FDFD2DScatteringSolver.polarisation_defaults(pol))
     opts.update(solver or {})
     t0 = time.perf_counter()
     x, info = A.solve(b, raise_on_noconv=False, **opts)

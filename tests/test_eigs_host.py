@@ -47,6 +47,11 @@ def test_plane_block_solver_algebra(Nz):
     s = fdfd_b200.PeriodicModeSolver3D(6, 5, Nz, 3e-3, 2.5e-3, 2e-3, 30e9, 1, sigma_guess=-200j, tol=1e-8, ncv=10)
     s.add_block(4, 1, (1e-3, 2e-3), (0, 1e-3), (0, Nz), subpixels=2)
     s.add_pec((0, 3e-3), (2e-3, 2.5e-3), (0, Nz))
+    # the class assembles its staggered operators on the GPU; on this CPU box the oracle's (bit-identical,
+    # tests/test_oracle_vs_reference.py) stand in so that the host algebra of the block solver can be checked
+    from oracle import periodic3d_oracle
+    for name, mat in periodic3d_oracle.operators(6, 5, Nz, s.dx, s.dy, s.dz).items():
+        setattr(s, name, mat)
     A, B = s._build_eigen_matrices()
     solver = eigs.PlaneBlockShiftedSolver(A.tocsr(), B.tocsr(), s.sigma_guess, s._unknown_planes(), s.Nz, "cpu", refine=False)
     assert solver.ns == (Nz + 1) // 2
