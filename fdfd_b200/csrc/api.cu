@@ -157,7 +157,10 @@ struct HostPipe {
 template <typename C>
 int apply_host_pipelined(Helm2D& op, HostPipe& pipe, const C* xh, C* yh) {
     const int Nx = op.Nx, Ny = op.Ny;
-    int rows = (int)(((size_t)24 << 20) / ((size_t)Nx * sizeof(C)));      // ~24 MB per chunk
+    // chunk size: the pipeline's fill / drain costs two chunk transfers on top of the streaming time, so
+    // chunks are kept small (FDFD_HOST_CHUNK_MB overrides; measured in profiles/r02_host_pipeline_chunks.txt)
+    static const int chunk_mb = [] { const char* e = getenv("FDFD_HOST_CHUNK_MB"); int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+    int rows = (int)(((size_t)chunk_mb << 20) / ((size_t)Nx * sizeof(C)));
     rows = rows < 8 ? 8 : (rows / 8) * 8;                                 // multiple of the tile height
     const int nch = (Ny + rows - 1) / rows;
     FDFD_TRY(pipe.ensure((size_t)nch));
