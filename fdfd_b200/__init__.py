@@ -16,5 +16,11 @@ from .periodic_solver_3d import PeriodicModeSolver3D  # noqa: F401
 from .eigs import refined_shift_invert_arnoldi  # noqa: F401
 from . import sweeps, stagger  # noqa: F401
 
+
+def trim_memory():
+    """Release the library's cached device work buffers (csrc/devpool.cu); returns the bytes released."""
+    from . import _lib
+    return int(_lib.lib().fdfd_trim_memory())
+
 __all__ = ["yeeder2d", "yeeder2d_device", "HelmholtzOperator2D", "SlabComm", "slab_rows",
-           "FDFD2DScatteringSolver", "BandDiagramSolver2D", "BandStructureResult", "ModeSolver2D", "PeriodicModeSolver3D", "refined_shift_invert_arnoldi", "sweeps", "stagger", "FdfdError", "NoConvergence"]
+           "FDFD2DScatteringSolver", "BandDiagramSolver2D", "BandStructureResult", "ModeSolver2D", "PeriodicModeSolver3D", "refined_shift_invert_arnoldi", "sweeps", "stagger", "FdfdError", "NoConvergence", "trim_memory"]

@@ -52,6 +52,7 @@ _PROTOTYPES = {
     "fdfd_version": (C.c_int, []),
     "fdfd_krylov_opts_size": (C.c_int, []),
     "fdfd_device_count": (C.c_int, []),
+    "fdfd_trim_memory": (C.c_int64, []),
     "fdfd_yee2d_csr_nnz": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                      C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "fdfd_yee2d_csr_fill": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.c_void_p, C.c_void_p,
@@ -82,6 +83,8 @@ _PROTOTYPES = {
                                       C.c_void_p, C.c_void_p]),
     "fdfd_blas_multi_axpy": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                        C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "fdfd_tsqr_r": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p,
+                              C.c_void_p]),
     "fdfd_band_max_nx": (C.c_int, []),
     "fdfd_band_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int,

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 _VARIANT = os.environ.get("FDFD_BUILD_VARIANT", "")
 _VNAME = "trace" if os.environ.get("FDFD_COARSE_TRACE") else (_VARIANT.split(":", 1)[0] if _VARIANT else "")
 LIB = os.path.join(HERE, f"libfdfd_b200_{_VNAME}.so" if _VNAME else "libfdfd_b200.so")
-SOURCES = ["api.cu", "yee_assemble.cu", "helm2d.cu", "blas1.cu", "krylov.cu", "comm.cu", "p2p.cu", "mg.cu", "csr_ops.cu", "band.cu"]
+SOURCES = ["api.cu", "yee_assemble.cu", "helm2d.cu", "blas1.cu", "krylov.cu", "comm.cu", "p2p.cu", "mg.cu", "csr_ops.cu", "band.cu", "devpool.cu", "tsqr.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -11,15 +11,15 @@
 namespace fdfd {
 
 int Scalars::alloc() {
-    FDFD_CUDA(cudaMalloc(&slot, sizeof(double2) * kSlots));
+    FDFD_CUDA(dev_alloc(&slot, sizeof(double2) * kSlots));
     FDFD_CUDA(cudaMemset(slot, 0, sizeof(double2) * kSlots));
-    FDFD_CUDA(cudaMalloc(&partials, sizeof(double) * 2 * kMaxBlocks * 64));
-    FDFD_CUDA(cudaMalloc(&counter, sizeof(unsigned int)));
+    FDFD_CUDA(dev_alloc(&partials, sizeof(double) * 2 * kMaxBlocks * 64));
+    FDFD_CUDA(dev_alloc(&counter, sizeof(unsigned int)));
     FDFD_CUDA(cudaMemset(counter, 0, sizeof(unsigned int)));
     return FDFD_OK;
 }
 void Scalars::release() {
-    cudaFree(slot); cudaFree(partials); cudaFree(counter);
+    dev_free(slot); dev_free(partials); dev_free(counter);
     slot = nullptr; partials = nullptr; counter = nullptr;
 }
 

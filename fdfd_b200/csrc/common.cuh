@@ -28,6 +28,13 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// cached device allocations for small work buffers (devpool.cu): same contract as cudaMalloc / cudaFree,
+// the contents of a recycled block are undefined
+cudaError_t dev_alloc(void** out, size_t bytes);
+template <typename T> inline cudaError_t dev_alloc(T** out, size_t bytes) { return dev_alloc((void**)out, bytes); }
+void dev_free(void* p);
+size_t dev_trim();
+
 // ---- complex arithmetic on (re, im) pairs -------------------------------------------------
 template <typename T> struct cplx_of;
 template <> struct cplx_of<double> { using type = double2; };

@@ -63,7 +63,7 @@ struct CsrProductOp : LinOp {
     CsrDev P, Q;
     double shift_re = 0.0, shift_im = 0.0;
     void* tmp = nullptr;   // m elements
-    ~CsrProductOp() override { cudaFree(tmp); }
+    ~CsrProductOp() override { dev_free(tmp); }
     int64_t n_local() const override { return P.nrows; }
 
     template <typename C>
@@ -331,8 +331,8 @@ struct PbState {
     double* result = nullptr;
     int grid = 0;
     ~PbState() {
-        for (auto p : vec) cudaFree(p);
-        cudaFree(partials); cudaFree(bar); cudaFree(result);
+        for (auto p : vec) dev_free(p);
+        dev_free(partials); dev_free(bar); dev_free(result);
     }
 };
 
@@ -348,13 +348,13 @@ int csr_product_bicgstab_persistent(CsrProductOp& A, PbState*& stp, const fdfd_k
     if (!stp) {
         stp = new PbState();
         const size_t nb = (size_t)A.P.nrows * sizeof(double2), mb = (size_t)A.Q.nrows * sizeof(double2);
-        for (int k = 0; k < 7; ++k) FDFD_CUDA(cudaMalloc(&stp->vec[k], nb));
-        FDFD_CUDA(cudaMalloc(&stp->vec[7], mb));
+        for (int k = 0; k < 7; ++k) FDFD_CUDA(dev_alloc(&stp->vec[k], nb));
+        FDFD_CUDA(dev_alloc(&stp->vec[7], mb));
         stp->grid = sms;
-        FDFD_CUDA(cudaMalloc(&stp->partials, (size_t)stp->grid * kPbVals * sizeof(double)));
-        FDFD_CUDA(cudaMalloc(&stp->bar, 2 * sizeof(unsigned int)));
+        FDFD_CUDA(dev_alloc(&stp->partials, (size_t)stp->grid * kPbVals * sizeof(double)));
+        FDFD_CUDA(dev_alloc(&stp->bar, 2 * sizeof(unsigned int)));
         FDFD_CUDA(cudaMemset(stp->bar, 0, 2 * sizeof(unsigned int)));
-        FDFD_CUDA(cudaMalloc(&stp->result, 4 * sizeof(double)));
+        FDFD_CUDA(dev_alloc(&stp->result, 4 * sizeof(double)));
     }
     PbArgs a;
     a.n = A.P.nrows; a.m = A.Q.nrows;
@@ -429,7 +429,7 @@ extern "C" int fdfd_csr_product_create(fdfd_linop_t** out, int dtype, int n, int
     op->P.nrows = n; op->P.ncols = m; op->P.indptr = P_indptr; op->P.indices = P_indices; op->P.data = P_data;
     op->Q.nrows = m; op->Q.ncols = n; op->Q.indptr = Q_indptr; op->Q.indices = Q_indices; op->Q.data = Q_data;
     op->shift_re = shift_re; op->shift_im = shift_im;
-    cudaError_t e = cudaMalloc(&op->tmp, (size_t)m * op->elem());
+    cudaError_t e = dev_alloc(&op->tmp, (size_t)m * op->elem());
     if (e != cudaSuccess) { delete op; return cuda_fail(e, "cudaMalloc(csr product tmp)", __FILE__, __LINE__); }
     *out = new fdfd_linop{op};
     return FDFD_OK;

@@ -21,7 +21,7 @@ struct DeviceBuf {
     void* p = nullptr;
     bool owned = true;
     int alloc(size_t bytes) {
-        FDFD_CUDA(cudaMalloc(&p, bytes));
+        FDFD_CUDA(dev_alloc(&p, bytes));
         return FDFD_OK;
     }
     // carve from a caller-owned arena (256-byte aligned) when one is given
@@ -32,7 +32,7 @@ struct DeviceBuf {
         cursor += (bytes + 255) & ~(size_t)255;
         return FDFD_OK;
     }
-    ~DeviceBuf() { if (p && owned) cudaFree(p); }
+    ~DeviceBuf() { if (p && owned) dev_free(p); }
 };
 
 int read_slots(Scalars& sc, int s0, int count, double2* host, cudaStream_t stream) {
@@ -51,7 +51,7 @@ struct JacobiPrecond : Precond {
     int64_t n = 0;
     void* dinv = nullptr;
     bool owned = true;
-    ~JacobiPrecond() override { if (dinv && owned) cudaFree(dinv); }
+    ~JacobiPrecond() override { if (dinv && owned) dev_free(dinv); }
     int apply(const void* v, void* z, cudaStream_t stream) override {
         ++applies;
         if (dtype == FDFD_C128)
@@ -66,15 +66,15 @@ int BicgWorkspace::ensure(size_t bytes, bool precond) {
     if (!sc.slot) FDFD_TRY(sc.alloc());
     const int need = precond ? 7 : 5;
     if (bytes > cap) {
-        for (int i = 0; i < 7; ++i) { cudaFree(v[i]); v[i] = nullptr; }
+        for (int i = 0; i < 7; ++i) { dev_free(v[i]); v[i] = nullptr; }
         cap = bytes; count = 0;
     }
-    for (int i = count; i < need; ++i) FDFD_CUDA(cudaMalloc(&v[i], cap));
+    for (int i = count; i < need; ++i) FDFD_CUDA(dev_alloc(&v[i], cap));
     if (need > count) count = need;
     return FDFD_OK;
 }
 BicgWorkspace::~BicgWorkspace() {
-    for (int i = 0; i < 7; ++i) cudaFree(v[i]);
+    for (int i = 0; i < 7; ++i) dev_free(v[i]);
     sc.release();
 }
 
@@ -522,7 +522,7 @@ int fgmres_t(LinOp& A, Precond* M, const fdfd_krylov_opts& o, const C* b, C* x, 
 int make_jacobi_precond(Helm2D& A, Precond** out, cudaStream_t stream) {
     JacobiPrecond* P = new JacobiPrecond();
     P->dtype = A.dtype; P->n = A.n_local();
-    cudaError_t e = cudaMalloc(&P->dinv, (size_t)A.n_local() * A.elem());
+    cudaError_t e = dev_alloc(&P->dinv, (size_t)A.n_local() * A.elem());
     if (e != cudaSuccess) { delete P; return cuda_fail(e, "cudaMalloc(dinv)", __FILE__, __LINE__); }
     // halo not needed: the diagonal only depends on coefficients
     int st;

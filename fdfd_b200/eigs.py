@@ -73,6 +73,21 @@ class DeviceBlas:
                                                     C.byref(nrm) if want_norm else None, self._stream()))
         return nrm.value if want_norm else None
 
+    def tsqr_r(self, AV, BV=None, theta=0.0):
+        """Triangular factor R (m x m numpy) of the QR factorisation of (AV - theta * BV)^T, AV / BV being
+        (m, n) device tensors with contiguous rows (K7, csrc/tsqr.cu)."""
+        import torch
+        m, n = AV.shape
+        if AV.dtype != torch.complex128 or AV.stride(1) != 1 or (BV is not None and (BV.shape != AV.shape or BV.stride() != AV.stride()
+                                                                                  or BV.dtype != AV.dtype)):
+            raise ValueError("tsqr_r needs complex128 (m, n) tensors with contiguous rows and equal strides")
+        Rt = torch.empty((m, m), dtype=torch.complex128, device=self.device)
+        theta = complex(theta)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.fdfd_tsqr_r(m, n, AV.data_ptr(), BV.data_ptr() if BV is not None else None, AV.stride(0),
+                                           theta.real, theta.imag, Rt.data_ptr(), self._stream()))
+        return Rt.cpu().numpy().T.copy()
+
 
 def krylov_schur(op, n, k, *, ncv=None, tol=1e-10, max_restarts=100, v0=None, seed=0, device=None,
                  dtype=None, blas=None):
@@ -470,11 +485,15 @@ def refined_shift_invert_arnoldi(A, B, sigma, num_modes, tol, ncv=None, max_rest
         for t in theta[np.argsort(np.abs(theta - sigma))]:
             if any(abs(t - s) <= 1e-8 * max(1.0, abs(t)) for s in seen):
                 continue
-            W = (AV - complex(t) * BV).T.contiguous()             # n x m residual basis
-            R = torch.linalg.qr(W, mode="r").R.cpu().numpy()
+            # refined Ritz vector: right singular vector of the n x m matrix (A - t B) V for its smallest singular
+            # value = that of the triangular factor R (K7: Householder TSQR kernel, the matrix is never formed)
+            if count <= 64:
+                R = blas.tsqr_r(AV, BV, t)
+            else:                                                   # wider than the kernel's panels (ncv > 64)
+                R = torch.linalg.qr((AV - complex(t) * BV).T.contiguous(), mode="r").R.cpu().numpy()
             y = np.linalg.svd(R)[2].conj().T[:, -1]
-            x = torch.from_numpy(np.ascontiguousarray(y)).to(device) @ Vc
-            nx = float(torch.linalg.vector_norm(x))
+            x = torch.zeros(n, dtype=torch.complex128, device=device)
+            nx = float(np.sqrt(max(blas.multi_axpy(Vc, count, x, y, 1.0, want_norm=True), 0.0)))      # x = sum y_i V_i
             if nx == 0:
                 continue
             x = x / nx

@@ -49,6 +49,9 @@ int fdfd_version(void);
 int fdfd_krylov_opts_size(void);
 /* number of visible CUDA devices (0 when none) — the Python layer refuses to run on 0. */
 int fdfd_device_count(void);
+/* The library recycles its small device work buffers (<= 64 MB each, <= 1 GB in total) between operators and
+ * solves instead of returning them to the driver; this releases them.  Returns the bytes released. */
+int64_t fdfd_trim_memory(void);
 
 /* ------------------------------------------------------------------------------------------
  * K1  Yee derivative-operator assembly  — replaces yeeder2d(NS, RES, BC, kinc)
@@ -207,6 +210,14 @@ int fdfd_blas_multi_dot(fdfd_blas_t*, int dtype, int64_t n, int k, const void* V
                         const void* w, double* h_host, void* stream);
 int fdfd_blas_multi_axpy(fdfd_blas_t*, int dtype, int64_t n, int k, const void* V, int64_t ldv,
                          void* w, const double* h_host, double sign, double* nrm2_host, void* stream);
+
+/* K7  tall-skinny QR of W = (AV - theta * BV)^T (n x m) for the refined Ritz extraction — replaces the n x m SVD
+ *     of refined_shift_invert_arnoldi.py:85 (`np.linalg.svd((A - theta B) V)`): the right singular vectors of W are
+ *     those of its m x m factor R.  AV, BV: device complex128, m rows of length n, leading dimension ld; BV may be
+ *     NULL.  Rt_dev (device, m*m complex128) receives R column by column (Rt[c*m + i] = R[i][c]).  1 <= m <= 64.
+ *     Householder panels in shared memory + a tree over the stacked triangles (csrc/tsqr.cu). */
+int fdfd_tsqr_r(int m, int64_t n, const void* AV, const void* BV, int64_t ld, double theta_re, double theta_im,
+                void* Rt_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K6b  batched shift-invert Arnoldi for the Bloch sweep of a unit cell — replaces, for ALL path points at
