@@ -79,6 +79,15 @@ def test_no_cpu_fallback(lib):
     sim.add_source("plane_wave")
     with pytest.raises(fdfd_b200.FdfdError):
         sim.solve_total_field_TE()
+    # the newer entry points refuse as well (argument checks first, then the device check), and the memory cache is
+    # empty on a box that never allocated
+    buf = (C.c_double * 8)()
+    assert lib.fdfd_tsqr_r(2, 2, buf, None, 2, 0.0, 0.0, buf, None) == _lib.FDFD_ERR_CUDA
+    assert lib.fdfd_tsqr_r(65, 100, buf, None, 100, 0.0, 0.0, buf, None) == _lib.FDFD_ERR_ARG
+    assert lib.fdfd_tsqr_r(2, 4, buf, None, 3, 0.0, 0.0, buf, None) == _lib.FDFD_ERR_ARG
+    assert fdfd_b200.trim_memory() == 0
+    with pytest.raises(fdfd_b200.FdfdError):
+        fdfd_b200.ModeSolver2D(50e9, 2e-3, 2e-3, 8, 8, 1).solve()
 
 
 def test_product_does_not_import_oracle():
