@@ -15,6 +15,9 @@
 #include "krylov.cuh"
 #include "persist.cuh"
 
+#include <algorithm>
+#include <vector>
+
 namespace fdfd {
 
 constexpr int kCsrLanes = 4;
@@ -323,6 +326,204 @@ __global__ void __launch_bounds__(kPbThreads, 1) csr_product_bicgstab_kernel(PbA
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Resident variant: when both factors have at most gridDim.x * blockDim.x rows, thread t of CTA b OWNS row
+// b*T + t of every vector for the whole solve.  x, r, r^, p, v, p^, s^ and 1/diag of that row live in registers;
+// the CSR rows of the CTA (P and Q, ~75 KB each at config 2) are staged into shared memory once per solve, so
+// the only global traffic of an iteration is what other threads must see (p^, s^, Q-products) and the gathers of
+// it — one L2 round trip per sparse phase with all gathers of a row in flight (kPrBatch).  rho_{k+1} comes from
+// (r^, s) - omega (r^, t) and ||r||^2 from (s,s) - |(t,s)|^2 / (t,t), so the x / r update needs no barrier of its
+// own: 6 grid barriers per iteration.  Convergence test, true-residual confirmation, restart and rounding-floor
+// stop are those of the general kernel above.
+constexpr int kPrMaxThreads = 576;
+constexpr int kPrBatch = 8;
+
+__device__ __forceinline__ double2 pr_row(const int32_t* idx, const double2* dat, int e0, int cnt, const double2* x) {
+    double ax = 0, ay = 0;
+    for (int j0 = 0; j0 < cnt; j0 += kPrBatch) {
+        double2 xv[kPrBatch];
+#pragma unroll
+        for (int j = 0; j < kPrBatch; ++j)
+            xv[j] = (j0 + j < cnt) ? __ldcg(&x[idx[e0 + j0 + j]]) : make_double2(0, 0);
+#pragma unroll
+        for (int j = 0; j < kPrBatch; ++j) {
+            if (j0 + j < cnt) {
+                const double2 d = dat[e0 + j0 + j];
+                ax += d.x * xv[j].x - d.y * xv[j].y;
+                ay += d.x * xv[j].y + d.y * xv[j].x;
+            }
+        }
+    }
+    return make_double2(ax, ay);
+}
+
+// CTA-wide sums of K doubles per thread -> partials row (runtime block size)
+template <int K>
+__device__ __forceinline__ void pr_partials(double (&v)[K], double* row, double* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, W = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+        if (lane == 0) sm[k * (kPrMaxThreads / 32) + warp] = v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double s = 0.0;
+        for (int w = 0; w < W; ++w) s += sm[threadIdx.x * (kPrMaxThreads / 32) + w];
+        row[threadIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kPrMaxThreads, 1) csr_product_bicgstab_resident_kernel(PbArgs a, int capP, int capQ) {
+    extern __shared__ __align__(16) unsigned char pr_smem[];
+    double2* P_dat = reinterpret_cast<double2*>(pr_smem);
+    double2* Q_dat = P_dat + capP;
+    int32_t* P_idx = reinterpret_cast<int32_t*>(Q_dat + capQ);
+    int32_t* Q_idx = P_idx + capP;
+    __shared__ double red[kPbVals * (kPrMaxThreads / 32)];
+    const int T = blockDim.x, t = threadIdx.x;
+    const int row = blockIdx.x * T + t;
+    const bool liveP = row < a.n, liveQ = row < a.m;
+    double* prow = a.partials + (size_t)blockIdx.x * kPbVals;
+    const unsigned int nblk = gridDim.x;
+    unsigned int gen = ld_acquire_u32(&a.bar[1]);
+
+    // stage this CTA's rows of both factors
+    int pe0 = 0, pcnt = 0, qe0 = 0, qcnt = 0;
+    {
+        const int r0 = min(a.n, (int)blockIdx.x * T), r1 = min(a.n, (int)blockIdx.x * T + T);
+        const int base = a.P_indptr[r0], end = a.P_indptr[r1];
+        for (int e = base + t; e < end; e += T) { P_idx[e - base] = a.P_indices[e]; P_dat[e - base] = a.P_data[e]; }
+        if (liveP) { const int s0 = a.P_indptr[row]; pe0 = s0 - base; pcnt = a.P_indptr[row + 1] - s0; }
+    }
+    {
+        const int r0 = min(a.m, (int)blockIdx.x * T), r1 = min(a.m, (int)blockIdx.x * T + T);
+        const int base = a.Q_indptr[r0], end = a.Q_indptr[r1];
+        for (int e = base + t; e < end; e += T) { Q_idx[e - base] = a.Q_indices[e]; Q_dat[e - base] = a.Q_data[e]; }
+        if (liveQ) { const int s0 = a.Q_indptr[row]; qe0 = s0 - base; qcnt = a.Q_indptr[row + 1] - s0; }
+    }
+    __syncthreads();
+
+    const double2 zero = make_double2(0, 0);
+    double2 x = liveP ? a.x[row] : zero;
+    const double2 dinv = (liveP && a.dinv) ? a.dinv[row] : make_double2(1, 0);
+    double2 r = zero, rh = zero, p = zero, v = zero, ph = zero, sh = zero;
+
+    auto total = [&](double (&acc)[kPbVals], double (&tot)[kPbVals]) {
+        pr_partials<kPbVals>(acc, prow, red);
+        grid_barrier(a.bar, nblk, gen);
+        grid_total<kPbVals>(a.partials, kPbVals, tot, red);
+    };
+    // tmp = Q in  (in: a global vector every thread has already published its entry of)
+    auto apply_Q = [&](const double2* in) {
+        grid_barrier(a.bar, nblk, gen);                         // `in` complete
+        if (liveQ) a.tmp[row] = pr_row(Q_idx, Q_dat, qe0, qcnt, in);
+        grid_barrier(a.bar, nblk, gen);                         // tmp complete
+    };
+
+    double bnorm2 = 0, rr = 0, true_rr = 0, last_true = -1.0;
+    double2 rho = make_double2(1, 0), rho_old = rho, alpha = rho, omega = rho;
+    int it = 0, restarts = 0, floor_hits = 0, since_best = 0;
+    double best = 0;
+    bool stop = false;
+
+    // (re)start: r = b - A x, r^ = r, p = v = 0
+    auto restart = [&](bool first) {
+        if (liveP) a.x[row] = x;
+        apply_Q(a.x);
+        double acc[kPbVals] = {0, 0, 0, 0, 0, 0, 0, 0}, tot[kPbVals];
+        if (liveP) {
+            double2 s = pr_row(P_idx, P_dat, pe0, pcnt, a.tmp);
+            s = cfma(a.shift, x, s);
+            const double2 bv = a.b[row];
+            r = csub(bv, s); rh = r; p = zero; v = zero;
+            acc[0] = r.x * r.x + r.y * r.y;
+            acc[1] = bv.x * bv.x + bv.y * bv.y;
+        }
+        total(acc, tot);
+        rr = tot[0];
+        if (first) bnorm2 = tot[1] > 0 ? tot[1] : 1.0;
+        rho = make_double2(rr, 0); rho_old = make_double2(1, 0); alpha = rho_old; omega = rho_old;
+        best = rr; since_best = 0;
+    };
+    restart(true);
+    const double target2 = a.rtol * a.rtol * bnorm2;
+    true_rr = rr;
+
+    while (rr > target2 && it < a.maxit && !stop) {
+        ++it;
+        // p = r + beta (p - omega v) ; p^ = dinv p
+        const double2 beta = cmul(pb_div(rho, rho_old), pb_div(alpha, omega));
+        p = cfma(cneg(cmul(beta, omega)), v, cfma(beta, p, r));
+        ph = cmul(dinv, p);
+        if (liveP) a.ph[row] = ph;
+        // v = A p^ ; (r^, v)
+        apply_Q(a.ph);
+        double acc[kPbVals] = {0, 0, 0, 0, 0, 0, 0, 0}, tot[kPbVals];
+        if (liveP) {
+            v = cfma(a.shift, ph, pr_row(P_idx, P_dat, pe0, pcnt, a.tmp));
+            acc[0] = rh.x * v.x + rh.y * v.y;
+            acc[1] = rh.x * v.y - rh.y * v.x;
+        }
+        total(acc, tot);
+        alpha = pb_div(rho, make_double2(tot[0], tot[1]));
+        // s = r - alpha v (kept in r) ; s^ = dinv s ; (s,s) and (r^,s) ride along with the next total
+        r = csub(r, cmul(alpha, v));
+        sh = cmul(dinv, r);
+        if (liveP) a.sh[row] = sh;
+        // t = A s^ ; (t,s), (t,t), (r^,t)
+        apply_Q(a.sh);
+        for (int k = 0; k < kPbVals; ++k) acc[k] = 0;
+        double2 tv = zero;
+        if (liveP) {
+            tv = cfma(a.shift, sh, pr_row(P_idx, P_dat, pe0, pcnt, a.tmp));
+            acc[0] = tv.x * r.x + tv.y * r.y;
+            acc[1] = tv.x * r.y - tv.y * r.x;
+            acc[2] = tv.x * tv.x + tv.y * tv.y;
+            acc[3] = rh.x * tv.x + rh.y * tv.y;
+            acc[4] = rh.x * tv.y - rh.y * tv.x;
+            acc[5] = r.x * r.x + r.y * r.y;
+            acc[6] = rh.x * r.x + rh.y * r.y;
+            acc[7] = rh.x * r.y - rh.y * r.x;
+        }
+        total(acc, tot);
+        omega = pb_div(make_double2(tot[0], tot[1]), make_double2(tot[2], 0));
+        // x += alpha p^ + omega s^ ; r = s - omega t ; rho = (r^,s) - omega (r^,t) ; ||r||^2 = (s,s) - |(t,s)|^2/(t,t)
+        x = cfma(omega, sh, cfma(alpha, ph, x));
+        r = csub(r, cmul(omega, tv));
+        rho_old = rho;
+        rho = csub(make_double2(tot[6], tot[7]), cmul(omega, make_double2(tot[3], tot[4])));
+        rr = tot[5] - (tot[2] > 0 ? (tot[0] * tot[0] + tot[1] * tot[1]) / tot[2] : 0.0);
+        if (rr < 0) rr = 0;
+        if (!isfinite(rr)) {
+            if (++restarts > 5) { stop = true; break; }
+            restart(false);
+            if (!isfinite(rr)) { stop = true; break; }
+            continue;
+        }
+        if (rr < best) { best = rr; since_best = 0; }
+        else if (++since_best >= 200) { ++restarts; restart(false); }
+        if (rr <= target2) {
+            restart(false);                                  // true residual; rebuilds the recurrences
+            true_rr = rr;
+            if (rr > target2) {
+                if (last_true > 0 && rr > 0.25 * last_true) ++floor_hits; else floor_hits = 0;
+                last_true = rr;
+                if (floor_hits >= 3) stop = true;           // rounding floor of b - A x reached
+            }
+        }
+    }
+    restart(false);                                          // publishes x, true residual of the returned iterate
+    true_rr = rr;
+    if (blockIdx.x == 0 && t == 0) {
+        a.result[0] = it;
+        a.result[1] = sqrt(true_rr / bnorm2);
+        a.result[2] = restarts;
+        a.result[3] = (sqrt(true_rr / bnorm2) <= a.rtol * 1.0000001) ? 0.0 : 1.0;
+    }
+}
+
 // persistent-solve state of a CsrProductOp (allocated on first use)
 struct PbState {
     double2* vec[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -330,11 +531,40 @@ struct PbState {
     unsigned int* bar = nullptr;
     double* result = nullptr;
     int grid = 0;
+    // resident variant (csr_product_bicgstab_resident_kernel): block size and shared-memory capacities, 0 = not usable
+    int res_threads = 0, res_capP = 0, res_capQ = 0;
+    size_t res_smem = 0;
     ~PbState() {
         for (auto p : vec) dev_free(p);
         dev_free(partials); dev_free(bar); dev_free(result);
     }
 };
+
+// Decides whether the resident kernel applies: one row of each factor per thread (<= kPrMaxThreads per CTA) and
+// the largest per-CTA slice of P plus Q within the shared memory of an SM.
+static int resident_plan(CsrProductOp& A, PbState& st) {
+    const int n = A.P.nrows, m = A.Q.nrows, grid = st.grid;
+    const int per = (std::max(n, m) + grid - 1) / grid;
+    const int T = std::max(64, ((per + 31) / 32) * 32);
+    if (T > kPrMaxThreads) return FDFD_OK;
+    std::vector<int32_t> ip(n + 1), iq(m + 1);
+    FDFD_CUDA(cudaMemcpy(ip.data(), A.P.indptr, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost));
+    FDFD_CUDA(cudaMemcpy(iq.data(), A.Q.indptr, sizeof(int32_t) * (m + 1), cudaMemcpyDeviceToHost));
+    int capP = 1, capQ = 1;
+    for (int b = 0; b < grid; ++b) {
+        const int64_t lo = (int64_t)b * T, hi = lo + T;
+        capP = std::max(capP, ip[(size_t)std::min<int64_t>(n, hi)] - ip[(size_t)std::min<int64_t>(n, lo)]);
+        capQ = std::max(capQ, iq[(size_t)std::min<int64_t>(m, hi)] - iq[(size_t)std::min<int64_t>(m, lo)]);
+    }
+    const size_t smem = (size_t)(capP + capQ) * (sizeof(double2) + sizeof(int32_t));
+    if (smem > ((size_t)200 << 10)) return FDFD_OK;
+    FDFD_CUDA(cudaFuncSetAttribute(csr_product_bicgstab_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    FDFD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_product_bicgstab_resident_kernel, T, smem));
+    if (per_sm < 1) return FDFD_OK;
+    st.res_threads = T; st.res_capP = capP; st.res_capQ = capQ; st.res_smem = smem;
+    return FDFD_OK;
+}
 
 int csr_product_bicgstab_persistent(CsrProductOp& A, PbState*& stp, const fdfd_krylov_opts& o, const double2* dinv,
                                     const double2* b, double2* x, SolveInfo& info, cudaStream_t st, bool* used) {
@@ -355,6 +585,7 @@ int csr_product_bicgstab_persistent(CsrProductOp& A, PbState*& stp, const fdfd_k
         FDFD_CUDA(dev_alloc(&stp->bar, 2 * sizeof(unsigned int)));
         FDFD_CUDA(cudaMemset(stp->bar, 0, 2 * sizeof(unsigned int)));
         FDFD_CUDA(dev_alloc(&stp->result, 4 * sizeof(double)));
+        FDFD_TRY(resident_plan(A, *stp));
     }
     PbArgs a;
     a.n = A.P.nrows; a.m = A.Q.nrows;
@@ -365,8 +596,15 @@ int csr_product_bicgstab_persistent(CsrProductOp& A, PbState*& stp, const fdfd_k
     a.r = stp->vec[0]; a.rh = stp->vec[1]; a.p = stp->vec[2]; a.v = stp->vec[3]; a.t = stp->vec[4];
     a.ph = stp->vec[5]; a.sh = stp->vec[6]; a.tmp = stp->vec[7];
     a.partials = stp->partials; a.bar = stp->bar; a.rtol = o.rtol; a.maxit = o.maxit; a.result = stp->result;
-    void* args[] = {&a};
-    FDFD_CUDA(cudaLaunchCooperativeKernel((const void*)csr_product_bicgstab_kernel, dim3(stp->grid), dim3(kPbThreads), args, 0, st));
+    const bool resident = stp->res_threads > 0 && getenv("FDFD_NO_RESIDENT_BICGSTAB") == nullptr;
+    if (resident) {
+        void* args[] = {&a, &stp->res_capP, &stp->res_capQ};
+        FDFD_CUDA(cudaLaunchCooperativeKernel((const void*)csr_product_bicgstab_resident_kernel, dim3(stp->grid),
+                                              dim3(stp->res_threads), args, stp->res_smem, st));
+    } else {
+        void* args[] = {&a};
+        FDFD_CUDA(cudaLaunchCooperativeKernel((const void*)csr_product_bicgstab_kernel, dim3(stp->grid), dim3(kPbThreads), args, 0, st));
+    }
     double res[4];
     FDFD_CUDA(cudaMemcpyAsync(res, stp->result, sizeof(res), cudaMemcpyDeviceToHost, st));
     FDFD_CUDA(cudaStreamSynchronize(st));
