@@ -324,6 +324,38 @@ class BandDiagramSolver2D:
                              "the spectrum and a cell that fits the shared-memory block factorisation")
         return ok
 
+    @staticmethod
+    def _projected_chunk(Hm, b, k, keep):
+        """Ritz pairs, residual estimates and the thick-restart basis of a stack of projected matrices."""
+        ncv = Hm.shape[-1]
+        mu, S = np.linalg.eig(Hm)
+        order = np.argsort(-np.abs(mu), axis=1)
+        mu = np.take_along_axis(mu, order, axis=1)
+        S = np.take_along_axis(S, order[:, None, :], axis=2)
+        S = S / np.linalg.norm(S, axis=1, keepdims=True)
+        res = np.abs(np.einsum("pc,pck->pk", b, S))
+        Sk = np.ascontiguousarray(S[:, :, :k].transpose(0, 2, 1))
+        Q, _ = np.linalg.qr(S[:, :, :keep])
+        Tn = np.zeros((Hm.shape[0], ncv + 1, ncv), dtype=np.complex128)
+        Tn[:, :keep, :keep] = np.conj(Q.transpose(0, 2, 1)) @ Hm @ Q
+        Tn[:, keep, :keep] = np.einsum("pc,pck->pk", b, Q)
+        return mu, res, Sk, np.ascontiguousarray(Q.transpose(0, 2, 1)), Tn
+
+    @classmethod
+    def _projected_problems(cls, Hm, b, k, keep, min_chunk=24):
+        """`_projected_chunk` over all active path points; the points are independent, so the stack is cut into
+        chunks that run on a thread pool (LAPACK releases the GIL) — the result does not depend on the cut."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        P = Hm.shape[0]
+        workers = max(1, min(8, (os.cpu_count() or 1), P // min_chunk))
+        if workers == 1:
+            return cls._projected_chunk(Hm, b, k, keep)
+        cuts = np.array_split(np.arange(P), workers)
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            parts = list(pool.map(lambda c: cls._projected_chunk(Hm[c], b[c], k, keep), cuts))
+        return tuple(np.concatenate([q[i] for q in parts], axis=0) for i in range(5))
+
     def _sweep_device(self, kind, A0, Mdev, beta_path, num_bands, sigma, tol, delta, pol, eigenvalues, frequencies,
                       info, max_restarts=100, seed=0):
         """All path points of one polarisation in lock-step on this library's own kernels (csrc/band.cu, C-ABI
@@ -372,22 +404,9 @@ class BandDiagramSolver2D:
                 # self-adjoint in the M inner product, so its Ritz vectors are well conditioned and the thick
                 # restart keeps the span of the `keep` dominant ones, orthonormalised by QR (the same subspace
                 # an ordered Schur form would keep): A (V Q) = (V Q)(Q^H H Q) + v (b Q).
-                Pa = len(active)
-                Hm, b = Hh[active, :ncv, :ncv], Hh[active, ncv, :ncv]
-                mu, S = np.linalg.eig(Hm)
-                order = np.argsort(-np.abs(mu), axis=1)
-                mu = np.take_along_axis(mu, order, axis=1)
-                S = np.take_along_axis(S, order[:, None, :], axis=2)
-                S = S / np.linalg.norm(S, axis=1, keepdims=True)
-                res = np.abs(np.einsum("pc,pck->pk", b, S))
+                mu, res, Sk, Qk, Tn = self._projected_problems(Hh[active, :ncv, :ncv], Hh[active, ncv, :ncv], k, keep)
                 done = np.all(res[:, :k] <= tol * np.abs(mu[:, :k]), axis=1) | (restarts >= max_restarts)
                 mus = mu[:, :k]
-                Sk = np.ascontiguousarray(S[:, :, :k].transpose(0, 2, 1))
-                Q, _ = np.linalg.qr(S[:, :, :keep])
-                Tn = np.zeros((Pa, ncv + 1, ncv), dtype=np.complex128)
-                Tn[:, :keep, :keep] = np.conj(Q.transpose(0, 2, 1)) @ Hm @ Q
-                Tn[:, keep, :keep] = np.einsum("pc,pck->pk", b, Q)
-                Qk = np.ascontiguousarray(Q.transpose(0, 2, 1))
                 t = lap("t_host_projected", t)
                 fin = np.flatnonzero(done)
                 if fin.size:

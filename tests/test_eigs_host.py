@@ -105,3 +105,26 @@ def test_probed_dense_assembly_matches_explicit_matrix(pol, shape, bc):
         assert StubOperator.applies == px * py <= Nx * Ny
     else:
         assert StubOperator.applies == Nx * Ny          # too short to colour: one apply per column
+
+
+def test_band_projected_problems_do_not_depend_on_the_thread_cut():
+    """BandDiagramSolver2D._projected_problems (thread pool over chunks of path points) equals the single stacked
+    call bit for bit, and its Ritz values / restart blocks satisfy the Krylov-Schur relations."""
+    from fdfd_b200.band_diagram import BandDiagramSolver2D as B
+    rng = np.random.default_rng(3)
+    P, ncv, k, keep = 100, 20, 5, 12
+    G = rng.standard_normal((P, ncv, ncv)) + 1j * rng.standard_normal((P, ncv, ncv))
+    Hm = G @ np.conj(G.transpose(0, 2, 1)) / ncv
+    b = rng.standard_normal((P, ncv)) + 1j * rng.standard_normal((P, ncv))
+    one = B._projected_chunk(Hm, b, k, keep)
+    many = B._projected_problems(Hm, b, k, keep, min_chunk=7)
+    assert all(np.array_equal(x, y) for x, y in zip(one, many))
+    mu, res, Sk, Qk, Tn = many
+    for p in (0, 57, 99):
+        assert np.allclose(np.sort(np.abs(mu[p]))[::-1], np.abs(mu[p]))                 # dominant first
+        for i in range(k):
+            assert np.linalg.norm(Hm[p] @ Sk[p, i] - mu[p, i] * Sk[p, i]) <= 1e-10 * abs(mu[p, i])
+        Q = Qk[p].T
+        assert np.allclose(Q.conj().T @ Q, np.eye(keep), atol=1e-12)
+        assert np.allclose(Tn[p, :keep, :keep], Q.conj().T @ Hm[p] @ Q, atol=1e-12)
+        assert np.allclose(Tn[p, keep, :keep], b[p] @ Q, atol=1e-12)
