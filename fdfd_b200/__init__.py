@@ -13,6 +13,7 @@ from .scattering import FDFD2DScatteringSolver  # noqa: F401
 from .band_diagram import BandDiagramSolver2D, BandStructureResult  # noqa: F401
 from .mode_solver_2d import ModeSolver2D  # noqa: F401
 from .periodic_solver_3d import PeriodicModeSolver3D  # noqa: F401
+from .periodic_solver_2d import PeriodicModeSolver2D  # noqa: F401
 from .eigs import refined_shift_invert_arnoldi  # noqa: F401
 from . import sweeps, stagger  # noqa: F401
 
@@ -23,4 +24,4 @@ def trim_memory():
     return int(_lib.lib().fdfd_trim_memory())
 
 __all__ = ["yeeder2d", "yeeder2d_device", "HelmholtzOperator2D", "SlabComm", "slab_rows",
-           "FDFD2DScatteringSolver", "BandDiagramSolver2D", "BandStructureResult", "ModeSolver2D", "PeriodicModeSolver3D", "refined_shift_invert_arnoldi", "sweeps", "stagger", "FdfdError", "NoConvergence", "trim_memory"]
+           "FDFD2DScatteringSolver", "BandDiagramSolver2D", "BandStructureResult", "ModeSolver2D", "PeriodicModeSolver3D", "PeriodicModeSolver2D", "refined_shift_invert_arnoldi", "sweeps", "stagger", "FdfdError", "NoConvergence", "trim_memory"]

@@ -293,7 +293,7 @@ class DenseShiftedSolver:
     densely — the GPU counterpart of the reference's SuperLU `splu`
     (refined_shift_invert_arnoldi.py:140-141) — and larger ones are refused loudly."""
 
-    def __init__(self, A, B, sigma, device, limit=45000):
+    def __init__(self, A, B, sigma, device, limit=45000, refine=True):
         import torch
         n = A.shape[0]
         if n > limit:
@@ -306,10 +306,19 @@ class DenseShiftedSolver:
         dense.index_put_(idx, torch.from_numpy(S.data.astype(np.complex128)).to(device), accumulate=True)
         self.LU, self.piv = torch.linalg.lu_factor(dense)
         del dense
+        from .operators import CsrOperator
+        self.S = CsrOperator((A - sigma * B).tocsr(), device=device) if refine else None
 
-    def __call__(self, r):
+    def _lu(self, r):
         import torch
         return torch.linalg.lu_solve(self.LU, self.piv, r.reshape(-1, 1)).reshape(-1)
+
+    def __call__(self, r):
+        r = r.reshape(-1)
+        x = self._lu(r)
+        if self.S is not None:             # one step of iterative refinement against the sparse matrix itself
+            x = x + self._lu(r - self.S.apply(x))
+        return x
 
 
 class PlaneBlockShiftedSolver:
@@ -416,6 +425,22 @@ class PlaneBlockShiftedSolver:
         if self.S is not None:
             x = x + self._sweep(r - self.S.apply(x))
         return x
+
+
+def ruiz_equilibrate(M, iterations=8):
+    """Row / column scalings (dr, dc) that bring the largest magnitude of every row and column of the sparse matrix
+    M to ~1 (Ruiz' iteration: divide by the square roots of the row / column maxima).  Host, O(nnz) per sweep."""
+    import scipy.sparse as sp
+    M = abs(M).tocsr()
+    n, m = M.shape
+    dr, dc = np.ones(n), np.ones(m)
+    for _ in range(int(iterations)):
+        S = sp.diags(dr) @ M @ sp.diags(dc)
+        r = np.sqrt(np.asarray(S.max(axis=1).todense()).ravel())
+        c = np.sqrt(np.asarray(S.max(axis=0).todense()).ravel())
+        dr /= np.where(r > 0, r, 1.0)
+        dc /= np.where(c > 0, c, 1.0)
+    return dr, dc
 
 
 def make_shifted_solver(A, B, sigma, device, *, dense_limit=45000, planes=None, nplanes=None, block_min=4000):

@@ -292,7 +292,68 @@ def periodic3d_fixture():
     np.savez_compressed(os.path.join(HERE, "periodic3d_golden.npz"), **out)
 
 
+def periodic2d_cases():
+    """Problem definitions of the 2-D periodic solver shared by the fixture generator and the tests."""
+    def antenna(cls):        # Periodic_Solver_2D/example_surface_wave_antenna.py:3-22 verbatim (TM, 200 x 80, n = 32 000)
+        s = cls("TM", freq=20e9, x_range=10e-3, z_range=8e-3, Nx=200, Nz=80, num_modes=8, guess=0, mode_filter=False)
+        s.add_pec((2.27e-3, 2.28e-3), (1.0e-3, 2.0e-3))
+        s.add_pec((0.9e-3, 1.0e-3), (0, 80))
+        s.add_rectangle(10.2, 1, (1.0e-3, 2.27e-3), (0, 80), subpixels=16)
+        s.add_pml(pml_width=50, n=3, sigma_max=5, direction="x+")
+        return s
+
+    def slab_te(cls):        # TE modes of a dielectric slab on a PEC-like ground with a PMC-like strip; both PMLs
+        s = cls("TE", freq=30e9, x_range=6e-3, z_range=4e-3, Nx=60, Nz=16, num_modes=4, guess=0)
+        s.add_pec((0, 3), (0, 16))
+        s.add_rectangle((9.8, 9.8, 6.0), 1, (0.3e-3, 1.7e-3), (0, 16), subpixels=8)
+        s.add_pmc((30, 32), (4, 9), components=("xx", "zz"))
+        s.add_pml(pml_width=15, n=3, sigma_max=4, direction="x+")
+        s.guess = (-0.08 + 0.87j) * s.k0          # next to the one pair ARPACK converges here (neff = -0.0811 + 0.8712j)
+        return s
+
+    def grating_tm(cls):     # TM, periodic dielectric teeth (z-dependent cell), small: dense shifted solve
+        s = cls("TM", freq=25e9, x_range=5e-3, z_range=3e-3, Nx=40, Nz=12, num_modes=4, guess=0)
+        s.add_pec((0, 2), (0, 12))
+        s.add_rectangle(6.15, 1, (0.2e-3, 1.2e-3), (0, 12), subpixels=8)
+        s.add_rectangle(6.15, 1, (1.2e-3, 1.7e-3), (0.4e-3, 1.6e-3), subpixels=8)
+        s.add_pml(pml_width=12, n=3, sigma_max=5, direction="x+")
+        s.guess = (-0.02 + 1.39j) * s.k0          # next to neff = -0.0183 + 1.3869j
+        return s
+    return dict(antenna=antenna, slab_te=slab_te, grating_tm=grating_tm)
+
+
+def periodic2d_fixture():
+    """Eigenvalues of the unmodified reference with the relative residual of every returned pair in its own pencil:
+    the parity tests compare the pairs ARPACK actually converged (see scripts/periodic2d_reproducibility.py)."""
+    from oracle import periodic2d_oracle as po
+    mod = ref_loader.load("Periodic_Solver_2D")
+    out = {}
+    for name, build in periodic2d_cases().items():
+        s = build(mod.PeriodicModeSolver2D)
+        s.solve()
+        m = s._effective_materials_and_masks()
+        A, B = (s._build_tm_system(m[0], m[2], m[4]) if s.polarization == "TM" else s._build_te_system(m[1], m[3], m[5]))
+        free = s._free_mask(m[6], m[7], m[9], m[10])
+        A, B = A[free, :][:, free], B[free, :][:, free]
+        out[f"{name}_eigenvalues"] = s.eigenvalues
+        out[f"{name}_neff"] = s.neff
+        out[f"{name}_residuals"] = po.relative_residuals(A, B, s.eigenvalues, s.eigenvectors[free, :])
+        conv = np.flatnonzero(out[f"{name}_residuals"] <= 1e-9)
+        out[f"{name}_converged"] = conv
+        first, second = ("Ex", "Hy") if s.polarization == "TM" else ("Hx", "Ey")
+        for fld in (first, second):                      # decimated fields of the converged pairs only
+            arr = getattr(s, fld)
+            shape = getattr(s, "shape_" + fld.lower())
+            out[f"{name}_{fld}_dec"] = np.array([arr[:, k].reshape(shape, order="F")[::3, ::2] for k in conv])
+    np.savez_compressed(os.path.join(HERE, "periodic2d_golden.npz"), **out)
+    for name in periodic2d_cases():
+        print(name, out[f"{name}_eigenvalues"], out[f"{name}_residuals"])
+
+
 if __name__ == "__main__":
+    if "--p2d-only" in sys.argv:
+        periodic2d_fixture()
+        sys.exit(0)
     if "--scatter-1024" in sys.argv:
         scatter_1024()
         sys.exit(0)
@@ -315,6 +376,7 @@ if __name__ == "__main__":
     band_fixture()
     mode_fixture()
     periodic3d_fixture()
+    periodic2d_fixture()
     scatter_small()
     scatter_cfg1()
     for f in sorted(os.listdir(HERE)):

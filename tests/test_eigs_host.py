@@ -128,3 +128,17 @@ def test_band_projected_problems_do_not_depend_on_the_thread_cut():
         assert np.allclose(Q.conj().T @ Q, np.eye(keep), atol=1e-12)
         assert np.allclose(Tn[p, :keep, :keep], Q.conj().T @ Hm[p] @ Q, atol=1e-12)
         assert np.allclose(Tn[p, keep, :keep], b[p] @ Q, atol=1e-12)
+
+
+def test_ruiz_equilibrate_scales_rows_and_columns_to_one():
+    import scipy.sparse as sp
+    from fdfd_b200 import eigs
+    rng = np.random.default_rng(5)
+    n = 300
+    M = sp.random(n, n, density=0.02, random_state=5, format="csr") + sp.identity(n)
+    M = sp.diags(10.0 ** rng.uniform(-6, 6, n)) @ M @ sp.diags(10.0 ** rng.uniform(-6, 6, n))     # 24 decades of scale
+    dr, dc = eigs.ruiz_equilibrate(M, iterations=12)
+    S = abs(sp.diags(dr) @ M @ sp.diags(dc)).tocsr()
+    rmax, cmax = np.asarray(S.max(axis=1).todense()).ravel(), np.asarray(S.max(axis=0).todense()).ravel()
+    assert np.all(np.abs(rmax - 1) <= 0.05) and np.all(np.abs(cmax - 1) <= 0.05)
+    assert np.all(dr > 0) and np.all(dc > 0)

@@ -1,6 +1,7 @@
 """CPU tests: the oracle against the committed golden vectors (generated from the unmodified
 reference by tests/golden/make_golden.py) and the known-answer values of SURVEY.md §8c."""
 import numpy as np
+import pytest
 import scipy.sparse as sp
 
 from oracle import scattering_oracle as so, yee_oracle
@@ -88,3 +89,27 @@ def test_band_golden(golden):
         ref = g[f"sq_ev_{pol}"][:, [1, 3]]
         assert np.max(np.abs(o[pol][0] - ref)) <= 1e-9 * np.abs(ref).max()
     assert np.allclose(o["TM"][1][:, 0], [0.1161753797, 0.2956241914, 0.3903181775, 0.3991116489, 0.4862472813], atol=1e-9)
+
+
+@pytest.mark.parametrize("case", ["antenna", "slab_te", "grating_tm"])
+def test_periodic2d_oracle_golden(golden, case):
+    """oracle/periodic2d_oracle.py (operators, averaging, pencil, eigs call) on the cell tensors of the drop-in
+    class reproduces the pairs the reference converged (relative residual <= 1e-9 in its own pencil)."""
+    import importlib.util
+    import os
+    import fdfd_b200
+    from oracle import periodic2d_oracle as po
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    s = m.periodic2d_cases()[case](fdfd_b200.PeriodicModeSolver2D)
+    g = golden("periodic2d_golden.npz")
+    cell = {f"{p}_{c}": getattr(s, f"cell_{p}_r_{c}") for p in ("eps", "mu") for c in ("xx", "yy", "zz")}
+    mats = po.materials_on_fields(cell, s.material_no_average_mask)
+    lam, X, res = po.solve(s.polarization, mats, s.Nx, s.Nz, s.dx, s.dz, s.omega, s.num_modes, s.guess)
+    conv = g[f"{case}_converged"]
+    assert conv.size >= 1
+    for k in conv:
+        ref = g[f"{case}_eigenvalues"][k]
+        j = int(np.argmin(np.abs(lam - ref)))
+        assert abs(lam[j] - ref) <= 1e-8 * abs(ref) and res[j] <= 1e-9

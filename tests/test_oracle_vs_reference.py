@@ -194,6 +194,66 @@ def test_periodic3d_host_logic_and_oracle(case):
     assert rs == ref.refined_restarts and np.allclose(res, ref.refined_residuals, rtol=1e-6)
 
 
+def _p2d_cases():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.periodic2d_cases()
+
+
+@pytest.mark.parametrize("case", ["antenna", "slab_te", "grating_tm"])
+def test_periodic2d_host_logic_and_oracle(case):
+    """Drop-in 2-D periodic class: cell tensors, field-location materials, masks, the twelve operators and the
+    pencil (A, B, free mask) are bit-identical to the reference's; error behaviour of the region helpers too."""
+    import fdfd_b200
+    from oracle import periodic2d_oracle as po
+    build = _p2d_cases()[case]
+    ref = build(ref_loader.load("Periodic_Solver_2D").PeriodicModeSolver2D)
+    mine = build(fdfd_b200.PeriodicModeSolver2D)
+    assert mine.k0 == ref.k0 and mine.guess == ref.guess and mine.shape_ez == ref.shape_ez
+    comps = [f"{p}_r_{c}" for p in ("eps", "mu") for c in ("xx", "yy", "zz")]
+    for n in comps:
+        assert np.array_equal(getattr(ref, "cell_" + n), getattr(mine, "cell_" + n)), n
+        assert np.array_equal(getattr(ref, n), getattr(mine, n)), n
+    assert np.array_equal(ref.material_no_average_mask, mine.material_no_average_mask)
+    assert ref._pec_regions == mine._pec_regions and ref._pmc_regions == mine._pmc_regions
+    D = po.operators(ref.Nx, ref.Nz, ref.dx, ref.dz)
+    for name in fdfd_b200.PeriodicModeSolver2D._OPERATORS:
+        r, other = getattr(ref, name), D[name]          # the product's GPU-assembled operators: tests/test_periodic2d_gpu.py
+        assert r.shape == other.shape and r.format == other.format, name
+        assert r.indptr.tobytes() == other.indptr.tobytes() and r.indices.tobytes() == other.indices.tobytes(), name
+        assert r.data.tobytes() == other.data.tobytes(), name
+        setattr(mine, name, other)                      # stand in for the GPU assembly on this CPU box
+    mr, mm = ref._effective_materials_and_masks(), mine._effective_materials_and_masks()
+    assert len(mr) == len(mm) == 12
+    for a, b in zip(mr, mm):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    if ref.polarization == "TM":
+        Ar, Br = ref._build_tm_system(mr[0], mr[2], mr[4])
+    else:
+        Ar, Br = ref._build_te_system(mr[1], mr[3], mr[5])
+    free = ref._free_mask(mr[6], mr[7], mr[9], mr[10])
+    Am, Bm, fm = mine._pencil()
+    assert np.array_equal(free, fm)
+    Ar, Br = Ar[free, :][:, free], Br[free, :][:, free]
+    assert (Ar != Am).nnz == 0 and (Br != Bm).nnz == 0
+    cell = {f"{p}_{c}": getattr(ref, f"cell_{p}_r_{c}") for p in ("eps", "mu") for c in ("xx", "yy", "zz")}
+    Ao, Bo = po.pencil(ref.polarization, po.materials_on_fields(cell, ref.material_no_average_mask), D, ref.omega)
+    assert (Ao[free, :][:, free] != Ar).nnz == 0 and (Bo[free, :][:, free] != Br).nnz == 0
+    assert np.array_equal(mine._unknown_planes().shape, free.shape)
+    for bad in (lambda s: s.add_rectangle(2, 1, (0.0, 1.0), (0, 4)), lambda s: s.add_pec((5, 5), (0, 4)),
+                lambda s: s.add_pmc((0, 2), (0, 3), components=("xy",)), lambda s: s.add_pml(direction="z"),
+                lambda s: s.add_rectangle(2, 1, (0, 4), (0, 4), subpixels=0), lambda s: s.add_pec("ab", (0, 4))):
+        msgs = []
+        for obj in (ref, mine):
+            with pytest.raises(ValueError) as e:
+                bad(obj)
+            msgs.append(str(e.value))
+        assert msgs[0] == msgs[1]
+
+
 @pytest.mark.parametrize("N,pw,direction", [(120, 20, "both"), (97, 11, "x"), (64, 9, "y"), (40, 20, "both")])
 def test_scattering_dropin_host_arrays_bitwise(N, pw, direction):
     """Host side of the drop-in class (frame-only UPML scaling, broadcast grid, lazy identity mask) against
