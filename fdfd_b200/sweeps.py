@@ -105,3 +105,27 @@ def periodic_3d_dispersion(frequencies, build, guess_func=None, solve_kwargs=Non
             rec["error"] = str(exc)
         out.append(rec)
     return gather_replicas(out)
+
+
+def periodic_2d_dispersion(frequencies, build, num_modes, guess_func=None):
+    """The frequency loop of Periodic_2D_Dispersion.py:20-54: ``build(freq, guess)`` returns a configured
+    PeriodicModeSolver2D (the reference passes ``guess_func(f)``, 0 by default); per frequency the table row
+    ``{"Frequency (Hz)", "Alpha_Mode_m", "Beta_Mode_m"}`` with alpha = Re(neff), beta = Im(neff), NaN where the solve
+    failed (the reference prints a warning and carries on).  Frequencies are distributed over the ranks."""
+    frequencies = np.asarray(frequencies, dtype=float)
+    lo, hi = replica_slice(len(frequencies))
+    rows = []
+    for f in frequencies[lo:hi]:
+        row = {"Frequency (Hz)": float(f)}
+        try:
+            s = build(float(f), guess_func(f) if guess_func else 0)
+            s.solve()
+            neff = [complex(s.neff[m]) for m in range(num_modes)]
+        except Exception as exc:  # noqa: BLE001
+            row["error"] = str(exc)
+            neff = [complex(np.nan, np.nan)] * num_modes
+        for m in range(num_modes):
+            row[f"Alpha_Mode_{m + 1}"] = neff[m].real
+            row[f"Beta_Mode_{m + 1}"] = neff[m].imag
+        rows.append(row)
+    return gather_replicas(rows)

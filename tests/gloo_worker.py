@@ -74,6 +74,18 @@ def main():
     assert [r["frequency"] for r in recs] == [21e9, 22e9, 23e9, 24e9, 25e9] and "error" in recs[2]
     # a chain starts from guess_func and continues with last_gamma * k0
     assert recs[0]["sigma_guess"] == -1j
+
+    class Fake2DPeriodic:
+        def __init__(self, f, guess):
+            self.f, self.guess = f, guess
+        def solve(self):
+            if self.f == 18e9:
+                raise RuntimeError("no shifts could be applied")
+            self.neff = np.array([0.1 + 1j * self.f * 1e-10, -0.1 - 1j * self.f * 1e-10, 0.3 + 0.2j])
+    rows = sweeps.periodic_2d_dispersion(np.arange(16e9, 21e9, 1e9), Fake2DPeriodic, 2, guess_func=lambda f: 0)
+    assert [r["Frequency (Hz)"] for r in rows] == [16e9, 17e9, 18e9, 19e9, 20e9]
+    assert np.isnan(rows[2]["Alpha_Mode_1"]) and "error" in rows[2] and abs(rows[4]["Beta_Mode_1"] - 2.0) < 1e-9
+    assert rows[0]["Alpha_Mode_2"] == -0.1 and "Alpha_Mode_3" not in rows[0]
     dist.destroy_process_group()
     if rank == 0:
         print("GLOO_OK nccl_id=%d" % okt.item(), flush=True)
