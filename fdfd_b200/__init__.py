@@ -4,6 +4,8 @@ Public surface (names as in SolverNotConverging/FDFD):
     yeeder2d(NS, RES, BC, kinc=None)          GPU assembly of the Yee derivative operators
     FDFD2DScatteringSolver                    2-D TEz/TMz scattering, matrix-free GPU Krylov solve
     BandDiagramSolver2D                       photonic band structure, GPU Krylov-Schur shift-invert
+    ModeSolver2D, PeriodicModeSolver2D,
+    PeriodicModeSolver3D                      waveguide / periodic-cell eigenmodes, GPU shift-invert Arnoldi
     HelmholtzOperator2D                       the matrix-free operator + solver handle
 """
 from ._lib import FdfdError, NoConvergence, LIB_PATH  # noqa: F401

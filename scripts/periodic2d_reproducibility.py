@@ -1,9 +1,9 @@
-"""Evidence for DESIGN.md §8 ("PeriodicModeSolver2D is not built"): on its shipped example
+"""Evidence for DESIGN.md §8 (why parity of `PeriodicModeSolver2D` is asserted on converged pairs only): on its shipped example
 (Periodic_Solver_2D/example_surface_wave_antenna.py: 200 x 80, TM, `eigs(A, M=B, k=8, sigma=0, v0=ones)`,
 Periodic_Solver_2D.py:523-566) most of the values the UNMODIFIED reference returns are not eigenvalues of its
 own pencil: their relative residuals ||A x - lambda B x|| / (||A x|| + |lambda| ||B x||) are 1e-5 ... 3e-2, and
 they move when only the ARPACK start vector or the subspace size changes.  There is no reproducible answer to
-be bit- or 1e-8-identical to beyond the first +- pair.
+be bit- or 1e-8-identical to beyond the first +- pair (fdfd_b200.PeriodicModeSolver2D returns eight converged pairs).
 
 Runs in the build container only (needs /root/reference):   python scripts/periodic2d_reproducibility.py
 """
