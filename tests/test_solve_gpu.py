@@ -199,3 +199,32 @@ def test_compressed_krylov_basis(pol):
     ref = so.solve_total_field(so.cylinder_problem(N, eps_r=-1e6, pml_width=20, mask=40), pol)
     assert np.linalg.norm(F - ref) <= 1e-6 * np.linalg.norm(ref)
     assert its[1] <= 1.15 * its[0] + 3
+
+
+@pytest.mark.parametrize("pol", ["TE", "TM"])
+@pytest.mark.parametrize("Nx,Ny,er,angle", [(260, 180, 4.0 - 0.2j, 20.0), (150, 310, -1e6, 70.0)])
+def test_scattering_rectangular_grids_default_options(Nx, Ny, er, angle, pol):
+    """Non-square grids (dx != dy, more rows than columns and vice versa), lossy dielectric and metal-like
+    scatterers, oblique incidence: the drop-in class with its DEFAULT options (polarisation-dependent restart /
+    shift, residual tolerance derived from the 1e-6 field bar) against the oracle's direct solve."""
+    import fdfd_b200
+    f0 = 10e9
+    lam = 299792458 / f0
+    Lx, Ly = Nx / 45 * lam, Ny / 55 * lam
+    sim = fdfd_b200.FDFD2DScatteringSolver(f0, Lx, Ly, Nx, Ny)
+    p = so.make_problem(f0, Lx, Ly, Nx, Ny)
+    inside = ((sim.X / (0.9 * lam)) ** 2 + (sim.Y / (0.5 * lam)) ** 2) <= 1.0
+    sim.add_object(er, 1.0, inside)
+    so.add_object(p, er, 1.0, np.broadcast_to(inside, (Ny, Nx)))
+    sim.add_UPML(pml_width=30, sigma_max=8)
+    so.add_upml(p, pml_width=30, sigma_max=8)
+    sim.add_mask(55)
+    so.add_mask(p, 55)
+    sim.add_source("plane_wave", angle_deg=angle, polarization="TE")
+    so.add_source(p, "plane_wave", angle_deg=angle, polarization="TE")
+    F = getattr(sim, "solve_total_field_" + pol)()
+    ref = so.solve_total_field(p, pol)
+    info = sim.solver_info[pol]
+    assert info["converged"] and info["relres"] <= info["rtol"] <= 1e-8
+    assert F.shape == (Ny, Nx)
+    assert np.linalg.norm(F - ref.reshape(Ny, Nx)) <= 1e-6 * np.linalg.norm(ref)
