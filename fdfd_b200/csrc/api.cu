@@ -43,7 +43,7 @@ struct fdfd_helm2d {
 struct fdfd_comm { Comm* c; };
 
 extern "C" const char* fdfd_last_error(void) { return g_err; }
-extern "C" int fdfd_version(void) { return 100; }
+extern "C" int fdfd_version(void) { return 200; }   // 200: round-2 ABI (options struct without lgmres_k, band / stagger / tsqr / scatter_fill entry points)
 extern "C" int fdfd_krylov_opts_size(void) { return (int)sizeof(fdfd_krylov_opts); }
 extern "C" int fdfd_device_count(void) {
     int n = 0;

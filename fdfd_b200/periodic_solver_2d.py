@@ -378,10 +378,16 @@ class PeriodicModeSolver2D:
                                                          ncv=ncv, tol=max(float(tol or 0.0), 1e-12), v0=v0, device=dev)
         order = np.argsort(np.abs(lam - guess))
         lam = lam[order]
+        # relative residual of every pair in the reference's (unscaled) pencil, on the device:
+        # A x = Dr^-1 (A' x'), B x = Dr^-1 (B' x') for x = Dc x'
+        inv_dr = torch.from_numpy(1.0 / dr).to(dev)
+        resid = np.zeros(len(lam))
+        for pos, i in enumerate(order):
+            ax, bx = Ad.apply(X[i]) * inv_dr, Bd.apply(X[i]) * inv_dr
+            den = float(torch.linalg.vector_norm(ax)) + abs(lam[pos]) * float(torch.linalg.vector_norm(bx))
+            resid[pos] = float(torch.linalg.vector_norm(ax - complex(lam[pos]) * bx)) / den if den > 0 else 0.0
         X = X.T.cpu().numpy()[:, order] * dc[:, None]                       # back to the reference's variables
         X /= np.linalg.norm(X, axis=0, keepdims=True)
-        resid = np.array([np.linalg.norm(A @ X[:, i] - lam[i] * (B @ X[:, i])) /
-                          (np.linalg.norm(A @ X[:, i]) + abs(lam[i]) * np.linalg.norm(B @ X[:, i])) for i in range(len(lam))])
         self.solver_info = dict(residuals=resid, balanced_residuals=res[order], restarts=restarts, n=int(A.shape[0]), sigma=guess)
         eigenvectors = np.zeros((free.size, self.num_modes), dtype=complex)
         eigenvectors[free, :] = X
